@@ -1,0 +1,312 @@
+"""ctypes binding of libemu_b200.so (the C ABI in include/emu_b200.h).
+
+There is no CPU fallback: importing this module only loads the library; every compute entry point needs a
+CUDA device and raises :class:`EmuError` otherwise.  If the shared library is missing the import fails loudly.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libemu_b200.so")
+
+EMU_OK = 0
+ERRORS = {-1: "EMU_ERR_INVALID", -2: "EMU_ERR_CUDA", -3: "EMU_ERR_NOMEM", -4: "EMU_ERR_STATE",
+          -5: "EMU_ERR_UNSUPPORTED", -6: "EMU_ERR_NCCL"}
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_SWIGLU, EPI_GEGLU = 0, 1, 2, 3
+
+
+class EmuError(RuntimeError):
+    pass
+
+
+class EmuConfig(C.Structure):
+    _fields_ = [
+        ("llm_hidden", C.c_int), ("llm_layers", C.c_int), ("llm_heads", C.c_int), ("llm_head_dim", C.c_int),
+        ("llm_ffn", C.c_int), ("llm_vocab", C.c_int),
+        ("llm_rms_eps", C.c_float), ("llm_rope_theta", C.c_float),
+        ("llm_max_batch", C.c_int), ("llm_max_seq", C.c_int),
+        ("vit_image", C.c_int), ("vit_patch", C.c_int), ("vit_width", C.c_int), ("vit_layers", C.c_int),
+        ("vit_heads", C.c_int), ("vit_mlp", C.c_int),
+        ("vit_ln_eps", C.c_float), ("vit_postnorm", C.c_int), ("vit_final_ln", C.c_int), ("vit_max_batch", C.c_int),
+        ("cf_layers", C.c_int), ("cf_dim", C.c_int), ("cf_heads", C.c_int), ("cf_ffn", C.c_int),
+        ("cf_queries", C.c_int), ("cf_enc_width", C.c_int), ("cf_out_dim", C.c_int), ("cf_buckets", C.c_int),
+        ("cf_max_distance", C.c_int),
+        ("reserved", C.c_int * 8),
+    ]
+
+
+class EmuUNetConfig(C.Structure):
+    _fields_ = [
+        ("in_channels", C.c_int), ("out_channels", C.c_int), ("n_blocks", C.c_int),
+        ("block_out_channels", C.c_int * 4), ("layers_per_block", C.c_int), ("transformer_layers", C.c_int * 4),
+        ("head_dim", C.c_int), ("cross_attention_dim", C.c_int), ("use_linear_projection", C.c_int),
+        ("addition_time_embed_dim", C.c_int), ("projection_class_embeddings_input_dim", C.c_int),
+        ("norm_groups", C.c_int), ("norm_eps", C.c_float),
+    ]
+
+
+class EmuVAEConfig(C.Structure):
+    _fields_ = [
+        ("latent_channels", C.c_int), ("out_channels", C.c_int), ("n_blocks", C.c_int),
+        ("block_out_channels", C.c_int * 4), ("layers_per_block", C.c_int), ("norm_groups", C.c_int),
+    ]
+
+
+# every symbol declared in include/emu_b200.h (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_engine_load_tensor",
+    "emu_vit_forward", "emu_llm_reset", "emu_llm_embed", "emu_llm_prefill", "emu_llm_decode", "emu_llm_cur_len",
+    "emu_project", "emu_cformer_forward", "emu_unet_configure", "emu_unet_forward", "emu_denoise_step",
+    "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
+    "emu_op_attn_prefill", "emu_op_attn_decode", "emu_op_rmsnorm", "emu_op_layernorm", "emu_launch_count",
+    "emu_version",
+]
+
+_lib = None
+
+
+def load():
+    """Load libemu_b200.so; raise if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EmuError("libemu_b200.so not found at %s — run `python -m emu_b200.build` (needs nvcc)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib.emu_last_error.restype = C.c_char_p
+    lib.emu_last_error.argtypes = [C.c_void_p]
+    lib.emu_version.restype = C.c_char_p
+    lib.emu_launch_count.restype = C.c_uint64
+    lib.emu_engine_destroy.restype = None
+    lib.emu_engine_destroy.argtypes = [C.c_void_p]
+    lib.emu_engine_create.argtypes = [C.POINTER(EmuConfig), C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    assert t.is_cuda, "engine arguments must be CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(rc, engine=None):
+    if rc == EMU_OK:
+        return
+    msg = ERRORS.get(rc, str(rc))
+    if engine is not None:
+        detail = load().emu_last_error(engine)
+        if detail:
+            msg += ": " + detail.decode()
+    raise EmuError(msg)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise EmuError("emu_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+
+
+_DT = {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16, torch.float16: DTYPE_F16}
+
+
+class Engine:
+    """Thin RAII wrapper over EmuEngine*; methods map 1:1 to the C ABI."""
+
+    def __init__(self, cfg: EmuConfig, tp_rank=0, tp_size=1, nccl_uid: bytes = None):
+        require_cuda()
+        self.lib = load()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        uid = C.create_string_buffer(nccl_uid, 128) if nccl_uid is not None else None
+        rc = self.lib.emu_engine_create(C.byref(cfg), tp_rank, tp_size, uid, C.byref(self.h))
+        check(rc)
+        self.tp_rank, self.tp_size = tp_rank, tp_size
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.emu_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights ----
+    def load_tensor(self, key: str, t: torch.Tensor):
+        t = t.detach()
+        if not t.is_contiguous():
+            t = t.contiguous()
+        if t.dtype not in _DT:
+            t = t.float()
+        shape = (C.c_int64 * max(t.dim(), 1))(*([int(s) for s in t.shape] or [1]))
+        src = C.c_void_p(t.data_ptr())
+        rc = self.lib.emu_engine_load_tensor(self.h, key.encode(), src, _DT[t.dtype], shape, max(t.dim(), 1), _stream())
+        check(rc, self.h)
+
+    def load_state_dict(self, sd, prefix=""):
+        for k, v in sd.items():
+            if k.endswith("rotary_emb.inv_freq"):
+                continue
+            self.load_tensor(prefix + k, v)
+
+    # ---- ViT ----
+    def vit_forward(self, image: torch.Tensor, n_query: int, pool=True):
+        c = self.cfg
+        B = image.shape[0]
+        image = image.to(torch.bfloat16).contiguous()
+        G = c.vit_image // c.vit_patch
+        if pool:
+            out = torch.empty(B, n_query, c.vit_width, dtype=torch.bfloat16, device=image.device)
+        else:
+            out = torch.empty(B, G * G + 1, c.vit_width, dtype=torch.bfloat16, device=image.device)
+        check(self.lib.emu_vit_forward(self.h, _ptr(image), B, _ptr(out), n_query, 1 if pool else 0, _stream()), self.h)
+        return out
+
+    # ---- LLM ----
+    def llm_reset(self):
+        check(self.lib.emu_llm_reset(self.h, _stream()), self.h)
+
+    def llm_embed(self, ids: torch.Tensor):
+        ids32 = ids.to(torch.int32).contiguous()
+        out = torch.empty(*ids.shape, self.cfg.llm_hidden, dtype=torch.bfloat16, device=ids.device)
+        check(self.lib.emu_llm_embed(self.h, _ptr(ids32), ids32.numel(), _ptr(out), _stream()), self.h)
+        return out
+
+    def llm_prefill(self, embeds, attention_mask=None, hf_positions=True, want_hidden=False, want_logits=True):
+        B, N, H = embeds.shape
+        embeds = embeds.to(torch.bfloat16).contiguous()
+        mask = attention_mask.to(torch.int32).contiguous() if attention_mask is not None else None
+        hidden = torch.empty(B, N, H, dtype=torch.bfloat16, device=embeds.device) if want_hidden else None
+        logits = torch.empty(B, self.cfg.llm_vocab, dtype=torch.float32, device=embeds.device) if want_logits else None
+        check(self.lib.emu_llm_prefill(self.h, _ptr(embeds), _ptr(mask), B, N, 1 if hf_positions else 0, _ptr(hidden),
+                                       _ptr(logits), _stream()), self.h)
+        return hidden, logits
+
+    def llm_decode(self, token_ids=None, embeds=None, beam_src=None, logits=None, hidden=None, next_ids=None,
+                   ban_id=-1, B=None):
+        if B is None:
+            B = token_ids.shape[0] if token_ids is not None else embeds.shape[0]
+        check(self.lib.emu_llm_decode(self.h, _ptr(token_ids), _ptr(embeds), _ptr(beam_src), B, _ptr(logits),
+                                      _ptr(hidden), _ptr(next_ids), ban_id, _stream()), self.h)
+
+    def cur_len(self):
+        return self.lib.emu_llm_cur_len(self.h)
+
+    def project(self, which: int, x: torch.Tensor, out_dim: int):
+        x2 = x.reshape(-1, x.shape[-1]).to(torch.bfloat16).contiguous()
+        y = torch.empty(x2.shape[0], out_dim, dtype=torch.bfloat16, device=x.device)
+        check(self.lib.emu_project(self.h, which, _ptr(x2), x2.shape[0], _ptr(y), _stream()), self.h)
+        return y.reshape(*x.shape[:-1], out_dim)
+
+
+# ---- stand-alone operators (used by tests and micro-benchmarks) ----
+def op_gemm(A, W, bias=None, residual=None, epi=EPI_NONE, out_fp32=False, force_bn=0):
+    require_cuda()
+    lib = load()
+    M, K = A.shape
+    N = W.shape[0]
+    n_out = N // 2 if epi in (EPI_SWIGLU, EPI_GEGLU) else N
+    Cm = torch.empty(M, n_out, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=A.device)
+    rc = lib.emu_op_gemm(_ptr(A), A.stride(0), _ptr(W), W.stride(0), M, N, K, _ptr(bias), _ptr(residual),
+                         residual.stride(0) if residual is not None else 0, epi, _ptr(Cm), n_out,
+                         1 if out_fp32 else 0, force_bn, _stream())
+    check(rc)
+    return Cm
+
+
+def op_conv3x3(x_nhwc, w_k, bias=None, residual=None):
+    require_cuda()
+    lib = load()
+    NB, H, W_, Cin = x_nhwc.shape
+    Cout = w_k.shape[0]
+    y = torch.empty(NB, H, W_, Cout, dtype=torch.bfloat16, device=x_nhwc.device)
+    check(lib.emu_op_conv3x3(_ptr(x_nhwc), NB, H, W_, Cin, _ptr(w_k), Cout, _ptr(bias), _ptr(residual), _ptr(y),
+                             _stream()))
+    return y
+
+
+def op_gemv(W, x, norm_w=None, eps=1e-6, mode=EPI_NONE, bias=None, residual=None, out_fp32=False, pdl=False):
+    require_cuda()
+    lib = load()
+    N, K = W.shape
+    B = x.shape[0]
+    n_out = N // 2 if mode == EPI_SWIGLU else N
+    y = torch.empty(B, n_out, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
+    rc = lib.emu_op_gemv(_ptr(W), N, K, _ptr(x), x.stride(0), B, _ptr(norm_w), C.c_float(eps), mode, _ptr(bias),
+                         _ptr(residual), residual.stride(0) if residual is not None else 0, _ptr(y), n_out,
+                         1 if out_fp32 else 0, 1 if pdl else 0, _stream())
+    check(rc)
+    return y
+
+
+def op_gemv_rope_qkv(W, n_heads, head_dim, x, norm_w, eps, rope_cos, rope_sin, pos, pos_off, k_cache, v_cache, t_max):
+    require_cuda()
+    lib = load()
+    B = x.shape[0]
+    q = torch.empty(B, n_heads * head_dim, dtype=torch.bfloat16, device=x.device)
+    rc = lib.emu_op_gemv_rope_qkv(_ptr(W), n_heads, head_dim, W.shape[1], _ptr(x), x.stride(0), B, _ptr(norm_w),
+                                  C.c_float(eps), _ptr(rope_cos), _ptr(rope_sin), _ptr(pos), _ptr(pos_off), _ptr(q),
+                                  _ptr(k_cache), _ptr(v_cache), t_max, _stream())
+    check(rc)
+    return q
+
+
+def op_attn_prefill(q, k, v, scale, causal=False, kv_start=None, bias=None):
+    """q [B,Nq,H,D], k/v [B,Nk,H,D] (any strides with contiguous D) -> [B,Nq,H,D]"""
+    require_cuda()
+    lib = load()
+    B, Nq, H, D = q.shape
+    Nk = k.shape[1]
+    out = torch.empty(B, Nq, H, D, dtype=torch.bfloat16, device=q.device)
+    st = []
+    for t in (q, k, v, out):
+        assert t.stride(3) == 1
+        st += [t.stride(0), t.stride(1), t.stride(2)]
+    st12 = (C.c_int64 * 12)(*st)
+    rc = lib.emu_op_attn_prefill(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, H, Nq, Nk, D, st12, C.c_float(scale),
+                                 1 if causal else 0, _ptr(kv_start), _ptr(bias), _stream())
+    check(rc)
+    return out
+
+
+def op_attn_decode(q, k_cache, v_cache, pos, start, scale, max_len):
+    """q [B,H*D]; caches [B,H,T,D]; pos/start int32 [B] -> [B,H*D]"""
+    require_cuda()
+    lib = load()
+    B, H, T, D = k_cache.shape
+    out = torch.empty(B, H * D, dtype=torch.bfloat16, device=q.device)
+    rc = lib.emu_op_attn_decode(_ptr(q), _ptr(k_cache), _ptr(v_cache), B, H, D, T, _ptr(pos), _ptr(start),
+                                C.c_float(scale), _ptr(out), max_len, _stream())
+    check(rc)
+    return out
+
+
+def op_rmsnorm(x, w, eps):
+    require_cuda()
+    y = torch.empty_like(x)
+    check(load().emu_op_rmsnorm(_ptr(x), _ptr(w), _ptr(y), x.shape[0], x.shape[1], C.c_float(eps), _stream()))
+    return y
+
+
+def op_layernorm(x, w, b, eps, residual=None):
+    require_cuda()
+    y = torch.empty_like(x)
+    check(load().emu_op_layernorm(_ptr(x), _ptr(w), _ptr(b), _ptr(residual), _ptr(y), x.shape[0], x.shape[1],
+                                  C.c_float(eps), _stream()))
+    return y
+
+
+def launch_count():
+    return int(load().emu_launch_count())

@@ -1,0 +1,396 @@
+// emu_b200 — tcgen05 GEMM:  C[M,N] = epilogue( A[M,K] · W[N,K]^T )
+//
+// The dense-contraction workhorse of the generate path: ViT QKV/proj/MLP (Emu2/emu/eva_vit.py:194-200,
+// 105-114), LLaMA prefill q/k/v/o/gate/up/down (HF LlamaDecoderLayer, called from Emu2/emu/emu.py:133-138,
+// 213-229), project_up/project_down (emu.py:53-55), UNet linears and — through the 4-D TMA "conv" A-loader —
+// the UNet/VAE 3x3 convolutions (diffusers UNet2DConditionModel, called from Emu2/emu/diffusion.py:136-141).
+//
+// Design (one CTA per SM, persistent over output tiles):
+//   warp 0      : TMA producer — cp.async.bulk.tensor loads of 128x64 (A) and BNx64 (W) bf16 tiles into a
+//                 kStages-deep ring of 128B-swizzled shared-memory stages, completion on mbarriers
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, M=128, N=BN, K=16),
+//                 fp32 accumulators double-buffered in TMEM so the epilogue of tile i overlaps tile i+1
+//   warps 2..5  : epilogue — tcgen05.ld accumulator rows to registers, fused bias / GELU / residual /
+//                 SwiGLU / GEGLU, bf16 or fp32 stores
+// A and W are both K-major, so neither operand needs a transpose anywhere in the model.
+#include "common.cuh"
+#include "ops.h"
+
+namespace emu {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStageBytes = (BM + BN) * BK * 2;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, K;
+  // epilogue
+  void* C;         // bf16 or fp32
+  int ldc;         // elements
+  const bf16* bias;      // [N] or null
+  const bf16* residual;  // [M, ldr] or null (added AFTER rounding the linear output to bf16, like `x + lin(x)`)
+  int ldr;
+  int epi;         // EpiMode
+  int out_fp32;
+  // conv A-loader (mode 1): A is an NHWC tensor [NB, H, W, Cin]; M = NB*H*W output pixels (stride 1, pad 1),
+  // K index = tap * Cin + c.  tile rows = th x tw spatial patch (th*tw == 128)
+  int conv;        // 0 = plain 2-D A, 1 = 3x3 conv (pad 1), 2 = 3x3 conv stride 2 is NOT handled here
+  int H, W, Cin, tw, th;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int kStages = GemmSmem<BN>::kStages;
+  constexpr int kStageBytes = GemmSmem<BN>::kStageBytes;
+  constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator stages (256 or 512 columns)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int kblocks_per_tap = p.conv ? (p.Cin + BK - 1) / BK : (p.K + BK - 1) / BK;
+  const int num_kb = p.conv ? 9 * kblocks_per_tap : kblocks_per_tap;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile % tiles_m, tn = tile / tiles_m;
+        int img = 0, h0 = 0, w0 = 0;
+        if (p.conv) {
+          const int tiles_w = p.W / p.tw, tiles_h = p.H / p.th;
+          w0 = (tm % tiles_w) * p.tw;
+          h0 = ((tm / tiles_w) % tiles_h) * p.th;
+          img = tm / (tiles_w * tiles_h);
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + BM * BK * 2;
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          if (p.conv) {
+            const int tap = kb / kblocks_per_tap, cb = kb % kblocks_per_tap;
+            const int r = tap / 3, s = tap % 3;
+            tma_load_4d(sa, &tmA, &full_bar[stage], cb * BK, w0 + s - 1, h0 + r - 1, img);
+            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + cb * BK, tn * BN);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, tm * BM);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, tn * BN);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + BM * BK * 2;
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr>>4) field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile % tiles_m, tn = tile / tiles_m;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      // output row owned by this thread
+      long row;
+      const int r_in_tile = q * 32 + lane;
+      bool row_ok;
+      if (p.conv) {
+        const int tiles_w = p.W / p.tw, tiles_h = p.H / p.th;
+        const int w0 = (tm % tiles_w) * p.tw;
+        const int h0 = ((tm / tiles_w) % tiles_h) * p.th;
+        const int img = tm / (tiles_w * tiles_h);
+        const int hh = h0 + r_in_tile / p.tw, ww = w0 + r_in_tile % p.tw;
+        row = ((long)img * p.H + hh) * p.W + ww;
+        row_ok = row < p.M;
+      } else {
+        row = (long)tm * BM + r_in_tile;
+        row_ok = row < p.M;
+      }
+      const bool pair = (p.epi == EPI_SWIGLU || p.epi == EPI_GEGLU);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        const int col0 = tn * BN + c * 32;
+        if (row_ok && col0 < p.N) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) f[i] += __bfloat162float(p.bias[col0 + i]);
+          }
+          if (pair) {
+            // interleaved (a_j, b_j) column pairs -> one output column j
+            // SwiGLU: silu(gate)*up with HF's bf16 rounding points; GEGLU: hidden * gelu(gate)
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = round_bf16(f[2 * i]), b = round_bf16(f[2 * i + 1]);
+              if (p.epi == EPI_SWIGLU) o[i] = round_bf16(silu(a)) * b;
+              else o[i] = a * round_bf16(gelu_erf(b));
+            }
+            const int oc0 = col0 >> 1;
+            bf16* dst = reinterpret_cast<bf16*>(p.C) + row * p.ldc + oc0;
+            if (oc0 + 16 <= (p.N >> 1) && (p.ldc % 8 == 0)) {
+              uint4 w0, w1;
+              w0.x = pack_bf16(o[0], o[1]); w0.y = pack_bf16(o[2], o[3]); w0.z = pack_bf16(o[4], o[5]); w0.w = pack_bf16(o[6], o[7]);
+              w1.x = pack_bf16(o[8], o[9]); w1.y = pack_bf16(o[10], o[11]); w1.z = pack_bf16(o[12], o[13]); w1.w = pack_bf16(o[14], o[15]);
+              reinterpret_cast<uint4*>(dst)[0] = w0;
+              reinterpret_cast<uint4*>(dst)[1] = w1;
+            } else {
+              for (int i = 0; i < 16; ++i)
+                if (oc0 + i < (p.N >> 1)) dst[i] = __float2bfloat16_rn(o[i]);
+            }
+          } else {
+            if (p.epi == EPI_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = gelu_erf(round_bf16(f[i]));
+            }
+            if (p.residual != nullptr) {
+              const bf16* rsd = p.residual + row * p.ldr + col0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) f[i] = round_bf16(f[i]) + __bfloat162float(rsd[i]);
+            }
+            if (p.out_fp32) {
+              float* dst = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
+              if (col0 + 32 <= p.N && (p.ldc % 4 == 0)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  reinterpret_cast<float4*>(dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              } else {
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) dst[i] = f[i];
+              }
+            } else {
+              bf16* dst = reinterpret_cast<bf16*>(p.C) + row * p.ldc + col0;
+              if (col0 + 32 <= p.N && (p.ldc % 8 == 0)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  uint4 w;
+                  w.x = pack_bf16(f[8 * i], f[8 * i + 1]);
+                  w.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+                  w.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+                  w.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+                  reinterpret_cast<uint4*>(dst)[i] = w;
+                }
+              } else {
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+// 2-D K-major bf16 matrix [rows, cols] with row stride ld (elements); box = box_rows x 64 cols, 128B swizzle
+int make_tmap_2d(CUtensorMap* out, const void* base, long rows, long cols, long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return EMU_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? EMU_OK : EMU_ERR_CUDA;
+}
+
+// 4-D NHWC bf16 activation [NB, H, W, C]; box = {64 ch, tw, th, 1}; out-of-bounds (the conv halo) reads as zero
+int make_tmap_nhwc(CUtensorMap* out, const void* base, int NB, int H, int W, int C, int tw, int th) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return EMU_ERR_CUDA;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? EMU_OK : EMU_ERR_CUDA;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kBytes) !=
+        cudaSuccess)
+      return EMU_ERR_CUDA;
+    attr_set = true;
+  }
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  gemm_tc_kernel<BN><<<grid, kGemmThreads, GemmSmem<BN>::kBytes, st>>>(tmA, tmB, p);
+  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+}
+
+static int pick_bn(int M, int N) {
+  // prefer the widest tile that still yields >= one wave of CTAs
+  const long tm = (M + BM - 1) / BM;
+  if (tm * ((N + 255) / 256) >= kNumSMs) return 256;
+  if (tm * ((N + 127) / 128) >= kNumSMs / 2) return 128;
+  return 64;
+}
+
+int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& e,
+              cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return EMU_ERR_INVALID;
+  if ((lda % 8) || (ldw % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return EMU_ERR_INVALID;
+  const bool pair = e.mode == EPI_SWIGLU || e.mode == EPI_GEGLU;
+  if (pair && (N & 1)) return EMU_ERR_INVALID;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.C = e.C; p.ldc = e.ldc; p.bias = e.bias; p.residual = e.residual; p.ldr = e.ldr;
+  p.epi = e.mode; p.out_fp32 = e.out_fp32; p.conv = 0;
+  const int bn = e.force_bn ? e.force_bn : pick_bn(M, N);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(&tmA, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, W, N, K, ldw, bn);
+  if (rc) return rc;
+  switch (bn) {
+    case 256: return launch_gemm<256>(tmA, tmB, p, st);
+    case 128: return launch_gemm<128>(tmA, tmB, p, st);
+    case 64: return launch_gemm<64>(tmA, tmB, p, st);
+  }
+  return EMU_ERR_INVALID;
+}
+
+// 3x3 stride-1 pad-1 convolution on NHWC bf16 as an implicit GEMM. Wk is [Cout, 9*Cin] with k = (r*3+s)*Cin + c.
+int conv3x3_bf16(const bf16* X, int NB, int H, int W, int Cin, const bf16* Wk, int Cout, const GemmEpilogue& e,
+                 cudaStream_t st) {
+  if (Cin % 8) return EMU_ERR_INVALID;
+  int tw = W >= 128 ? 128 : W;  // tile = th x tw pixels, th*tw = 128
+  if (128 % tw) return EMU_ERR_UNSUPPORTED;
+  int th = 128 / tw;
+  if (H % th || W % tw) return EMU_ERR_UNSUPPORTED;
+  GemmParams p{};
+  p.M = NB * H * W; p.N = Cout; p.K = 9 * Cin;
+  p.C = e.C; p.ldc = e.ldc; p.bias = e.bias; p.residual = e.residual; p.ldr = e.ldr;
+  p.epi = e.mode; p.out_fp32 = e.out_fp32;
+  p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tw = tw; p.th = th;
+  const int bn = e.force_bn ? e.force_bn : pick_bn(p.M, Cout);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_nhwc(&tmA, X, NB, H, W, Cin, tw, th);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, Wk, Cout, 9L * Cin, 9L * Cin, bn);
+  if (rc) return rc;
+  switch (bn) {
+    case 256: return launch_gemm<256>(tmA, tmB, p, st);
+    case 128: return launch_gemm<128>(tmA, tmB, p, st);
+    case 64: return launch_gemm<64>(tmA, tmB, p, st);
+  }
+  return EMU_ERR_INVALID;
+}
+
+}  // namespace emu

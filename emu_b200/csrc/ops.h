@@ -1,0 +1,107 @@
+// emu_b200 — internal op launchers (C++ side of the C ABI declared in include/emu_b200.h).
+// Every launcher enqueues work on the caller's stream, never synchronises, and returns an EMU_* code.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace emu {
+
+typedef __nv_bfloat16 bf16;
+
+enum EpiMode {
+  EPI_NONE = 0,    // C = A W^T (+bias) (+residual)
+  EPI_GELU = 1,    // C = gelu_erf(A W^T + bias)
+  EPI_SWIGLU = 2,  // W rows interleaved (gate_j, up_j): C[:, j] = silu(g_j) * u_j          (N_out = N/2)
+  EPI_GEGLU = 3,   // W rows interleaved (hidden_j, gate_j): C[:, j] = h_j * gelu_erf(g_j)   (N_out = N/2)
+};
+
+struct GemmEpilogue {
+  void* C = nullptr;
+  int ldc = 0;
+  const bf16* bias = nullptr;
+  const bf16* residual = nullptr;
+  int ldr = 0;
+  int mode = EPI_NONE;
+  int out_fp32 = 0;
+  int force_bn = 0;  // tests only: force the N tile (64/128/256)
+};
+
+// ---- gemm_tc.cu : tcgen05 GEMM / implicit-GEMM conv ----
+int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& e,
+              cudaStream_t st);
+int conv3x3_bf16(const bf16* X_nhwc, int NB, int H, int W, int Cin, const bf16* Wk, int Cout, const GemmEpilogue& e,
+                 cudaStream_t st);
+
+// ---- gemv.cu : weight-streaming skinny GEMM for the decode loop (batch <= 8) ----
+struct GemvArgs {
+  const bf16* W = nullptr;  // [N, K] row-major
+  int N = 0, K = 0;
+  const bf16* x = nullptr;  // [B, ldx]
+  int ldx = 0;
+  int B = 0;
+  const bf16* norm_w = nullptr;  // fused RMSNorm prologue on x (HF LlamaRMSNorm rounding), or null
+  float norm_eps = 1e-6f;
+  int mode = EPI_NONE;           // EPI_NONE / EPI_SWIGLU, or GEMV_ROPE_QKV below
+  const bf16* bias = nullptr;    // [N] or null
+  const bf16* residual = nullptr;  // [B, ldr]
+  int ldr = 0;
+  void* y = nullptr;  // [B, ldy] bf16 (or fp32 if out_fp32)
+  int ldy = 0;
+  int out_fp32 = 0;
+  // mode == GEMV_ROPE_QKV: rows are [q heads | k heads | v heads], q/k head rows pair-interleaved
+  // (row 2j <- orig j, row 2j+1 <- orig j + D/2). Epilogue applies RoPE to q,k, writes q to y and k,v
+  // straight into the KV cache at slot pos[b].
+  int n_heads = 0, head_dim = 0;
+  const bf16* rope_cos = nullptr;  // [max_pos, D/2] bf16
+  const bf16* rope_sin = nullptr;
+  const int* pos = nullptr;      // [B] cache slot of the new token
+  const int* pos_off = nullptr;  // [B] rope position = pos - pos_off
+  bf16* k_cache = nullptr;       // [B, n_heads, T_max, D] (this layer)
+  bf16* v_cache = nullptr;
+  int t_max = 0;
+  int pdl = 0;  // launch with programmatic dependent launch
+};
+constexpr int GEMV_ROPE_QKV = 16;
+int gemv_bf16(const GemvArgs& a, cudaStream_t st);
+
+// ---- attention.cu ----
+// decode: one query token per sequence against the KV cache (slots [start[b], pos[b]] inclusive)
+int attn_decode(const bf16* q /*[B, H*D] pair-interleaved like k*/, const bf16* k_cache, const bf16* v_cache,
+                int B, int H, int D, int t_max, const int* pos, const int* start, float scale, bf16* out /*[B,H*D]*/,
+                float* workspace, int* counters, int max_len_hint, int pdl, cudaStream_t st);
+size_t attn_decode_workspace_bytes(int B, int H, int D);
+// prefill / encoder attention (flash style, mma.sync): q,k,v given as strided [B, N, H, D] views
+struct AttnArgs {
+  const bf16* q = nullptr; const bf16* k = nullptr; const bf16* v = nullptr;
+  long q_bs = 0, q_ts = 0, q_hs = 0;  // element strides: batch, token, head
+  long k_bs = 0, k_ts = 0, k_hs = 0;
+  long v_bs = 0, v_ts = 0, v_hs = 0;
+  bf16* out = nullptr; long o_bs = 0, o_ts = 0, o_hs = 0;
+  int B = 0, H = 0, Nq = 0, Nk = 0, D = 0;
+  float scale = 1.f;
+  int causal = 0;                 // query i attends keys j <= i + (Nk - Nq)
+  const int* kv_start = nullptr;  // [B] first valid key (left padding) or null
+  const float* bias = nullptr;    // [H, Nq, Nk] additive (T5 relative position bias) or null
+};
+int attn_prefill(const AttnArgs& a, cudaStream_t st);
+
+// ---- elementwise.cu ----
+int rmsnorm(const bf16* x, const bf16* w, bf16* y, int rows, int cols, float eps, int t5_style, cudaStream_t st);
+int layernorm(const bf16* x, const bf16* w, const bf16* b, const bf16* residual, bf16* y, int rows, int cols, float eps,
+              cudaStream_t st);  // y = residual + LN(x)  (residual may be null)
+int rope_kv_write(bf16* qkv /*[B,N,3*H*D] pair-interleaved q,k*/, int B, int N, int H, int D, const bf16* cos,
+                  const bf16* sin, const int* pos_off /*[B]*/, int pos0, bf16* k_cache, bf16* v_cache, int t_max,
+                  cudaStream_t st);
+int embed_gather(const bf16* table, const int* ids, bf16* out, int n, int dim, cudaStream_t st);
+int argmax_rows(const float* logits, int rows, int cols, int* out_idx, cudaStream_t st);
+int vit_im2col(const bf16* img_nchw, bf16* out, int B, int C, int HW, int P, int Kpad, cudaStream_t st);
+int vit_assemble(const bf16* patches, const bf16* cls, const bf16* pos, bf16* x, int B, int Np, int dim,
+                 cudaStream_t st);
+int vit_pool(const bf16* x /*[B,1+G*G,dim]*/, bf16* out /*[B,n_query,dim]*/, int B, int G, int dim, int stride,
+             cudaStream_t st);
+int kv_reorder(bf16* cache, bf16* scratch, const int* src_idx, int B, long per_seq_elems, int n_used_tokens, int H,
+               int D, int t_max, cudaStream_t st);
+int add_rows(const bf16* a, const bf16* b, bf16* out, long n, cudaStream_t st);
+
+}  // namespace emu

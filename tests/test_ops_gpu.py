@@ -1,0 +1,184 @@
+"""Kernel parity: every CUDA operator, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances (relative max-abs error, oracle.emu_oracle.rel_err):
+  * fp32 outputs (logits)      : 1e-3   (north_star tolerance; observed ~1e-6: same bf16 inputs, fp32 accumulate)
+  * bf16 outputs               : 6e-3   (one bf16 rounding of the largest element is 2^-9 = 2e-3)
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import emu_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-3
+TOL_BF16 = 6e-3
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 64, 128), (1, 64, 64, 64), (75, 320, 192, 0), (1025, 5376, 1792, 0), (300, 1000, 584, 64),
+    (257, 768, 1408, 128), (4096, 640, 640, 256), (64, 6656, 1792, 0), (513, 264, 72, 0),
+])
+def test_gemm_plain(cuda, M, N, K, bn):
+    from emu_b200 import _lib
+    A, W = _rand((M, K), 1), _rand((N, K), 2, 0.05)
+    ref = O.op_linear(A, W)
+    out32 = _lib.op_gemm(A.cuda(), W.cuda(), out_fp32=True, force_bn=bn).cpu()
+    assert O.rel_err(out32, ref) < TOL_F32
+    out16 = _lib.op_gemm(A.cuda(), W.cuda(), force_bn=bn).cpu()
+    assert O.rel_err(out16, ref) < TOL_BF16
+
+
+def test_gemm_epilogues(cuda):
+    from emu_b200 import _lib
+    M, N, K = 200, 384, 256
+    A, W, b, r = _rand((M, K), 3), _rand((N, K), 4, 0.05), _rand((N,), 5), _rand((M, N), 6)
+    lin = O.op_linear(A, W, b)
+    assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), bias=b.cuda()).cpu(), lin) < TOL_BF16
+    assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), bias=b.cuda(), epi=_lib.EPI_GELU).cpu(),
+                     torch.nn.functional.gelu(lin)) < TOL_BF16
+    assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), bias=b.cuda(), residual=r.cuda()).cpu(), lin + r.float()) < TOL_BF16
+    # interleaved pair epilogues: rows (2j, 2j+1) = (gate_j, up_j) / (hidden_j, gate_j)
+    g, u = O.op_linear(A, W[0::2]), O.op_linear(A, W[1::2])
+    assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), epi=_lib.EPI_SWIGLU).cpu(),
+                     torch.nn.functional.silu(g) * u) < TOL_BF16
+    hb, gb = O.op_linear(A, W[0::2], b[0::2]), O.op_linear(A, W[1::2], b[1::2])
+    assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), bias=b.cuda(), epi=_lib.EPI_GEGLU).cpu(),
+                     hb * torch.nn.functional.gelu(gb)) < TOL_BF16
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(1, 16, 8, 64, 64), (2, 32, 32, 128, 320), (1, 64, 64, 8, 96),
+                                              (1, 8, 128, 320, 32)])
+def test_conv3x3(cuda, NB, H, W, Cin, Cout):
+    from emu_b200 import _lib
+    x = _rand((NB, Cin, H, W), 7)
+    w = _rand((Cout, Cin, 3, 3), 8, 0.05)
+    b = _rand((Cout,), 9)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous().cuda()  # k = (r*3+s)*Cin + c
+    out = _lib.op_conv3x3(x_nhwc, wk, bias=b.cuda()).cpu()
+    assert O.rel_err(out, ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("N,K,B", [(6656, 6656, 1), (1024, 256, 5), (32272, 512, 3), (2000, 1792, 8), (48, 64, 2),
+                                   (35840, 6656, 1), (6656, 17920, 5)])
+def test_gemv_plain(cuda, N, K, B):
+    from emu_b200 import _lib
+    W, x = _rand((N, K), 10, 0.05), _rand((B, K), 11)
+    ref = O.op_linear(x, W)
+    assert O.rel_err(_lib.op_gemv(W.cuda(), x.cuda(), out_fp32=True).cpu(), ref) < TOL_F32
+    assert O.rel_err(_lib.op_gemv(W.cuda(), x.cuda(), pdl=True).cpu(), ref) < TOL_BF16
+
+
+def test_gemv_fused(cuda):
+    from emu_b200 import _lib
+    N, K, B = 1024, 512, 4
+    W, x, nw, r = _rand((N, K), 12, 0.05), _rand((B, K), 13), 1 + 0.1 * _rand((K,), 14).float(), _rand((B, N), 15)
+    nw = nw.to(torch.bfloat16)
+    xn = O.rms_norm(x, nw, 1e-6)          # bf16 rounding points of HF LlamaRMSNorm
+    ref = O.op_linear(xn, W)
+    assert O.rel_err(_lib.op_gemv(W.cuda(), x.cuda(), norm_w=nw.cuda(), out_fp32=True).cpu(), ref) < TOL_F32
+    assert O.rel_err(_lib.op_gemv(W.cuda(), x.cuda(), norm_w=nw.cuda(), residual=r.cuda()).cpu(),
+                     ref + r.float()) < TOL_BF16
+    g, u = O.op_linear(xn, W[0::2]), O.op_linear(xn, W[1::2])
+    assert O.rel_err(_lib.op_gemv(W.cuda(), x.cuda(), norm_w=nw.cuda(), mode=_lib.EPI_SWIGLU).cpu(),
+                     torch.nn.functional.silu(g) * u) < TOL_BF16
+
+
+@pytest.mark.parametrize("B,Nq,Nk,H,D,causal", [
+    (1, 1025, 1025, 16, 112, False), (2, 257, 257, 4, 88, False), (2, 75, 75, 4, 128, True),
+    (1, 32, 257, 12, 64, False), (2, 40, 100, 3, 128, True), (1, 300, 300, 2, 64, True), (1, 17, 17, 2, 32, False),
+])
+def test_attn_prefill(cuda, B, Nq, Nk, H, D, causal):
+    from emu_b200 import _lib
+    q, k, v = _rand((B, Nq, H, D), 20), _rand((B, Nk, H, D), 21), _rand((B, Nk, H, D), 22)
+    kv_start = torch.tensor([0, 7][:B], dtype=torch.int32) if causal else None
+    ref = O.op_attention(q, k, v, D ** -0.5, causal=causal, kv_start=kv_start)
+    out = _lib.op_attn_prefill(q.cuda(), k.cuda(), v.cuda(), D ** -0.5, causal=causal,
+                               kv_start=None if kv_start is None else kv_start.cuda()).cpu()
+    if kv_start is not None:  # fully masked (left-pad) query rows are don't-care
+        for b in range(B):
+            s = int(kv_start[b]) - (Nk - Nq)
+            if s > 0:
+                out[b, :s] = 0
+                ref[b, :s] = 0
+    assert O.rel_err(out, ref) < TOL_BF16
+
+
+def test_attn_prefill_bias(cuda):
+    from emu_b200 import _lib
+    B, N, H, D = 2, 32, 12, 64
+    q, k, v = _rand((B, N, H, D), 23, 0.3), _rand((B, N, H, D), 24, 0.3), _rand((B, N, H, D), 25)
+    bias = torch.randn(H, N, N, generator=torch.Generator().manual_seed(26))
+    ref = O.op_attention(q, k, v, 1.0, causal=True, bias=bias)
+    out = _lib.op_attn_prefill(q.cuda(), k.cuda(), v.cuda(), 1.0, causal=True, bias=bias.cuda()).cpu()
+    assert O.rel_err(out, ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("B,H,D,T,lens,starts", [(1, 52, 128, 512, [200], [0]), (5, 4, 128, 96, [90, 90, 90, 90, 90], [0, 3, 0, 10, 1]),
+                                                  (2, 12, 64, 2048, [1999, 1999], [0, 100]), (1, 2, 128, 64, [1], [0])])
+def test_attn_decode(cuda, B, H, D, T, lens, starts):
+    from emu_b200 import _lib
+    q = _rand((B, H * D), 30)
+    kc, vc = _rand((B, H, T, D), 31), _rand((B, H, T, D), 32)
+    pos = torch.tensor([l - 1 for l in lens], dtype=torch.int32)
+    start = torch.tensor(starts, dtype=torch.int32)
+    out = _lib.op_attn_decode(q.cuda(), kc.cuda(), vc.cuda(), pos.cuda(), start.cuda(), D ** -0.5, T).cpu()
+    for b in range(B):
+        kk = kc[b, :, starts[b]:lens[b]].transpose(0, 1)[None]
+        vv = vc[b, :, starts[b]:lens[b]].transpose(0, 1)[None]
+        ref = O.op_attention(q[b].view(1, 1, H, D), kk, vv, D ** -0.5)
+        assert O.rel_err(out[b].view(1, 1, H, D), ref) < TOL_BF16
+
+
+def test_norms(cuda):
+    from emu_b200 import _lib
+    x, w, b, r = _rand((300, 1792), 40), (1 + 0.1 * _rand((1792,), 41).float()).to(torch.bfloat16), _rand((1792,), 42), _rand((300, 1792), 43)
+    ref = torch.nn.functional.layer_norm(x.float(), (1792,), w.float(), b.float(), 1e-6)
+    assert O.rel_err(_lib.op_layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-6).cpu(), ref) < TOL_BF16
+    assert O.rel_err(_lib.op_layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-6, residual=r.cuda()).cpu(), ref + r.float()) < TOL_BF16
+    assert O.rel_err(_lib.op_rmsnorm(x.cuda(), w.cuda(), 1e-6).cpu(), O.rms_norm(x.float(), w.float(), 1e-6)) < TOL_BF16
+
+
+def test_gemv_rope_qkv(cuda):
+    """fused RMSNorm + QKV + RoPE + KV-cache append vs the HF formulation (oracle.rotate_half path)."""
+    from emu_b200 import _lib
+    Hh, D, K, B, T = 4, 128, 256, 3, 32
+    Wq, Wk, Wv = _rand((Hh * D, K), 50, 0.05), _rand((Hh * D, K), 51, 0.05), _rand((Hh * D, K), 52, 0.05)
+    x, nw = _rand((B, K), 53), (1 + 0.1 * _rand((K,), 54).float()).to(torch.bfloat16)
+    pos = torch.tensor([5, 9, 20], dtype=torch.int32)
+    off = torch.tensor([0, 2, 7], dtype=torch.int32)
+    xn = O.rms_norm(x, nw, 1e-6)
+    q = O.op_linear(xn, Wq).view(B, Hh, D)
+    k = O.op_linear(xn, Wk).view(B, Hh, D)
+    v = O.op_linear(xn, Wv).view(B, Hh, D)
+    cos, sin = O.rope_cos_sin((pos - off).long()[:, None], D, 10000.0, torch.float32)   # [B,1,D]
+    qr = q * cos + O.rotate_half(q) * sin
+    kr = k * cos + O.rotate_half(k) * sin
+
+    def interleave(w):  # row 2j <- j, 2j+1 <- j + D/2 inside each head
+        w = w.view(Hh, D, K)
+        return torch.stack((w[:, :D // 2], w[:, D // 2:]), dim=2).reshape(Hh * D, K)
+    W = torch.cat((interleave(Wq), interleave(Wk), Wv), dim=0).contiguous()
+    tab_pos = torch.arange(64)[None]
+    ct, st_ = O.rope_cos_sin(tab_pos, D, 10000.0, torch.bfloat16)
+    ct, st_ = ct[0, :, :D // 2].contiguous(), st_[0, :, :D // 2].contiguous()
+    kc = torch.zeros(B, Hh, T, D, dtype=torch.bfloat16, device="cuda")
+    vc = torch.zeros_like(kc)
+    qo = _lib.op_gemv_rope_qkv(W.cuda(), Hh, D, x.cuda(), nw.cuda(), 1e-6, ct.cuda(), st_.cuda(), pos.cuda(), off.cuda(),
+                               kc, vc, T).cpu().view(B, Hh, D)
+
+    def deinterleave(t):  # [.., D] interleaved -> original order
+        return torch.cat((t[..., 0::2], t[..., 1::2]), dim=-1)
+    assert O.rel_err(deinterleave(qo), qr) < TOL_BF16
+    for b in range(B):
+        assert O.rel_err(deinterleave(kc[b, :, int(pos[b])].cpu()), kr[b]) < TOL_BF16
+        assert O.rel_err(vc[b, :, int(pos[b])].cpu(), v[b]) < TOL_BF16
