@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Emu2 image->text generate path on B200 (BASELINE.json configs[1]).
+
+One "step" = one full pass of the hot path over one synthetic request: 1x448x448 image -> EVA-CLIP-4B ViT ->
+project_up -> splice into the ~75-token prompt -> LLaMA-33B prefill -> 128 greedily decoded tokens (EOS suppressed so
+exactly 128 steps run).  bf16 weights/activations, random-init weights of the real architecture, synthetic image/ids.
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA engine (tensor parallel for N > 1)
+  python bench.py --impl reference ...                   # the reference's CPU path, bounded sample (rank 0 only)
+
+Prints ONE JSON line (see the task contract): value = device-resident tok/s, e2e = through the public API with host
+buffers, roofline = achieved HBM GB/s of the decode step's weight-streaming kernels vs MEASURED_PEAKS.json,
+cpu_baseline = the oracle port timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "emu2_img2text_decode_tok_per_s"
+NEW_TOKENS = 128
+N_TEXT = 8
+
+
+def emu2_cfgs(small=False):
+    from emu_b200.emu2.conf import CLIPVisionCfg, EMU2_LLAMA_33B
+    if small:  # plumbing-only configuration for CPU-side dry runs of this script's logic (never reported)
+        return CLIPVisionCfg(image_size=56, width=128, layers=2, head_width=32, mlp_ratio=4.0, n_query=4), dict(
+            hidden_size=256, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512, rms_norm_eps=1e-6,
+            max_position_embeddings=512, vocab_size=32000, rope_theta=10000.0)
+    return CLIPVisionCfg(), dict(EMU2_LLAMA_33B)
+
+
+def llm_bytes_per_token(lc, vocab):
+    """Algorithmic HBM bytes one decoded token must read at batch 1: all decoder weights + lm_head."""
+    H, F, L = lc["hidden_size"], lc["intermediate_size"], lc["num_hidden_layers"]
+    per_layer = 4 * H * H + 3 * H * F + 2 * H
+    return 2 * (L * per_layer + H + vocab * H)
+
+
+def kv_bytes_per_ctx_token(lc):
+    return 2 * lc["num_hidden_layers"] * lc["hidden_size"] * 2
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference / cpu_baseline arm: the oracle port of the reference's CPU path on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, ctx=75, threads=None, budget_s=25.0):
+    """Time `tokens` single-token decode steps of `layers_sampled` real-shape LLaMA layers + lm_head in bf16 on the
+    host cores with the oracle (oracle/emu_oracle.llama_forward, KV cache), extrapolate to all layers -> tok/s."""
+    from oracle import emu_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    H, F, nh = lc["hidden_size"], lc["intermediate_size"], lc["num_attention_heads"]
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for l in range(layers_sampled):
+        p = f"decoder.lm.model.layers.{l}."
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            sd[p + f"self_attn.{n}.weight"] = (torch.randn(H, H, generator=g) * 0.02).to(torch.bfloat16)
+        sd[p + "mlp.gate_proj.weight"] = (torch.randn(F, H, generator=g) * 0.02).to(torch.bfloat16)
+        sd[p + "mlp.up_proj.weight"] = (torch.randn(F, H, generator=g) * 0.02).to(torch.bfloat16)
+        sd[p + "mlp.down_proj.weight"] = (torch.randn(H, F, generator=g) * 0.02).to(torch.bfloat16)
+        sd[p + "input_layernorm.weight"] = torch.ones(H, dtype=torch.bfloat16)
+        sd[p + "post_attention_layernorm.weight"] = torch.ones(H, dtype=torch.bfloat16)
+    sd["decoder.lm.model.norm.weight"] = torch.ones(H, dtype=torch.bfloat16)
+    sd["decoder.lm.lm_head.weight"] = (torch.randn(vocab, H, generator=g) * 0.02).to(torch.bfloat16)
+    cache = O.KVCache(layers_sampled)
+    with torch.no_grad():
+        x = (torch.randn(1, ctx, H, generator=g) * 0.02).to(torch.bfloat16)
+        mask = torch.ones(1, ctx, dtype=torch.long)
+        O.llama_forward(sd, x, mask, layers=layers_sampled, heads=nh, cache=cache)  # prefill (untimed)
+        per_tok = []
+        t_start = time.time()
+        for i in range(tokens + 1):
+            e = (torch.randn(1, 1, H, generator=g) * 0.02).to(torch.bfloat16)
+            mask = torch.cat((mask, torch.ones(1, 1, dtype=torch.long)), dim=1)
+            t0 = time.perf_counter()
+            h = O.llama_forward(sd, e, mask, layers=layers_sampled, heads=nh, cache=cache, final_norm=False)
+            t1 = time.perf_counter()
+            hn = O.rms_norm(h, sd["decoder.lm.model.norm.weight"], 1e-6)
+            O.lm_logits(sd, hn[:, -1]).float().argmax(-1)
+            t2 = time.perf_counter()
+            if i > 0:  # first step is warm-up
+                per_tok.append(((t1 - t0) / layers_sampled, t2 - t1))
+            if time.time() - t_start > budget_s and len(per_tok) >= 1:
+                break
+    layer_s = sum(a for a, _ in per_tok) / len(per_tok)
+    head_s = sum(b for _, b in per_tok) / len(per_tok)
+    tok_s = 1.0 / (layer_s * lc["num_hidden_layers"] + head_s)
+    sample = ("%d real-shape LLaMA-33B decoder layers (h=%d, ffn=%d, %d heads) + lm_head, bf16, %d decode steps at "
+              "ctx %d via oracle/emu_oracle.py, per-layer time extrapolated x%d layers (ViT/prefill excluded)" %
+              (layers_sampled, H, F, nh, len(per_tok), ctx, lc["num_hidden_layers"]))
+    return tok_s, threads, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vc, lc = emu2_cfgs(args.small)
+    vocab = 32272
+    vals = []
+    threads = os.cpu_count()
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, threads, sample = cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=2, budget_s=20.0)
+        if i >= args.warmup:
+            vals.append(v)
+    val = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * NEW_TOKENS / val, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "Emu2 image->text: 1x448x448 image, EVA-CLIP-4B ViT + LLaMA-33B decoder, bf16, prompt 75 "
+                        "tokens (1 bos + 66 image span + 8 text), 128 new tokens greedy (EOS suppressed), batch 1",
+            "global_batch": 1, "new_tokens": NEW_TOKENS,
+            "parallelism": "tp%d" % n_gpus if n_gpus > 1 else "single-gpu",
+            "l2_policy": "inputs larger than L2 (64.6 GB of weights streamed per token vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch.distributed as dist
+    from emu_b200 import _lib
+    from emu_b200.emu2.conf import TextDecoderCfg
+    from emu_b200.emu2.emu import EmuModel
+    from emu_b200.emu2 import synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            import ctypes
+            raw = ctypes.create_string_buffer(128)
+            _lib.check(_lib.load().emu_nccl_unique_id(raw))
+            buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    vc, lc = emu2_cfgs(args.small)
+    vocab = synthetic.VOCAB_EMU2
+    n_query = vc.n_query
+    prompt_len = 2 + n_query + 1 + N_TEXT
+    model = EmuModel(vc, TextDecoderCfg(), tokenizer=synthetic.SyntheticTokenizer(vocab), llama_config=lc,
+                     max_batch=1, max_seq=prompt_len + NEW_TOKENS + 8, tp_rank=rank, tp_size=world, nccl_uid=uid)
+    synthetic.load_random_weights(model, vc, lc, vocab, seed=0)
+
+    g = torch.Generator().manual_seed(1234)
+    image_host = torch.randn(1, 3, vc.image_size, vc.image_size, generator=g).to(torch.bfloat16).pin_memory()
+    ids_host, mask_host = synthetic.image_prompt_ids(n_query=n_query, n_text=N_TEXT)
+    ids_host, mask_host = ids_host.pin_memory(), mask_host.pin_memory()
+    image_dev, ids_dev, mask_dev = image_host.cuda(), ids_host.cuda(), mask_host.cuda()
+
+    def one_step(resident):
+        if resident:
+            toks = model.generate_from_ids(ids_dev, mask_dev, image=image_dev, num_beams=1, max_new_tokens=NEW_TOKENS,
+                                           min_len=NEW_TOKENS, check_every=0)
+            return toks
+        img = image_host.to("cuda", non_blocking=True)
+        ids = ids_host.to("cuda", non_blocking=True)
+        msk = mask_host.to("cuda", non_blocking=True)
+        toks = model.generate_from_ids(ids, msk, image=img, num_beams=1, max_new_tokens=NEW_TOKENS, min_len=NEW_TOKENS,
+                                       check_every=0)
+        return toks.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            toks = one_step(resident)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, toks
+
+    for _ in range(args.warmup):
+        one_step(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms, toks = timed(True, args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else {}
+    assert toks.shape[1] == NEW_TOKENS, toks.shape
+    value = args.steps * NEW_TOKENS / (ms / 1000.0)
+
+    # end to end through the public API with host buffers
+    one_step(False)
+    ms_e2e, _ = timed(False, args.steps)
+    e2e = args.steps * NEW_TOKENS / (ms_e2e / 1000.0)
+
+    # decode-step timing for the roofline: events around each CUDA-graphed decode step of one more generate
+    eng = model.engine
+    emb = eng.llm_embed(ids_dev)
+    e = model.encode_image(image_dev)
+    emb[ids_dev == 32003] = model._project_up(e.reshape(-1, e.shape[-1]))
+    eng.llm_reset()
+    _, logits = eng.llm_prefill(emb, mask_dev, hf_positions=True, want_logits=True)
+    out = torch.empty(NEW_TOKENS, 1, dtype=torch.int32, device="cuda")
+    out[0] = logits.argmax(-1).to(torch.int32)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(NEW_TOKENS)]
+    torch.cuda.synchronize()
+    evs[0].record()
+    for s in range(1, NEW_TOKENS):
+        eng.llm_decode(token_ids=out[s - 1], next_ids=out[s], ban_id=2, B=1)
+        evs[s].record()
+    torch.cuda.synchronize()
+    step_ms = sorted(evs[s - 1].elapsed_time(evs[s]) for s in range(1, NEW_TOKENS))
+    step_ms_avg = sum(step_ms) / len(step_ms)
+    ctx_avg = prompt_len + NEW_TOKENS / 2.0
+    alg_bytes = (llm_bytes_per_token(lc, vocab) + kv_bytes_per_ctx_token(lc) * ctx_avg) / world
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (step_ms_avg / 1000.0) / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, threads, sample = cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, budget_s=25.0)
+            cpu = {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample}
+        except Exception as ex:  # the CPU baseline must never take the GPU result down with it
+            cpu = {"value": None, "unit": "tok/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % ex}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": int(image_host.numel() * 2 + ids_host.numel() * 16),
+                "d2h_bytes_per_step": int(NEW_TOKENS * 8)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "gemv_kernel (the weight-streaming launches of one decode step; "
+                     ">99% of the CUDA-graphed step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                     "decode_step_ms": step_ms_avg, "decode_step_ms_p50": step_ms[len(step_ms) // 2],
+                     "algorithmic_bytes_per_step": alg_bytes},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--small", action="store_true", help="tiny plumbing config (debug only; never a bench number)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,6 +9,7 @@
 
 #include <dlfcn.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -281,6 +282,7 @@ extern "C" void emu_engine_destroy(EmuEngine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->unet) unet_destroy(e->unet);
   if (e->vae) vae_destroy(e->vae);
   if (e->cformer) cformer_destroy(e->cformer);
@@ -822,7 +824,8 @@ extern "C" int emu_llm_decode(EmuEngine* e, const int32_t* token_ids, const void
     count_launch();
   }
   int nl = 0;
-  const bool graphable = e->use_graphs && e->tp_size == 1;
+  const char* no_graph = getenv("EMU_NO_GRAPH");  // debugging / parity switch: launch the step eagerly
+  const bool graphable = e->use_graphs && e->tp_size == 1 && !(no_graph && no_graph[0] == '1');
   if (!graphable) {
     EMU_TRY(decode_step_body(e, token_ids, embeds, B, logits, hidden, next_ids, ban_id, st, &nl));
     count_launch(nl);
@@ -835,11 +838,15 @@ extern "C" int emu_llm_decode(EmuEngine* e, const int32_t* token_ids, const void
         e->graphs.clear();
         e->graph_nodes.clear();
       }
-      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess)
-        return e->fail(EMU_ERR_CUDA, "graph capture begin failed");
-      int rc = decode_step_body(e, token_ids, embeds, B, logits, hidden, next_ids, ban_id, st, &nl);
+      // capture on an engine-owned stream: the caller's stream may be the legacy default stream, which cannot
+      // be captured; the instantiated graph is then launched on the caller's stream
+      if (!e->cap_stream && cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return e->fail(EMU_ERR_CUDA, "capture stream create failed");
+      if (cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
+        return e->fail(EMU_ERR_CUDA, std::string("graph capture begin failed: ") + cudaGetErrorString(cudaGetLastError()));
+      int rc = decode_step_body(e, token_ids, embeds, B, logits, hidden, next_ids, ban_id, e->cap_stream, &nl);
       cudaGraph_t graph = nullptr;
-      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
       if (rc != EMU_OK || ce != cudaSuccess || !graph) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();

@@ -66,6 +66,7 @@ struct EmuEngine {
   std::map<GraphKey, cudaGraphExec_t> graphs;
   std::map<GraphKey, int> graph_nodes;
   bool use_graphs = true;
+  cudaStream_t cap_stream = nullptr;
 
   // ---- ViT ----
   std::vector<emu::VitBlock> vit;

@@ -42,16 +42,18 @@ def test_gemm_epilogues(cuda):
     A, W, b, r = _rand((M, K), 3), _rand((N, K), 4, 0.05), _rand((N,), 5), _rand((M, N), 6)
     lin = O.op_linear(A, W, b)
     assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), bias=b.cuda()).cpu(), lin) < TOL_BF16
+    # fused activations follow the reference's bf16 rounding points: Linear -> bf16 -> act -> bf16 (-> mul -> bf16)
+    bf = lambda t: t.to(torch.bfloat16)
     assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), bias=b.cuda(), epi=_lib.EPI_GELU).cpu(),
-                     torch.nn.functional.gelu(lin)) < TOL_BF16
+                     torch.nn.functional.gelu(bf(lin))) < TOL_BF16
     assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), bias=b.cuda(), residual=r.cuda()).cpu(), lin + r.float()) < TOL_BF16
     # interleaved pair epilogues: rows (2j, 2j+1) = (gate_j, up_j) / (hidden_j, gate_j)
     g, u = O.op_linear(A, W[0::2]), O.op_linear(A, W[1::2])
     assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), epi=_lib.EPI_SWIGLU).cpu(),
-                     torch.nn.functional.silu(g) * u) < TOL_BF16
+                     torch.nn.functional.silu(bf(g)) * bf(u)) < TOL_BF16
     hb, gb = O.op_linear(A, W[0::2], b[0::2]), O.op_linear(A, W[1::2], b[1::2])
     assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), bias=b.cuda(), epi=_lib.EPI_GEGLU).cpu(),
-                     hb * torch.nn.functional.gelu(gb)) < TOL_BF16
+                     bf(hb) * torch.nn.functional.gelu(bf(gb))) < TOL_BF16
 
 
 @pytest.mark.parametrize("NB,H,W,Cin,Cout", [(1, 16, 8, 64, 64), (2, 32, 32, 128, 320), (1, 64, 64, 8, 96),
@@ -89,8 +91,9 @@ def test_gemv_fused(cuda):
     assert O.rel_err(_lib.op_gemv(W.cuda(), x.cuda(), norm_w=nw.cuda(), residual=r.cuda()).cpu(),
                      ref + r.float()) < TOL_BF16
     g, u = O.op_linear(xn, W[0::2]), O.op_linear(xn, W[1::2])
+    bf = lambda t: t.to(torch.bfloat16)
     assert O.rel_err(_lib.op_gemv(W.cuda(), x.cuda(), norm_w=nw.cuda(), mode=_lib.EPI_SWIGLU).cpu(),
-                     torch.nn.functional.silu(g) * u) < TOL_BF16
+                     torch.nn.functional.silu(bf(g)) * bf(u)) < TOL_BF16
 
 
 @pytest.mark.parametrize("B,Nq,Nk,H,D,causal", [
@@ -160,9 +163,11 @@ def test_gemv_rope_qkv(cuda):
     q = O.op_linear(xn, Wq).view(B, Hh, D)
     k = O.op_linear(xn, Wk).view(B, Hh, D)
     v = O.op_linear(xn, Wv).view(B, Hh, D)
-    cos, sin = O.rope_cos_sin((pos - off).long()[:, None], D, 10000.0, torch.float32)   # [B,1,D]
-    qr = q * cos + O.rotate_half(q) * sin
-    kr = k * cos + O.rotate_half(k) * sin
+    # HF applies RoPE in the activation dtype: bf16 linear output, bf16 cos/sin, every op rounded to bf16
+    cos, sin = O.rope_cos_sin((pos - off).long()[:, None], D, 10000.0, torch.bfloat16)   # [B,1,D]
+    qb, kb = q.to(torch.bfloat16), k.to(torch.bfloat16)
+    qr = (qb * cos + O.rotate_half(qb) * sin).float()
+    kr = (kb * cos + O.rotate_half(kb) * sin).float()
 
     def interleave(w):  # row 2j <- j, 2j+1 <- j + D/2 inside each head
         w = w.view(Hh, D, K)

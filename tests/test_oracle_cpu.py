@@ -1,0 +1,83 @@
+"""CPU: the oracle restatement (oracle/emu_oracle.py) against the golden outputs of the UNMODIFIED reference
+(tests/golden/emu2_tiny.pt, made by tests/golden/gen_golden.py) and — when /root/reference is present — against the
+reference imported live."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import TINY_LLAMA, TINY_VISION, make_emu2_state_dict
+from oracle import emu_oracle as O, ref_shim
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "emu2_tiny.pt")
+L, NH = TINY_LLAMA["num_hidden_layers"], TINY_LLAMA["num_attention_heads"]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return make_emu2_state_dict()
+
+
+def test_vit_and_encode_image(gold, sd):
+    f = O.vit_forward_features(sd, gold["image"], patch=14, num_heads=4, layers=2)
+    assert O.rel_err(f, gold["vit_tokens"]) < 1e-5
+    e = O.encode_image(sd, gold["image"], patch=14, num_heads=4, layers=2, n_query=4)
+    assert O.rel_err(e, gold["encode_image"]) < 1e-5
+
+
+def _prompt_embeds(gold, sd):
+    e = O.encode_image(sd, gold["image"], patch=14, num_heads=4, layers=2, n_query=4)
+    pie = F.linear(e.view(-1, e.shape[-1]), sd["project_up.weight"])
+    return O.splice_embeds(sd, gold["gen_input_ids"], pie, 32003)
+
+
+def test_prefill_logits(gold, sd):
+    emb = _prompt_embeds(gold, sd)
+    mask = gold["gen_attention_mask"]
+    h = O.llama_forward(sd, emb, mask, layers=L, heads=NH, position_ids=O.hf_position_ids(mask))
+    assert O.rel_err(O.lm_logits(sd, h[:, -1]), gold["prefill_logits_last"]) < 1e-4
+
+
+def test_greedy_tokens(gold, sd):
+    toks = O.generate_greedy(sd, _prompt_embeds(gold, sd), gold["gen_attention_mask"], layers=L, heads=NH,
+                             max_new_tokens=12, min_len=1)
+    assert torch.equal(toks, gold["gen_ids_greedy"])
+
+
+def test_generate_image_literal_and_cached(gold, sd):
+    ids, mask = gold["genimg_input_ids"], gold["genimg_attention_mask"]
+    pe = F.embedding(ids, sd["decoder.lm.model.embed_tokens.weight"])
+    out = O.generate_image_cached(sd, pe, mask, 4, layers=L, heads=NH)
+    assert O.rel_err(out, gold["genimg_text"]) < 1e-4
+    # multimodal prompt: prompt-image slots filled with project_up(encode_image)
+    ids2, mask2 = gold["genimg_mm_input_ids"], gold["genimg_mm_attention_mask"]
+    e = O.encode_image(sd, gold["image"][:1], patch=14, num_heads=4, layers=2, n_query=4)
+    pe2 = O.splice_embeds(sd, ids2, F.linear(e.view(-1, e.shape[-1]), sd["project_up.weight"]), 32003)
+    out2 = O.generate_image_cached(sd, pe2, mask2, 4, layers=L, heads=NH)
+    assert O.rel_err(out2, gold["genimg_mm"]) < 1e-4
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_oracle_vs_live_reference(sd):
+    d = ref_shim.make_llama_config_dir(TINY_LLAMA["hidden_size"], L, NH, TINY_LLAMA["intermediate_size"])
+    vk = dict(TINY_VISION)
+    model = ref_shim.build_emu2_model(vk, d)
+    model.load_state_dict(sd, strict=True)
+    img = torch.randn(1, 3, 56, 56, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = model.encode_image(img)
+        gi = model.generate_image(text=["two dogs"])
+    assert O.rel_err(O.encode_image(sd, img, patch=14, num_heads=4, layers=2, n_query=4), ref) < 1e-5
+    tok = model.decoder.tokenizer
+
+    def ids_fn(k):
+        i = tok(["two dogs[IMG]" + "<image>" * k], padding="longest", return_tensors="pt")
+        return i.input_ids, i.attention_mask
+    lit = O.generate_image_regress(sd, ids_fn, 4, layers=L, heads=NH, image_token_id=32003, boi_token_id=32001)
+    assert O.rel_err(lit, gi) < 1e-5
