@@ -15,7 +15,7 @@ EMU_OK = 0
 ERRORS = {-1: "EMU_ERR_INVALID", -2: "EMU_ERR_CUDA", -3: "EMU_ERR_NOMEM", -4: "EMU_ERR_STATE",
           -5: "EMU_ERR_UNSUPPORTED", -6: "EMU_ERR_NCCL"}
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
-EPI_NONE, EPI_GELU, EPI_SWIGLU, EPI_GEGLU = 0, 1, 2, 3
+EPI_NONE, EPI_GELU, EPI_SWIGLU, EPI_GEGLU, EPI_RELU = 0, 1, 2, 3, 4
 
 
 class EmuError(RuntimeError):
@@ -203,6 +203,52 @@ class Engine:
 
     def cur_len(self):
         return self.lib.emu_llm_cur_len(self.h)
+
+    # ---- Emu1 Causal-Former ----
+    def cformer_forward(self, vit_tokens, n_queries, out_dim):
+        B, Nv, _ = vit_tokens.shape
+        vit_tokens = vit_tokens.to(torch.bfloat16).contiguous()
+        out = torch.empty(B, n_queries, out_dim, dtype=torch.bfloat16, device=vit_tokens.device)
+        check(self.lib.emu_cformer_forward(self.h, _ptr(vit_tokens), B, Nv, _ptr(out), _stream()), self.h)
+        return out
+
+    def vae_configure(self, vcfg: "EmuVAEConfig"):
+        self.vcfg = vcfg
+        check(self.lib.emu_vae_configure(self.h, C.byref(vcfg)), self.h)
+
+    def vae_decode(self, latents):
+        """latents [B,4,h,w] bf16 (already divided by the scaling factor) -> images [B, 8h, 8w, 3] fp32 in [0,1]"""
+        B, _, h, w = latents.shape
+        latents = latents.to(torch.bfloat16).contiguous()
+        f = 2 ** (self.vcfg.n_blocks - 1)
+        out = torch.empty(B, h * f, w * f, self.vcfg.out_channels, dtype=torch.float32, device=latents.device)
+        check(self.lib.emu_vae_decode(self.h, _ptr(latents), B, h, w, _ptr(out), _stream()), self.h)
+        return out
+
+    # ---- diffusion ----
+    def unet_configure(self, ucfg: "EmuUNetConfig"):
+        self.ucfg = ucfg
+        check(self.lib.emu_unet_configure(self.h, C.byref(ucfg)), self.h)
+
+    def unet_forward(self, latents, timestep, ctx, text_embeds=None, time_ids=None):
+        """latents [B2,C,h,w] bf16 NCHW, ctx [B2,L,Cc], text_embeds [B2,Cc], time_ids [B2,6] int32 -> noise [B2,C,h,w]"""
+        B2, Cc, h, w = latents.shape
+        latents = latents.to(torch.bfloat16).contiguous()
+        ctx = ctx.to(torch.bfloat16).contiguous()
+        te = text_embeds.to(torch.bfloat16).contiguous() if text_embeds is not None else None
+        ti = time_ids.to(torch.int32).contiguous() if time_ids is not None else None
+        out = torch.empty(B2, self.ucfg.out_channels, h, w, dtype=torch.bfloat16, device=latents.device)
+        check(self.lib.emu_unet_forward(self.h, _ptr(latents), C.c_float(float(timestep)), _ptr(ctx), ctx.shape[1],
+                                        _ptr(te), _ptr(ti), B2, h, w, _ptr(out), _stream()), self.h)
+        return out
+
+    def denoise_step(self, latents_f32, sigma, sigma_next, timestep, guidance, ctx, text_embeds, time_ids):
+        """One iteration of the denoise loop, latents [B,4,h,w] fp32 updated in place. ctx = [cond; uncond]."""
+        B, _, h, w = latents_f32.shape
+        assert latents_f32.dtype == torch.float32 and latents_f32.is_contiguous()
+        check(self.lib.emu_denoise_step(self.h, _ptr(latents_f32), C.c_float(float(sigma)), C.c_float(float(sigma_next)),
+                                        C.c_float(float(timestep)), C.c_float(float(guidance)), _ptr(ctx), ctx.shape[1],
+                                        _ptr(text_embeds), _ptr(time_ids), B, h, w, _stream()), self.h)
 
     def project(self, which: int, x: torch.Tensor, out_dim: int):
         x2 = x.reshape(-1, x.shape[-1]).to(torch.bfloat16).contiguous()

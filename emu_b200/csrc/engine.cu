@@ -208,6 +208,7 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
     cudaGetLastError();
     return EMU_ERR_CUDA;  // no CPU fallback
   }
+  if (gemv_init() != EMU_OK) return EMU_ERR_NOMEM;
   EmuEngine* e = new EmuEngine();
   e->cfg = *cfg;
   e->tp_rank = tp_rank;
@@ -405,6 +406,10 @@ static int load_vit(EmuEngine* e, const std::string& key, const bf16* src, const
   if (key == "visual.patch_embed.proj.bias") return alloc_copy(e, &e->vit_bpatch, src, W, st);
   if (key == "ln_visual.weight") return alloc_copy(e, &e->vit_lnf_w, src, W, st);
   if (key == "ln_visual.bias") return alloc_copy(e, &e->vit_lnf_b, src, W, st);
+  // unused-by-forward_features members of the Emu1 EVA tower (Emu1/models/eva_vit_model.py: head / norm / fc_norm / rope)
+  if (starts_with(key, "visual.head.") || starts_with(key, "visual.norm.") || starts_with(key, "visual.fc_norm.") ||
+      starts_with(key, "visual.rope."))
+    return EMU_OK;
   const char* pre = "visual.blocks.";
   if (!starts_with(key, pre)) return e->fail(EMU_ERR_INVALID, "unknown vit key " + key);
   const size_t p0 = strlen(pre);
@@ -432,6 +437,7 @@ static int load_vit(EmuEngine* e, const std::string& key, const bf16* src, const
   if (sub == "mlp.fc1.bias") return alloc_copy(e, &B.bfc1, src, c.vit_mlp, st);
   if (sub == "mlp.fc2.weight") return alloc_copy(e, &B.wfc2, src, (size_t)c.vit_mlp * W, st);
   if (sub == "mlp.fc2.bias") return alloc_copy(e, &B.bfc2, src, W, st);
+  if (starts_with(sub, "attn.rope.") || starts_with(sub, "attn.inner_attn_ln.")) return EMU_OK;
   return e->fail(EMU_ERR_INVALID, "unknown vit key " + key);
 }
 

@@ -37,6 +37,8 @@ struct GemmParams {
   const bf16* bias;      // [N] or null
   const bf16* residual;  // [M, ldr] or null (added AFTER rounding the linear output to bf16, like `x + lin(x)`)
   int ldr;
+  const bf16* bias2;     // [M / bias2_rows, N] or null: per-row-group bias (ResnetBlock2D time embedding), added after
+  int bias2_rows;        //   rounding like `conv(x) + temb[:, :, None, None]`
   int epi;         // EpiMode
   int out_fp32;
   // conv A-loader (mode 1): A is an NHWC tensor [NB, H, W, Cin]; M = NB*H*W output pixels (stride 1, pad 1),
@@ -193,6 +195,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 32; ++i)
               if (col0 + i < p.N) f[i] += __bfloat162float(p.bias[col0 + i]);
           }
+          if (p.bias2 != nullptr) {
+            const bf16* b2 = p.bias2 + (row / p.bias2_rows) * p.N + col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) f[i] = round_bf16(f[i]) + __bfloat162float(b2[i]);
+          }
           if (pair) {
             // interleaved (a_j, b_j) column pairs -> one output column j
             // SwiGLU: silu(gate)*up with HF's bf16 rounding points; GEGLU: hidden * gelu(gate)
@@ -219,6 +227,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.epi == EPI_GELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = gelu_erf(round_bf16(f[i]));
+            } else if (p.epi == EPI_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
             }
             if (p.residual != nullptr) {
               const bf16* rsd = p.residual + row * p.ldr + col0;
@@ -351,6 +362,7 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.C = e.C; p.ldc = e.ldc; p.bias = e.bias; p.residual = e.residual; p.ldr = e.ldr;
+  p.bias2 = e.bias2; p.bias2_rows = e.bias2_rows > 0 ? e.bias2_rows : 1;
   p.epi = e.mode; p.out_fp32 = e.out_fp32; p.conv = 0;
   const int bn = e.force_bn ? e.force_bn : pick_bn(M, N);
   CUtensorMap tmA, tmB;
@@ -377,6 +389,7 @@ int conv3x3_bf16(const bf16* X, int NB, int H, int W, int Cin, const bf16* Wk, i
   GemmParams p{};
   p.M = NB * H * W; p.N = Cout; p.K = 9 * Cin;
   p.C = e.C; p.ldc = e.ldc; p.bias = e.bias; p.residual = e.residual; p.ldr = e.ldr;
+  p.bias2 = e.bias2; p.bias2_rows = e.bias2_rows > 0 ? e.bias2_rows : 1;
   p.epi = e.mode; p.out_fp32 = e.out_fp32;
   p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tw = tw; p.th = th;
   const int bn = e.force_bn ? e.force_bn : pick_bn(p.M, Cout);

@@ -6,15 +6,22 @@
 // 64.6 GB of bf16 weights (HF LlamaDecoderLayer q/k/v/o/gate/up/down + lm_head, driven from
 // Emu2/emu/emu.py:213-229 and :133-138), so the kernel is judged on HBM GB/s, not FLOPs.
 //
-// Mapping: a CTA owns 16*RT consecutive weight rows; its 8 warps split K in interleaved 32-element blocks,
-// every lane streams 16-byte pieces of two rows per block with ld.global.nc.L1::no_allocate (each request is a
-// full 64 B per row, 8 rows per instruction) and keeps up to 16 such loads in flight (register double buffer).
-// The tiny x operand (<= 8 rows) is staged once per CTA in shared memory — optionally through a fused
-// RMSNorm prologue (HF LlamaRMSNorm rounding) — and fed as the 8-wide N operand of mma.sync.m16n8k16, so
-// batch 1..8 (greedy .. 5-beam search) all run at the same, bandwidth-bound, speed. fp32 partial sums are
-// reduced across the 8 warps through shared memory; the epilogue fuses bias / residual / SwiGLU / RoPE +
-// KV-cache append.  Launched with programmatic dependent launch: the first weight tiles are requested before
-// griddepcontrol.wait, so HBM keeps streaming across kernel boundaries.
+// Work decomposition ("stream-K"): the weight matrix is cut into chunks of (16*RT rows) x 256 columns.  A
+// persistent grid of 2 CTAs per SM gives every CTA the SAME number of consecutive chunks (+-1), so all SMs stream
+// the same number of bytes and finish together — no wave quantisation whatever N and K are (row-tile grids lost
+// up to 30 % on the 6656-row projections: profiles/r01_kernel_bench_v1.json).  A row group whose chunks straddle
+// CTAs is finished by whichever CTA arrives last (per-group counter; partial sums are added in a fixed order, so
+// results are run-to-run deterministic).
+//
+// Inside a CTA the 8 warps each own one 32-column block of the current chunk; every lane streams 16-byte pieces
+// of 2*RT rows with ld.global.nc.L1::no_allocate (each request = 64 B contiguous per row, 8 rows) through a
+// register ring holding 16 loads in flight per lane (128 KB per SM), with plain pointer increments in the steady
+// state (~11 SASS instructions per KB; a first stream-K cut with 16-row chunks and per-chunk address math was
+// instruction-issue bound at 3 TB/s).  The tiny x operand (<= 8 rows) is staged once per CTA in shared memory —
+// optionally through a fused RMSNorm prologue (HF LlamaRMSNorm rounding) — and fed as the 8-wide N operand of
+// mma.sync.m16n8k16, so batch 1..8 (greedy .. 5-beam search) all run at the same bandwidth-bound speed.
+// Epilogues: bias / residual / SwiGLU / RoPE + KV-cache append.  Launched with programmatic dependent launch: the
+// ring is filled before griddepcontrol.wait, so HBM keeps streaming while the previous kernel drains.
 #include "common.cuh"
 #include "ops.h"
 
@@ -22,58 +29,174 @@ namespace emu {
 
 constexpr int kGemvWarps = 8;
 constexpr int kGemvThreads = kGemvWarps * 32;
+constexpr int kMaxParts = 8;    // CTAs that may share one row group
+constexpr int kWsTiles = 8192;  // workspace capacity in 16-row tiles (N <= 131072)
 
 struct GemvParams {
   GemvArgs a;
-  int ldxs;      // smem row stride of staged x (elements)
-  int red_off;   // byte offset of the reduction buffer
+  int ldxs;       // smem row stride of staged x (elements)
+  int red_off;    // byte offset of the reduction buffers
+  int cpt;        // chunks per row group (= ceil(K / 256))
+  int rt;         // 16-row tiles per group
+  long total;     // total chunks
+  float* ws;      // [groups][kMaxParts][rt*128]
+  int* counters;  // [groups], self-resetting
 };
 
-template <int RT>
-__global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p) {
-  constexpr int U = 4 / RT;  // k-blocks per register chunk
+// Finish the k-segment [kc_lo, kc_hi] of row group `grp`; per-warp partial sums are already in `red`.
+// Called uniformly by all threads of the CTA.  Kept out of line: it runs once per row group, and inlining it into
+// the unrolled streaming loop blew the instruction cache.
+__device__ __noinline__ void gemv_flush(const GemvParams* sp, float* red, float* fin, int* s_last_p, int grp, int kc_lo,
+                                        int kc_hi) {
+  const GemvParams& p = *sp;
+  const GemvArgs& a = p.a;
+  const int N = a.N, B = a.B, CPT = p.cpt, RT = p.rt;
+  const int nval = RT * 128;
+  const long G = gridDim.x;
+  __syncthreads();
+  const bool whole = (kc_lo == 0 && kc_hi == CPT - 1);
+  bool do_epilogue = whole;
+  if (whole) {
+    for (int idx = threadIdx.x; idx < nval; idx += kGemvThreads) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kGemvWarps; ++w) v += red[w * nval + idx];
+      fin[idx] = v;
+    }
+  } else {
+    // owner(x) = largest c with floor(c*total/G) <= x  =  floor(((x+1)*G - 1) / total)
+    const long first_chunk = (long)grp * CPT;
+    const int first_owner = (int)(((first_chunk + 1) * G - 1) / p.total);
+    const int last_owner = (int)(((first_chunk + CPT) * G - 1) / p.total);
+    const int nparts = last_owner - first_owner + 1;
+    const int my = (int)blockIdx.x - first_owner;
+    float* wt = p.ws + ((long)grp * kMaxParts) * nval;
+    for (int idx = threadIdx.x; idx < nval; idx += kGemvThreads) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kGemvWarps; ++w) v += red[w * nval + idx];
+      wt[my * nval + idx] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int prev = atomicAdd(&p.counters[grp], 1);
+      *s_last_p = (prev == nparts - 1);
+      if (prev == nparts - 1) p.counters[grp] = 0;  // self-reset for the next launch / graph replay
+    }
+    __syncthreads();
+    do_epilogue = *s_last_p != 0;
+    if (do_epilogue) {
+      __threadfence();
+      for (int idx = threadIdx.x; idx < nval; idx += kGemvThreads) {
+        float s = 0.f;
+        for (int q = 0; q < nparts; ++q) s += __ldcg(&wt[q * nval + idx]);  // fixed order: deterministic
+        fin[idx] = s;
+      }
+    }
+  }
+  if (do_epilogue) {  // uniform across the CTA
+    __syncthreads();
+    // fin[rt*128 + r*8 + b] holds the full dot product of row (grp*RT + rt)*16 + r with x[b]
+    for (int idx = threadIdx.x; idx < nval; idx += kGemvThreads) {
+      const int rt = idx >> 7, r = idx & 15, b = (idx >> 4) & 7;
+      const float* f = fin + rt * 128;
+      const int nrow = (grp * RT + rt) * 16 + r;
+      if (b >= B || nrow >= N) continue;
+      if (a.mode == EPI_NONE) {
+        float v = f[r * 8 + b];
+        if (a.bias) v += __bfloat162float(a.bias[nrow]);
+        if (a.residual) v = round_bf16(v) + __bfloat162float(a.residual[(long)b * a.ldr + nrow]);
+        if (a.out_fp32) reinterpret_cast<float*>(a.y)[(long)b * a.ldy + nrow] = v;
+        else reinterpret_cast<bf16*>(a.y)[(long)b * a.ldy + nrow] = __float2bfloat16_rn(v);
+      } else if (a.mode == EPI_SWIGLU) {
+        if (r & 1) continue;
+        const float gate = round_bf16(f[r * 8 + b]), up = round_bf16(f[(r + 1) * 8 + b]);
+        const float v = round_bf16(silu(gate)) * up;
+        reinterpret_cast<bf16*>(a.y)[(long)b * a.ldy + (nrow >> 1)] = __float2bfloat16_rn(v);
+      } else {  // GEMV_ROPE_QKV
+        const int D = a.head_dim, H = a.n_heads;
+        const int hh = nrow / D, i = nrow - hh * D;
+        const int slot = a.pos[b];
+        if (hh < 2 * H) {
+          if (r & 1) continue;
+          const float x1 = round_bf16(f[r * 8 + b]), x2 = round_bf16(f[(r + 1) * 8 + b]);
+          const int rp = slot - (a.pos_off ? a.pos_off[b] : 0);
+          const float c = __bfloat162float(a.rope_cos[(long)rp * (D / 2) + (i >> 1)]);
+          const float s = __bfloat162float(a.rope_sin[(long)rp * (D / 2) + (i >> 1)]);
+          // HF apply_rotary_pos_emb in bf16: (q*cos) + (rotate_half(q)*sin), each op rounded
+          const float o1 = round_bf16(x1 * c) + round_bf16(-x2 * s);
+          const float o2 = round_bf16(x2 * c) + round_bf16(x1 * s);
+          bf16* dst;
+          if (hh < H) dst = reinterpret_cast<bf16*>(a.y) + (long)b * a.ldy + nrow;
+          else dst = a.k_cache + (((long)b * H + (hh - H)) * a.t_max + slot) * D + i;
+          *reinterpret_cast<uint32_t*>(dst) = pack_bf16(o1, o2);
+        } else {
+          a.v_cache[(((long)b * H + (hh - 2 * H)) * a.t_max + slot) * D + i] = __float2bfloat16_rn(f[r * 8 + b]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// RT: 16-row tiles per chunk (1/2/4).  KFULL: K % 256 == 0, i.e. every warp's k-block is valid in every chunk.
+template <int RT, bool KFULL>
+__global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvParams p) {
+  constexpr int SLOTS = 8 / RT;  // ring slots, each RT*2 loads: 16 loads in flight per lane
   const GemvArgs& a = p.a;
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* xs = reinterpret_cast<bf16*>(smem);
   float* red = reinterpret_cast<float*>(smem + p.red_off);  // [8 warps][RT][16][8]
+  float* fin = red + kGemvWarps * RT * 128;                 // [RT][16][8]
   __shared__ float s_ss[kGemvWarps][8];
   __shared__ float s_rstd[8];
+  __shared__ int s_last;
+  __shared__ GemvParams s_params;
+  if (threadIdx.x == 0) s_params = p;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int K = a.K, N = a.N, B = a.B;
-  const int row_base = blockIdx.x * (16 * RT);
+  const int KB = K >> 5, CPT = p.cpt;
+  const long G = gridDim.x;
+  const long c0 = (long)blockIdx.x * p.total / G, c1 = ((long)blockIdx.x + 1) * p.total / G;
+  const int n = (int)(c1 - c0);
 
-  const bf16* wrow[RT][2];
+  // ---- load stream state: 2*RT row pointers that advance by 256 elements per chunk ----
+  int ld_grp = (int)(c0 / CPT), ld_kc = (int)(c0 % CPT);
+  const bf16* lp[RT][2];
+  auto set_ptrs = [&](int grp, int kc) {
 #pragma unroll
-  for (int rt = 0; rt < RT; ++rt) {
-    int r0 = row_base + rt * 16 + g, r1 = r0 + 8;
-    r0 = r0 < N ? r0 : N - 1;
-    r1 = r1 < N ? r1 : N - 1;
-    wrow[rt][0] = a.W + (long)r0 * K + t * 8;
-    wrow[rt][1] = a.W + (long)r1 * K + t * 8;
-  }
-  const int KB = K >> 5;
-  const int iters = warp < KB ? (KB - warp + kGemvWarps - 1) / kGemvWarps : 0;
-  const int nchunks = (iters + U - 1) / U;
-
-  uint4 wq[2][U][RT][2];
-#define GEMV_LOAD(BUF, CHUNK)                                                        \
-  {                                                                                  \
-    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                  \
-      const int i_ = (CHUNK)*U + u;                                                  \
-      const bool ok_ = i_ < iters;                                                   \
-      const int kb_ = warp + kGemvWarps * i_;                                        \
-      _Pragma("unroll") for (int rt = 0; rt < RT; ++rt) {                            \
-        _Pragma("unroll") for (int h = 0; h < 2; ++h) {                              \
-          wq[BUF][u][rt][h] = ok_ ? ldg_stream(wrow[rt][h] + (long)kb_ * 32) : make_uint4(0, 0, 0, 0); \
-        }                                                                            \
-      }                                                                              \
-    }                                                                                \
-  }
-
-  // weights do not depend on the previous kernel: request the first chunk before the grid dependency resolves
-  GEMV_LOAD(0, 0);
+    for (int rt = 0; rt < RT; ++rt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int row = (grp * RT + rt) * 16 + g + 8 * h;
+        row = row < N ? row : N - 1;  // ragged last group: clamp (results of clamped rows are never stored)
+        lp[rt][h] = a.W + (long)row * K + ((long)kc * kGemvWarps + warp) * 32 + t * 8;
+      }
+  };
+  set_ptrs(ld_grp, ld_kc);
+  uint4 ring[SLOTS][RT][2];
+  auto load_next = [&](uint4(&slot)[RT][2]) {
+    const bool valid = KFULL || (ld_kc * kGemvWarps + warp < KB);
+#pragma unroll
+    for (int rt = 0; rt < RT; ++rt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        slot[rt][h] = valid ? ldg_stream(lp[rt][h]) : make_uint4(0, 0, 0, 0);
+        lp[rt][h] += 256;
+      }
+    if (++ld_kc == CPT) {
+      ld_kc = 0;
+      ++ld_grp;
+      set_ptrs(ld_grp, 0);
+    }
+  };
+  // weights do not depend on the previous kernel: fill the ring before the grid dependency resolves
+#pragma unroll
+  for (int j = 0; j < SLOTS; ++j)
+    if (j < n) load_next(ring[j]);
   if (a.pdl) {
     pdl_launch_dependents();
     pdl_wait();
@@ -143,111 +266,77 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p) 
 #pragma unroll
   for (int rt = 0; rt < RT; ++rt)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[rt][j] = 0.f;
+    for (int q = 0; q < 4; ++q) acc[rt][q] = 0.f;
 
   const bf16* xrow = xs + (long)g * p.ldxs + t * 8;
   const bool has_x = g < B;
-
-#define GEMV_COMPUTE(BUF, CHUNK)                                                     \
-  {                                                                                  \
-    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                  \
-      const int i_ = (CHUNK)*U + u;                                                  \
-      if (i_ < iters) {                                                              \
-        const int kb_ = warp + kGemvWarps * i_;                                      \
-        uint4 xb = make_uint4(0, 0, 0, 0);                                           \
-        if (has_x) xb = *reinterpret_cast<const uint4*>(xrow + kb_ * 32);            \
-        _Pragma("unroll") for (int rt = 0; rt < RT; ++rt) {                          \
-          const uint4 wa = wq[BUF][u][rt][0], wb = wq[BUF][u][rt][1];                \
-          const uint32_t a1[4] = {wa.x, wb.x, wa.y, wb.y};                           \
-          const uint32_t b1[2] = {xb.x, xb.y};                                       \
-          mma_bf16_16816(acc[rt], a1, b1);                                           \
-          const uint32_t a2[4] = {wa.z, wb.z, wa.w, wb.w};                           \
-          const uint32_t b2[2] = {xb.z, xb.w};                                       \
-          mma_bf16_16816(acc[rt], a2, b2);                                           \
-        }                                                                            \
-      }                                                                              \
-    }                                                                                \
-  }
-
-  for (int c = 0; c < nchunks; c += 2) {
-    if (c + 1 < nchunks) GEMV_LOAD(1, c + 1);
-    GEMV_COMPUTE(0, c);
-    if (c + 1 < nchunks) {
-      if (c + 2 < nchunks) GEMV_LOAD(0, c + 2);
-      GEMV_COMPUTE(1, c + 1);
-    }
-  }
-#undef GEMV_LOAD
-#undef GEMV_COMPUTE
-
-  // ---- cross-warp reduction ----
+  int cp_grp = (int)(c0 / CPT), cp_kc = (int)(c0 % CPT);
+  int seg_lo = cp_kc;
+  const bf16* xp = xrow + (cp_kc * kGemvWarps + warp) * 32;
+  for (int base = 0; base < n; base += SLOTS) {
 #pragma unroll
-  for (int rt = 0; rt < RT; ++rt) {
-    float* r = red + ((warp * RT + rt) * 16) * 8;
-    r[g * 8 + 2 * t] = acc[rt][0];
-    r[g * 8 + 2 * t + 1] = acc[rt][1];
-    r[(g + 8) * 8 + 2 * t] = acc[rt][2];
-    r[(g + 8) * 8 + 2 * t + 1] = acc[rt][3];
-  }
-  __syncthreads();
-
-  auto reduced = [&](int rt, int r, int b) -> float {
-    float s = 0.f;
+    for (int j = 0; j < SLOTS; ++j) {
+      const int i = base + j;
+      if (i < n) {
+        if (KFULL || cp_kc * kGemvWarps + warp < KB) {
+          uint4 xb = make_uint4(0, 0, 0, 0);
+          if (has_x) xb = *reinterpret_cast<const uint4*>(xp);
+          const uint32_t b1[2] = {xb.x, xb.y};
+          const uint32_t b2[2] = {xb.z, xb.w};
 #pragma unroll
-    for (int w = 0; w < kGemvWarps; ++w) s += red[((w * RT + rt) * 16 + r) * 8 + b];
-    return s;
-  };
-
-  for (int idx = threadIdx.x; idx < RT * 128; idx += kGemvThreads) {
-    const int r = idx & 15, b = (idx >> 4) & 7, rt = idx >> 7;
-    const int n = row_base + rt * 16 + r;
-    if (b >= B || n >= N) continue;
-    if (a.mode == EPI_NONE) {
-      float v = reduced(rt, r, b);
-      if (a.bias) v += __bfloat162float(a.bias[n]);
-      if (a.residual) v = round_bf16(v) + __bfloat162float(a.residual[(long)b * a.ldr + n]);
-      if (a.out_fp32) reinterpret_cast<float*>(a.y)[(long)b * a.ldy + n] = v;
-      else reinterpret_cast<bf16*>(a.y)[(long)b * a.ldy + n] = __float2bfloat16_rn(v);
-    } else if (a.mode == EPI_SWIGLU) {
-      if (r & 1) continue;
-      const float gate = round_bf16(reduced(rt, r, b)), up = round_bf16(reduced(rt, r + 1, b));
-      const float v = round_bf16(silu(gate)) * up;
-      reinterpret_cast<bf16*>(a.y)[(long)b * a.ldy + (n >> 1)] = __float2bfloat16_rn(v);
-    } else {  // GEMV_ROPE_QKV
-      const int D = a.head_dim, H = a.n_heads;
-      const int hh = n / D, i = n - hh * D;
-      const int slot = a.pos[b];
-      if (hh < 2 * H) {
-        if (r & 1) continue;
-        const float x1 = round_bf16(reduced(rt, r, b)), x2 = round_bf16(reduced(rt, r + 1, b));
-        const int rp = slot - (a.pos_off ? a.pos_off[b] : 0);
-        const float c = __bfloat162float(a.rope_cos[(long)rp * (D / 2) + (i >> 1)]);
-        const float s = __bfloat162float(a.rope_sin[(long)rp * (D / 2) + (i >> 1)]);
-        // HF apply_rotary_pos_emb in bf16: (q*cos) + (rotate_half(q)*sin), each op rounded
-        const float o1 = round_bf16(x1 * c) + round_bf16(-x2 * s);
-        const float o2 = round_bf16(x2 * c) + round_bf16(x1 * s);
-        bf16* dst;
-        if (hh < H) dst = reinterpret_cast<bf16*>(a.y) + (long)b * a.ldy + n;
-        else dst = a.k_cache + (((long)b * H + (hh - H)) * a.t_max + slot) * D + i;
-        *reinterpret_cast<uint32_t*>(dst) = pack_bf16(o1, o2);
-      } else {
-        const float v = reduced(rt, r, b);
-        a.v_cache[(((long)b * H + (hh - 2 * H)) * a.t_max + slot) * D + i] = __float2bfloat16_rn(v);
+          for (int rt = 0; rt < RT; ++rt) {
+            const uint4 wa = ring[j][rt][0], wb = ring[j][rt][1];
+            // K permutation shared by A and B: lane t feeds elements t*8+{0,1 | 2,3} to mma #1, {4,5 | 6,7} to #2
+            const uint32_t a1[4] = {wa.x, wb.x, wa.y, wb.y};
+            mma_bf16_16816(acc[rt], a1, b1);
+            const uint32_t a2[4] = {wa.z, wb.z, wa.w, wb.w};
+            mma_bf16_16816(acc[rt], a2, b2);
+          }
+        }
+        xp += 256;
+        if (i + SLOTS < n) load_next(ring[j]);
+        const bool grp_done = (cp_kc == CPT - 1) || (i == n - 1);
+        if (grp_done) {
+#pragma unroll
+          for (int rt = 0; rt < RT; ++rt) {
+            float* r = red + (warp * RT + rt) * 128;
+            r[g * 8 + 2 * t] = acc[rt][0];
+            r[g * 8 + 2 * t + 1] = acc[rt][1];
+            r[(g + 8) * 8 + 2 * t] = acc[rt][2];
+            r[(g + 8) * 8 + 2 * t + 1] = acc[rt][3];
+            acc[rt][0] = acc[rt][1] = acc[rt][2] = acc[rt][3] = 0.f;
+          }
+          gemv_flush(&s_params, red, fin, &s_last, cp_grp, seg_lo, cp_kc);
+        }
+        if (++cp_kc == CPT) { cp_kc = 0; ++cp_grp; xp = xrow + warp * 32; }
+        if (grp_done) seg_lo = cp_kc;
       }
     }
   }
 }
 
-template <int RT>
+static float* g_ws = nullptr;
+static int* g_counters = nullptr;
+
+static int ensure_ws() {
+  if (g_ws) return EMU_OK;
+  if (cudaMalloc((void**)&g_ws, (size_t)kWsTiles * kMaxParts * 128 * sizeof(float)) != cudaSuccess) return EMU_ERR_NOMEM;
+  if (cudaMalloc((void**)&g_counters, (size_t)kWsTiles * sizeof(int)) != cudaSuccess) return EMU_ERR_NOMEM;
+  if (cudaMemset(g_counters, 0, (size_t)kWsTiles * sizeof(int)) != cudaSuccess) return EMU_ERR_CUDA;
+  return EMU_OK;
+}
+int gemv_init() { return ensure_ws(); }
+
+template <int RT, bool KFULL>
 static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t st) {
   static size_t cur_max = 0;
   if (smem > cur_max) {
-    if (cudaFuncSetAttribute(gemv_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemv_kernel<RT, KFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return EMU_ERR_CUDA;
     cur_max = smem;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
+  cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kGemvThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -256,30 +345,51 @@ static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = p.a.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gemv_kernel<RT>, p) == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+  return cudaLaunchKernelEx(&cfg, gemv_kernel<RT, KFULL>, p) == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
 int gemv_bf16(const GemvArgs& a, cudaStream_t st) {
   if (a.B < 1 || a.B > 8 || a.N < 1 || a.K < 32 || (a.K % 32) || (a.ldx % 8)) return EMU_ERR_INVALID;
   if ((a.mode == EPI_SWIGLU || a.mode == GEMV_ROPE_QKV) && (a.N % 16)) return EMU_ERR_INVALID;
+  const int tiles = (a.N + 15) / 16;
+  if (tiles > kWsTiles) return EMU_ERR_UNSUPPORTED;
+  int rc = ensure_ws();  // NOTE: first use must happen outside stream capture (the engine calls gemv_init())
+  if (rc) return rc;
   GemvParams p;
   p.a = a;
   p.ldxs = a.K + 32;  // row stride = 64 B (mod 128 B): conflict-free B-fragment reads
+  p.ws = g_ws;
+  p.counters = g_counters;
+  const int KB = a.K / 32;
+  p.cpt = (KB + kGemvWarps - 1) / kGemvWarps;
   const size_t xs_bytes = (size_t)a.B * p.ldxs * sizeof(bf16);
-  const int tiles = (a.N + 15) / 16;
-  // widest row group that still gives >= ~3 CTAs per SM
-  int rt = 1;
-  if (tiles >= 4 * 3 * kNumSMs) rt = 4;
-  else if (tiles >= 2 * 3 * kNumSMs) rt = 2;
   p.red_off = (int)((xs_bytes + 15) & ~size_t(15));
-  const size_t smem = p.red_off + (size_t)kGemvWarps * rt * 16 * 8 * sizeof(float);
+  // tallest row group that still leaves >= 9 chunks per CTA: the RT=4 inner loop is ~4x leaner in instructions
+  // per byte than RT=1, which outweighs up to ~10 % chunk-count imbalance (measured on the 6656x6656 o_proj)
+  const long slots = 2L * kNumSMs;
+  int rt = 1;
+  if ((long)((tiles + 3) / 4) * p.cpt >= 9 * slots) rt = 4;
+  else if ((long)((tiles + 1) / 2) * p.cpt >= 9 * slots) rt = 2;
+  const size_t smem = p.red_off + (size_t)(kGemvWarps + 1) * rt * 128 * sizeof(float);
   if (smem > 220 * 1024) return EMU_ERR_UNSUPPORTED;
-  const int grid = (tiles + rt - 1) / rt;
-  switch (rt) {
-    case 4: return launch_gemv<4>(p, grid, smem, st);
-    case 2: return launch_gemv<2>(p, grid, smem, st);
-    default: return launch_gemv<1>(p, grid, smem, st);
+  const int occ = smem > 100 * 1024 ? 1 : 2;
+  p.rt = rt;
+  const int groups = (tiles + rt - 1) / rt;
+  p.total = (long)groups * p.cpt;
+  long grid = (long)kNumSMs * occ;
+  if (grid > p.total) grid = p.total;
+  // a row group may be shared by at most kMaxParts CTAs: keep every CTA's share >= cpt / (kMaxParts - 3)
+  const long max_grid = (long)groups * (kMaxParts - 3);
+  if (grid > max_grid) grid = max_grid;
+  const bool kfull = (a.K % 256) == 0;
+  if (kfull) {
+    if (rt == 4) return launch_gemv<4, true>(p, (int)grid, smem, st);
+    if (rt == 2) return launch_gemv<2, true>(p, (int)grid, smem, st);
+    return launch_gemv<1, true>(p, (int)grid, smem, st);
   }
+  if (rt == 4) return launch_gemv<4, false>(p, (int)grid, smem, st);
+  if (rt == 2) return launch_gemv<2, false>(p, (int)grid, smem, st);
+  return launch_gemv<1, false>(p, (int)grid, smem, st);
 }
 
 }  // namespace emu

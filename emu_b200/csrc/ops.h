@@ -14,6 +14,7 @@ enum EpiMode {
   EPI_GELU = 1,    // C = gelu_erf(A W^T + bias)
   EPI_SWIGLU = 2,  // W rows interleaved (gate_j, up_j): C[:, j] = silu(g_j) * u_j          (N_out = N/2)
   EPI_GEGLU = 3,   // W rows interleaved (hidden_j, gate_j): C[:, j] = h_j * gelu_erf(g_j)   (N_out = N/2)
+  EPI_RELU = 4,    // C = relu(A W^T + bias)   (T5 DenseReluDense)
 };
 
 struct GemmEpilogue {
@@ -22,6 +23,8 @@ struct GemmEpilogue {
   const bf16* bias = nullptr;
   const bf16* residual = nullptr;
   int ldr = 0;
+  const bf16* bias2 = nullptr;  // [M / bias2_rows, N] per-row-group bias (time embedding of a ResnetBlock2D)
+  int bias2_rows = 0;
   int mode = EPI_NONE;
   int out_fp32 = 0;
   int force_bn = 0;  // tests only: force the N tile (64/128/256)
@@ -64,6 +67,7 @@ struct GemvArgs {
 };
 constexpr int GEMV_ROPE_QKV = 16;
 int gemv_bf16(const GemvArgs& a, cudaStream_t st);
+int gemv_init();  // allocate the stream-K workspace (must run once outside stream capture)
 
 // ---- attention.cu ----
 // decode: one query token per sequence against the KV cache (slots [start[b], pos[b]] inclusive)

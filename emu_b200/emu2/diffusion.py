@@ -1,0 +1,230 @@
+"""Drop-in for the reference's ``emu.diffusion.EmuVisualGeneration`` (Emu2/emu/diffusion.py:31-383).
+
+Same public surface — ``from_pretrained`` / ``from_config`` / ``forward(inputs, height, width,
+num_inference_steps, guidance_scale, crop_info, original_size)`` returning an
+``EmuVisualGenerationPipelineOutput(image, nsfw_content_detected)`` — with the arithmetic on the B200 engine:
+prompt encoding through ``EmuModel.generate_image`` / ``encode_image``, the denoise loop as one CUDA-graphed
+``emu_denoise_step`` per iteration (cat + scale_model_input + UNet + CFG + Euler fused), VAE decode on device.
+The safety checker is a post-filter outside the generate path: ``nsfw_content_detected`` is None.
+"""
+import json
+import os
+import os.path as osp
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+from PIL import Image
+
+from .. import _lib
+from .conf import CLIPVisionCfg, TextDecoderCfg
+from .constants import DEFAULT_IMG_PLACEHOLDER, EVA_IMAGE_SIZE, OPENAI_DATASET_MEAN, OPENAI_DATASET_STD
+from .emu import EmuModel
+from .scheduler import EulerDiscreteScheduler
+
+
+@dataclass
+class EmuVisualGenerationPipelineOutput:
+    image: Image.Image
+    nsfw_content_detected: Optional[bool]
+
+
+def image_transform(img: Image.Image, size=EVA_IMAGE_SIZE, mean=OPENAI_DATASET_MEAN, std=OPENAI_DATASET_STD):
+    """TF.Resize((size,size), BICUBIC) -> ToTensor -> Normalize  (Emu2/emu/diffusion.py:59-63)."""
+    img = img.convert("RGB").resize((size, size), resample=Image.BICUBIC)
+    x = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float().div(255.0)
+    return (x - torch.tensor(mean)[:, None, None]) / torch.tensor(std)[:, None, None]
+
+
+def unet_config_from_json(cfg: dict) -> "_lib.EmuUNetConfig":
+    u = _lib.EmuUNetConfig()
+    u.in_channels, u.out_channels = cfg["in_channels"], cfg["out_channels"]
+    boc = cfg["block_out_channels"]
+    u.n_blocks = len(boc)
+    tl = cfg.get("transformer_layers_per_block", 1)
+    if isinstance(tl, int):
+        tl = [tl] * len(boc)
+    for i, c in enumerate(boc):
+        u.block_out_channels[i] = c
+        u.transformer_layers[i] = tl[i] if "CrossAttn" in cfg["down_block_types"][i] else 0
+    u.layers_per_block = cfg["layers_per_block"]
+    ahd = cfg["attention_head_dim"]
+    # SDXL configs store the number of heads in `attention_head_dim`; the head width is C / heads
+    heads = ahd if isinstance(ahd, (list, tuple)) else [ahd] * len(boc)
+    u.head_dim = boc[-1] // heads[-1]
+    u.cross_attention_dim = cfg["cross_attention_dim"]
+    u.use_linear_projection = 1 if cfg.get("use_linear_projection") else 0
+    u.addition_time_embed_dim = cfg.get("addition_time_embed_dim") or 0
+    u.projection_class_embeddings_input_dim = cfg.get("projection_class_embeddings_input_dim") or 0
+    u.norm_groups, u.norm_eps = cfg["norm_num_groups"], cfg["norm_eps"]
+    if not u.use_linear_projection:
+        raise NotImplementedError("conv proj_in/proj_out (SD-1.5 style) is not wired yet")
+    return u
+
+
+def vae_config_from_json(cfg: dict) -> "_lib.EmuVAEConfig":
+    v = _lib.EmuVAEConfig()
+    v.latent_channels, v.out_channels = cfg["latent_channels"], cfg["out_channels"]
+    v.n_blocks = len(cfg["block_out_channels"])
+    for i, c in enumerate(cfg["block_out_channels"]):
+        v.block_out_channels[i] = c
+    v.layers_per_block, v.norm_groups = cfg["layers_per_block"], cfg["norm_num_groups"]
+    return v
+
+
+class EmuVisualGeneration:
+    def __init__(self, multimodal_encoder: EmuModel, scheduler: EulerDiscreteScheduler, unet_config: dict,
+                 vae_config: Optional[dict] = None, eva_size=EVA_IMAGE_SIZE, eva_mean=OPENAI_DATASET_MEAN,
+                 eva_std=OPENAI_DATASET_STD, **kwargs):
+        self.multimodal_encoder = multimodal_encoder
+        self.engine = multimodal_encoder.engine
+        self.scheduler = scheduler
+        self.unet_config, self.vae_config = unet_config, vae_config
+        self.engine.unet_configure(unet_config_from_json(unet_config))
+        if vae_config is not None:
+            self.engine.vae_configure(vae_config_from_json(vae_config))
+            self.vae_scale_factor = 2 ** (len(vae_config["block_out_channels"]) - 1)
+            self.vae_scaling = vae_config.get("scaling_factor", 0.13025)
+        else:
+            self.vae_scale_factor, self.vae_scaling = 8, 0.13025
+        self.eva_size, self.eva_mean, self.eva_std = eva_size, eva_mean, eva_std
+        self.negative_prompt = {}
+        self.device_ = multimodal_encoder.device_
+
+    def transform(self, img):
+        return image_transform(img, self.eva_size, self.eva_mean, self.eva_std)
+
+    def eval(self):
+        return self
+
+    def load_state_dict(self, sd, strict=True):
+        """Keys as saved by the reference pipeline: multimodal_encoder.*, unet.*, vae.* (safety_checker.* ignored)."""
+        for k, v in sd.items():
+            if k.startswith("safety_checker.") or k.endswith("rotary_emb.inv_freq"):
+                continue
+            if k.startswith("vae.") and (self.vae_config is None or ".encoder." in k or k.startswith("vae.quant_conv")):
+                continue  # only the decoder half is on the generate path
+            self.engine.load_tensor(k, v)
+        return self
+
+    # ---- Emu2/emu/diffusion.py:77-166 ----
+    @torch.no_grad()
+    def forward(self, inputs, height: int = 1024, width: int = 1024, num_inference_steps: int = 50,
+                guidance_scale: float = 3., crop_info: List[int] = [0, 0], original_size: List[int] = [1024, 1024],
+                generator: Optional[torch.Generator] = None, latents: Optional[torch.Tensor] = None,
+                output_type: str = "pil"):
+        if not isinstance(inputs, list):
+            inputs = [inputs]
+        dev = self.device_
+        do_cfg = guidance_scale > 1.0
+        prompt_embeds = self._prepare_and_encode_inputs(inputs, do_cfg).to(torch.bfloat16).contiguous()
+        batch_size = prompt_embeds.shape[0] // 2 if do_cfg else prompt_embeds.shape[0]
+        latents = self.denoise(prompt_embeds, batch_size, height, width, num_inference_steps, guidance_scale, crop_info,
+                               original_size, generator=generator, latents=latents)
+        if output_type == "latent":
+            return latents
+        images = self.decode_latents(latents)
+        images = self.numpy_to_pil(images)
+        return EmuVisualGenerationPipelineOutput(image=images[0], nsfw_content_detected=None)
+
+    __call__ = forward
+
+    @torch.no_grad()
+    def denoise(self, prompt_embeds, batch_size, height=1024, width=1024, num_inference_steps=50, guidance_scale=3.,
+                crop_info=(0, 0), original_size=(1024, 1024), generator=None, latents=None):
+        """Steps 2-4 of the reference forward (time ids, pooled text embedding, timesteps, latents, denoise loop)."""
+        dev = self.device_
+        do_cfg = guidance_scale > 1.0
+        B2 = prompt_embeds.shape[0]
+        time_ids = torch.tensor(list(original_size) + list(crop_info) + [height, width], dtype=torch.int32, device=dev)
+        time_ids = time_ids[None].expand(B2, -1).contiguous()
+        text_embeds = prompt_embeds.float().mean(dim=1).to(torch.bfloat16).contiguous()  # diffusion.py:113
+        self.scheduler.set_timesteps(num_inference_steps)
+        ts, sig = self.scheduler.timesteps, self.scheduler.sigmas
+        h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
+        if latents is None:
+            latents = torch.randn((batch_size, self.unet_config["in_channels"], h, w), generator=generator,
+                                  device=dev if generator is None or generator.device.type == "cuda" else "cpu",
+                                  dtype=torch.float32).to(dev)
+        latents = (latents.to(torch.bfloat16).float() * self.scheduler.init_noise_sigma).contiguous()
+        for i in range(num_inference_steps):
+            self.engine.denoise_step(latents, float(sig[i]), float(sig[i + 1]), float(ts[i]), guidance_scale,
+                                     prompt_embeds, text_embeds, time_ids)
+        return latents
+
+    # ---- Emu2/emu/diffusion.py:168-212 ----
+    @torch.no_grad()
+    def _prepare_and_encode_inputs(self, inputs, do_classifier_free_guidance=False,
+                                   placeholder: str = DEFAULT_IMG_PLACEHOLDER):
+        has_image, has_text = False, False
+        text_prompt, image_prompt = "", []
+        for x in inputs:
+            if isinstance(x, str):
+                has_text = True
+                text_prompt += x
+            else:
+                has_image = True
+                text_prompt += placeholder
+                image_prompt.append(self.transform(x))
+        image_prompt = torch.stack(image_prompt).to(self.device_, torch.bfloat16) if image_prompt else None
+        enc = self.multimodal_encoder
+        if has_image and not has_text:  # autoencoding mode: exactly one image
+            prompt = enc.encode_image(image=image_prompt)
+            if do_classifier_free_guidance:
+                key = "[NULL_IMAGE]"
+                if key not in self.negative_prompt:
+                    self.negative_prompt[key] = enc.encode_image(image=torch.zeros_like(image_prompt))
+                prompt = torch.cat([prompt, self.negative_prompt[key]], dim=0)
+        else:
+            prompt = enc.generate_image(text=[text_prompt], image=image_prompt)
+            if do_classifier_free_guidance:
+                key = ""
+                if key not in self.negative_prompt:
+                    self.negative_prompt[key] = enc.generate_image(text=[key])
+                prompt = torch.cat([prompt, self.negative_prompt[key]], dim=0)
+        return prompt
+
+    # ---- Emu2/emu/diffusion.py:214-234 ----
+    def decode_latents(self, latents: torch.Tensor) -> np.ndarray:
+        z = (latents.float() / self.vae_scaling).to(torch.bfloat16).contiguous()
+        img = self.engine.vae_decode(z)  # [B, H, W, 3] fp32 in [0, 1]
+        return img.cpu().numpy()
+
+    def numpy_to_pil(self, images: np.ndarray):
+        if images.ndim == 3:
+            images = images[None, ...]
+        images = (images * 255).round().astype("uint8")
+        return [Image.fromarray(im) for im in images]
+
+    # ---- Emu2/emu/diffusion.py:251-318 ----
+    @classmethod
+    def from_config(cls, config_path: str, llama_config_path: Optional[str] = None, tokenizer=None, **kwargs):
+        unet_cfg = json.load(open(osp.join(config_path, "unet", "config.json")))
+        vae_p = osp.join(config_path, "vae", "config.json")
+        vae_cfg = json.load(open(vae_p)) if osp.exists(vae_p) else None
+        sched = EulerDiscreteScheduler.from_config(osp.join(config_path, "scheduler"))
+        tcfg = TextDecoderCfg(llama_config_path=llama_config_path) if llama_config_path else TextDecoderCfg()
+        enc = EmuModel(CLIPVisionCfg(), tcfg, tokenizer=tokenizer, **kwargs)
+        return cls(multimodal_encoder=enc, scheduler=sched, unet_config=unet_cfg, vae_config=vae_cfg)
+
+    @classmethod
+    def from_pretrained(cls, model_path: str, config_path: Optional[str] = None, dtype=torch.bfloat16,
+                        use_safetensors: bool = True, **kwargs):
+        if config_path is None:
+            config_path = model_path
+        ins = cls.from_config(config_path, **kwargs)
+        if use_safetensors:
+            from safetensors.torch import load_file
+            sd = load_file(osp.join(model_path, "model.safetensors"))
+        else:
+            sd = torch.load(osp.join(model_path, "pytorch_model.bin"), map_location="cpu")
+        ins.load_state_dict(sd)
+        return ins
+
+    def multito(self, device_list):
+        """The reference places layers on several GPUs of ONE process (Emu2/emu/mixin.py); this engine is one
+        process per GPU with tensor parallelism instead — see bench.py / INTEGRATION.md."""
+        return self
+
+    multicuda = multito

@@ -65,14 +65,46 @@ def test_prefill_logits_vs_reference(model, gold, sd):
     assert O.rel_err(logits.cpu(), gold["prefill_logits_last"]) < 3e-2
 
 
-def test_generate_greedy_tokens_vs_reference(model, gold):
+def _oracle_prompt(gold, sd):
+    e = O.encode_image(sd, gold["image"], patch=14, num_heads=4, layers=2, n_query=4)
+    pie = torch.nn.functional.linear(e.view(-1, e.shape[-1]), sd["project_up.weight"])
+    return O.splice_embeds(sd, gold["gen_input_ids"], pie, 32003)
+
+
+def _teacher_forced_logprobs(sd, emb, mask, toks):
+    """fp32 oracle log-probs of each step given the token history `toks` [B,T] -> [B,T,V]."""
+    B, T = toks.shape
+    cache = O.KVCache(2)
+    m = mask.clone()
+    h = O.llama_forward(sd, emb, m, layers=2, heads=2, position_ids=O.hf_position_ids(m), cache=cache)
+    outs = []
+    for t in range(T):
+        outs.append(torch.log_softmax(O.lm_logits(sd, h[:, -1]).float(), -1))
+        if t == T - 1:
+            break
+        m = torch.cat((m, torch.ones(B, 1, dtype=m.dtype)), dim=1)
+        e = torch.nn.functional.embedding(toks[:, t], sd["decoder.lm.model.embed_tokens.weight"]).unsqueeze(1)
+        h = O.llama_forward(sd, e, m, layers=2, heads=2, position_ids=m.long().sum(-1, keepdim=True) - 1, cache=cache)
+    return torch.stack(outs, dim=1)
+
+
+def test_generate_greedy_tokens_vs_reference(model, gold, sd):
+    """Random-init logits are nearly flat, so a bf16-level perturbation may legitimately pick the other side of a
+    near tie.  Accept a free-running greedy sequence iff, under the fp32 reference model teacher-forced on that
+    very sequence, every chosen token is within the numerical noise margin of the reference argmax; rows whose
+    choices never hit a near tie must reproduce the reference ids exactly."""
     ids = model.generate_from_ids(gold["gen_input_ids"], gold["gen_attention_mask"], image=gold["image"].cuda(),
-                                  num_beams=1, max_new_tokens=12, min_len=1)
+                                  num_beams=1, max_new_tokens=12, min_len=1).cpu()
     ref = gold["gen_ids_greedy"]
-    # random-init logits are nearly flat, so one bf16 flip can fork the sequence; require a common prefix
-    n = ref.shape[1]
-    same = (ids.cpu()[:, :n] == ref).long().cumprod(1).sum(1)
-    assert int(same.min()) >= 4, (ids.cpu(), ref)
+    assert ids.shape == ref.shape
+    lp = _teacher_forced_logprobs(sd, _oracle_prompt(gold, sd), gold["gen_attention_mask"], ids)
+    chosen = lp.gather(2, ids[:, :, None]).squeeze(2)
+    best = lp.max(-1)[0]
+    margin = 3e-2 * lp.abs().max()          # same budget as the logits parity tests
+    assert bool((best - chosen <= margin).all()), (best - chosen)
+    exact_rows = (best - chosen == 0).all(1)
+    assert bool(exact_rows.any())
+    assert torch.equal(ids[exact_rows], ref[exact_rows])
 
 
 def test_generate_greedy_matches_bf16_oracle(model, gold, sd):
@@ -97,13 +129,23 @@ def test_generate_greedy_matches_bf16_oracle(model, gold, sd):
         assert O.rel_err(buf.cpu(), logit_list[s]) < 3e-2, s
 
 
-def test_beam_search_vs_reference(model, gold):
+def test_beam_search_vs_reference(model, gold, sd):
+    """Beam search control flow is pinned exactly on CPU (tests/test_generation_cpu.py).  On the GPU the bf16
+    engine may break near ties differently, so compare hypothesis QUALITY under the fp32 reference model: the
+    returned sequence must score (sum of log-probs) within noise of the reference's own 5-beam result."""
     ids = model.generate_from_ids(gold["gen_input_ids"][:1], gold["gen_attention_mask"][:1],
                                   image=gold["image"][:1].cuda(), num_beams=5, max_new_tokens=12, min_len=1,
-                                  length_penalty=-1)
+                                  length_penalty=-1).cpu()
     ref = gold["gen_ids_beam5"]
-    same = (ids.cpu()[:, :ref.shape[1]] == ref[:, :ids.shape[1]]).long().cumprod(1).sum(1)
-    assert int(same.min()) >= 3, (ids.cpu(), ref)
+    emb = _oracle_prompt(gold, sd)[:1]
+    mask = gold["gen_attention_mask"][:1]
+
+    def score(t):
+        lp = _teacher_forced_logprobs(sd, emb, mask, t)
+        return float(lp.gather(2, t[:, :, None]).sum())
+    assert ids.shape[1] == ref.shape[1]
+    s_eng, s_ref = score(ids), score(ref)
+    assert s_eng >= s_ref - 0.03 * abs(s_ref), (s_eng, s_ref, ids, ref)
 
 
 def test_generate_image_vs_reference(model, gold):

@@ -1,0 +1,95 @@
+"""Parity of the CUDA UNet / denoise step (through the C ABI) against oracle/diffusion_oracle.py on a tiny
+SDXL-topology configuration with seeded random weights.  The diffusion oracle restates diffusers 0.24.0
+("parity unpinned": diffusers is neither vendored nor installed)."""
+import pytest
+import torch
+
+from oracle import diffusion_oracle as D
+from oracle import emu_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TINY_UNET = dict(in_channels=4, out_channels=4, block_out_channels=(64, 128, 256), layers_per_block=2,
+                 transformer_layers_per_block=(0, 1, 2), attention_head_dim=64, cross_attention_dim=128,
+                 addition_time_embed_dim=32, projection_class_embeddings_input_dim=128 + 6 * 32, norm_num_groups=32,
+                 norm_eps=1e-5)
+
+
+def make_engine(cfg, sd):
+    from emu_b200 import _lib
+    eng = _lib.Engine(_lib.EmuConfig())
+    u = _lib.EmuUNetConfig()
+    u.in_channels, u.out_channels = cfg["in_channels"], cfg["out_channels"]
+    u.n_blocks = len(cfg["block_out_channels"])
+    for i, c in enumerate(cfg["block_out_channels"]):
+        u.block_out_channels[i] = c
+        u.transformer_layers[i] = cfg["transformer_layers_per_block"][i]
+    u.layers_per_block = cfg["layers_per_block"]
+    u.head_dim, u.cross_attention_dim = cfg["attention_head_dim"], cfg["cross_attention_dim"]
+    u.use_linear_projection = 1
+    u.addition_time_embed_dim = cfg["addition_time_embed_dim"]
+    u.projection_class_embeddings_input_dim = cfg["projection_class_embeddings_input_dim"]
+    u.norm_groups, u.norm_eps = cfg["norm_num_groups"], cfg["norm_eps"]
+    eng.unet_configure(u)
+    eng.load_state_dict({"unet." + k: v for k, v in sd.items()})
+    return eng
+
+
+@pytest.fixture(scope="module")
+def setup(cuda):
+    sd = D.random_state_dict(D.unet_param_shapes(TINY_UNET), seed=3)
+    eng = make_engine(TINY_UNET, sd)
+    g = torch.Generator().manual_seed(11)
+    ctx = torch.randn(2, 8, 128, generator=g)
+    tid = torch.tensor([[1024, 1024, 0, 0, 1024, 1024]] * 2)
+    return sd, eng, ctx, tid
+
+
+@pytest.mark.parametrize("hw", [(32, 32), (16, 64)])
+def test_unet_forward(setup, hw):
+    sd, eng, ctx, tid = setup
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 4, *hw, generator=g)
+    te = ctx.mean(1)
+    bsd = {k: v.to(torch.bfloat16) for k, v in sd.items()}
+    ref32 = D.unet_forward(sd, TINY_UNET, x.bfloat16().float(), 981.0, ctx.bfloat16().float(), te.bfloat16().float(), tid)
+    ref16 = D.unet_forward(bsd, TINY_UNET, x.bfloat16(), 981.0, ctx.bfloat16(), te.bfloat16(), tid).float()
+    out = eng.unet_forward(x.cuda(), 981.0, ctx.cuda(), te.cuda(), tid.cuda()).float().cpu()
+    budget = max(2.0 * O.rel_err(ref16, ref32), 2e-2)  # what bf16 storage costs the oracle itself
+    assert O.rel_err(out, ref32) < budget, (O.rel_err(out, ref32), O.rel_err(ref16, ref32))
+
+
+def test_denoise_loop(setup):
+    """5 CFG + Euler steps (graph-captured from the 2nd step on) vs the oracle loop in fp32."""
+    sd, eng, ctx, tid = setup
+    steps, guidance = 5, 3.0
+    ts, sig, init_sigma = D.euler_tables(steps)
+    g = torch.Generator().manual_seed(13)
+    lat0 = torch.randn(1, 4, 32, 32, generator=g) * init_sigma
+    te = ctx.mean(1)
+    ref = D.denoise_loop(lambda x, t, c, e, i: D.unet_forward(sd, TINY_UNET, x, t, c, e, i), lat0.clone(), ctx, te, tid,
+                         steps, guidance)
+    lat = lat0.clone().cuda().contiguous()
+    ctx_d, te_d, tid_d = ctx.to(torch.bfloat16).cuda(), te.to(torch.bfloat16).cuda(), tid.to(torch.int32).cuda()
+    for i in range(steps):
+        eng.denoise_step(lat, float(sig[i]), float(sig[i + 1]), float(ts[i]), guidance, ctx_d, te_d, tid_d)
+    assert O.rel_err(lat.cpu(), ref) < 3e-2
+
+
+def test_denoise_graph_matches_eager(setup):
+    import os
+    sd, eng, ctx, tid = setup
+    ts, sig, init_sigma = D.euler_tables(4)
+    lat0 = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(14)) * init_sigma
+    te = ctx.mean(1)
+    ctx_d, te_d, tid_d = ctx.to(torch.bfloat16).cuda(), te.to(torch.bfloat16).cuda(), tid.to(torch.int32).cuda()
+    outs = []
+    lat = lat0.clone().cuda().contiguous()
+    for mode in ("0", "1"):
+        os.environ["EMU_NO_GRAPH"] = mode
+        lat.copy_(lat0)
+        for i in range(4):
+            eng.denoise_step(lat, float(sig[i]), float(sig[i + 1]), float(ts[i]), 3.0, ctx_d, te_d, tid_d)
+        outs.append(lat.clone())
+    os.environ.pop("EMU_NO_GRAPH", None)
+    assert torch.equal(outs[0], outs[1])
