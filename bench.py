@@ -202,6 +202,139 @@ def workload_config(n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
+# second half of the headline metric: Emu2-Gen denoise steps/s (BASELINE.json configs[2])
+# ------------------------------------------------------------------------------------------------
+UNET_FLOP_PER_SAMPLE_STEP = 6.74e12  # 6.74 TFLOP per sample per UNet forward at 1024x1024
+
+
+def emu2_unet_json():
+    return dict(in_channels=4, out_channels=4, block_out_channels=[320, 640, 1280], layers_per_block=2,
+                transformer_layers_per_block=[1, 2, 10], attention_head_dim=[5, 10, 20], cross_attention_dim=1792,
+                down_block_types=["DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"],
+                use_linear_projection=True, addition_time_embed_dim=256, projection_class_embeddings_input_dim=3328,
+                norm_num_groups=32, norm_eps=1e-5)
+
+
+def unet_param_shapes(cfg):
+    """(key, shape) of every UNet parameter, diffusers naming (mirrors emu_unet_configure's module tree)."""
+    boc, lpb, cd = cfg["block_out_channels"], cfg["layers_per_block"], cfg["cross_attention_dim"]
+    tl = [t if "CrossAttn" in d else 0 for t, d in zip(cfg["transformer_layers_per_block"], cfg["down_block_types"])]
+    nb, temb = len(boc), boc[0] * 4
+    out = []
+
+    def lin(p, o, i, bias=True):
+        out.append((p + ".weight", (o, i)))
+        if bias:
+            out.append((p + ".bias", (o,)))
+
+    def cv(p, o, i, k=3):
+        out.append((p + ".weight", (o, i, k, k)))
+        out.append((p + ".bias", (o,)))
+
+    def nrm(p, c):
+        out.append((p + ".weight", (c,)))
+        out.append((p + ".bias", (c,)))
+
+    def resnet(p, cin, cout):
+        nrm(p + "norm1", cin); cv(p + "conv1", cout, cin); lin(p + "time_emb_proj", cout, temb)
+        nrm(p + "norm2", cout); cv(p + "conv2", cout, cout)
+        if cin != cout:
+            cv(p + "conv_shortcut", cout, cin, 1)
+
+    def tfm(p, c, n):
+        nrm(p + "norm", c); lin(p + "proj_in", c, c)
+        for k in range(n):
+            q = "%stransformer_blocks.%d." % (p, k)
+            for a, kd in (("attn1.", c), ("attn2.", cd)):
+                lin(q + a + "to_q", c, c, False); lin(q + a + "to_k", c, kd, False); lin(q + a + "to_v", c, kd, False)
+                lin(q + a + "to_out.0", c, c)
+            for n_ in ("norm1", "norm2", "norm3"):
+                nrm(q + n_, c)
+            lin(q + "ff.net.0.proj", 8 * c, c); lin(q + "ff.net.2", c, 4 * c)
+        lin(p + "proj_out", c, c)
+
+    cv("conv_in", boc[0], cfg["in_channels"])
+    lin("time_embedding.linear_1", temb, boc[0]); lin("time_embedding.linear_2", temb, temb)
+    lin("add_embedding.linear_1", temb, cfg["projection_class_embeddings_input_dim"]); lin("add_embedding.linear_2", temb, temb)
+    cin, skip = boc[0], [boc[0]]
+    for i in range(nb):
+        for j in range(lpb):
+            resnet("down_blocks.%d.resnets.%d." % (i, j), cin, boc[i]); cin = boc[i]
+            if tl[i]:
+                tfm("down_blocks.%d.attentions.%d." % (i, j), cin, tl[i])
+            skip.append(cin)
+        if i < nb - 1:
+            cv("down_blocks.%d.downsamplers.0.conv" % i, cin, cin); skip.append(cin)
+    resnet("mid_block.resnets.0.", cin, cin)
+    if tl[-1]:
+        tfm("mid_block.attentions.0.", cin, tl[-1])
+    resnet("mid_block.resnets.1.", cin, cin)
+    for i in range(nb):
+        ri = nb - 1 - i
+        for j in range(lpb + 1):
+            resnet("up_blocks.%d.resnets.%d." % (i, j), cin + skip.pop(), boc[ri]); cin = boc[ri]
+            if tl[ri]:
+                tfm("up_blocks.%d.attentions.%d." % (i, j), cin, tl[ri])
+        if i < nb - 1:
+            cv("up_blocks.%d.upsamplers.0.conv" % i, cin, cin)
+    nrm("conv_norm_out", boc[0]); cv("conv_out", cfg["out_channels"], boc[0])
+    return out
+
+
+def run_denoise(steps=50, warm_loops=1, timed_loops=1, batch=1, hw=128, seed=0):
+    """50 Euler steps of the Emu2-Gen denoise loop (CFG, guidance 3, 1024x1024 -> latent 128x128) on random-init weights
+    of the published UNet topology; returns (steps_per_s, ms_per_step, launches_per_step)."""
+    from emu_b200 import _lib
+    from emu_b200.emu2.diffusion import unet_config_from_json
+    from emu_b200.emu2.scheduler import EulerDiscreteScheduler
+    cfg = emu2_unet_json()
+    eng = _lib.Engine(_lib.EmuConfig())
+    eng.unet_configure(unet_config_from_json(cfg))
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    for k, shp in unet_param_shapes(cfg):
+        if k.endswith(".bias"):
+            t = torch.zeros(shp, device="cuda", dtype=torch.bfloat16)
+        elif len(shp) == 1:
+            t = torch.ones(shp, device="cuda", dtype=torch.bfloat16)
+        else:
+            fan = 1
+            for d in shp[1:]:
+                fan *= d
+            t = (torch.randn(shp, generator=g, device="cuda", dtype=torch.float32) * (fan ** -0.5)).to(torch.bfloat16)
+        eng.load_tensor("unet." + k, t)
+        del t
+    sched = EulerDiscreteScheduler()
+    sched.set_timesteps(steps)
+    ts, sig = sched.timesteps, sched.sigmas
+    ctx = torch.randn(2 * batch, 64, cfg["cross_attention_dim"], generator=g, device="cuda").to(torch.bfloat16)
+    te = ctx.float().mean(1).to(torch.bfloat16).contiguous()
+    tid = torch.tensor([[1024, 1024, 0, 0, 1024, 1024]] * (2 * batch), dtype=torch.int32, device="cuda")
+    lat0 = torch.randn(batch, 4, hw, hw, generator=g, device="cuda") * sched.init_noise_sigma
+    lat = lat0.clone()
+
+    def loop():
+        lat.copy_(lat0)
+        for i in range(steps):
+            eng.denoise_step(lat, float(sig[i]), float(sig[i + 1]), float(ts[i]), 3.0, ctx, te, tid)
+
+    for _ in range(warm_loops):
+        loop()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(timed_loops):
+        loop()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / (timed_loops * steps)
+    launches = (_lib.launch_count() - l0) / (timed_loops * steps)
+    finite = bool(torch.isfinite(lat).all())
+    eng.close()
+    return 1000.0 / ms, ms, launches, finite
+
+
+# ------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
 def run_cuda(args):
@@ -320,6 +453,27 @@ def run_cuda(args):
             dist.destroy_process_group()
         return
 
+    denoise = None
+    if world == 1 and not args.small and not args.no_denoise:
+        try:
+            torch.cuda.empty_cache()
+            sps, ms_d, lpl, finite = run_denoise()
+            bf16_peak = 1739.4
+            try:
+                bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+            except Exception:
+                pass
+            ach = 2 * UNET_FLOP_PER_SAMPLE_STEP / (ms_d / 1000.0) / 1e12
+            denoise = {"metric": "emu2gen_denoise_steps_per_s", "value": sps, "unit": "steps/s", "ms_per_step": ms_d,
+                       "config": "SDXL-topology UNet 2.53B, 1024x1024 (latent 128x128), batch 1 + CFG (UNet batch 2), "
+                                 "50 Euler steps, guidance 3, ctx [2,64,1792], bf16, CUDA-graphed fused step",
+                       "gpu_launches_per_step": lpl, "finite": finite,
+                       "roofline": {"bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s",
+                                    "frac": ach / bf16_peak, "flops_per_step": 2 * UNET_FLOP_PER_SAMPLE_STEP,
+                                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"}}
+        except Exception as ex:
+            denoise = {"metric": "emu2gen_denoise_steps_per_s", "value": None, "error": repr(ex)}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -342,6 +496,7 @@ def run_cuda(args):
                      "decode_step_ms": step_ms_avg, "decode_step_ms_p50": step_ms[len(step_ms) // 2],
                      "algorithmic_bytes_per_step": alg_bytes},
         "cpu_baseline": cpu,
+        "denoise": denoise,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -356,6 +511,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--small", action="store_true", help="tiny plumbing config (debug only; never a bench number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-denoise", action="store_true", help="skip the Emu2-Gen denoise-loop measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

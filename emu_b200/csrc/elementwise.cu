@@ -259,8 +259,8 @@ int vit_pool(const bf16* x, bf16* out, int B, int G, int dim, int stride, cudaSt
 // cache is viewed as [outer, B, H*t_max*D-with-holes]; each thread owns one 16-byte column position
 // for ALL beams, so the in-place permutation needs no scratch.
 // ----------------------------------------------------------------------------------------------
-__global__ void kv_reorder_kernel(bf16* cache, const int* __restrict__ src_idx, int outer, int B, int H, int t_max,
-                                  int D, int n_tok) {
+__global__ void kv_reorder_kernel(bf16* cache, const int* __restrict__ src_idx, int outer, int B, int Bcap, int H,
+                                  int t_max, int D, int n_tok) {
   const int vec_per_tok = D >> 3;
   const long per_outer = (long)H * n_tok * vec_per_tok;
   const long total = (long)outer * per_outer;
@@ -272,7 +272,8 @@ __global__ void kv_reorder_kernel(bf16* cache, const int* __restrict__ src_idx, 
     const int t = (idx / vec_per_tok) % n_tok;
     const int h = (idx / ((long)vec_per_tok * n_tok)) % H;
     const long o = idx / per_outer;
-    uint4* base = reinterpret_cast<uint4*>(cache) + ((o * B * H + h) * (long)t_max + t) * vec_per_tok + v;
+    // the cache holds Bcap sequences per (layer, k/v) slab; only the first B are live
+    uint4* base = reinterpret_cast<uint4*>(cache) + ((o * Bcap * H + h) * (long)t_max + t) * vec_per_tok + v;
     const long bstride = (long)H * t_max * vec_per_tok;
     uint4 vals[8];
 #pragma unroll
@@ -283,11 +284,11 @@ __global__ void kv_reorder_kernel(bf16* cache, const int* __restrict__ src_idx, 
       if (b < B) base[b * bstride] = vals[b];
   }
 }
-int kv_reorder(bf16* cache, bf16*, const int* src_idx, int B, long outer, int n_used_tokens, int H, int D, int t_max,
+int kv_reorder(bf16* cache, int Bcap, const int* src_idx, int B, long outer, int n_used_tokens, int H, int D, int t_max,
                cudaStream_t st) {
   if (B > 8 || D % 8) return EMU_ERR_INVALID;
   if (n_used_tokens <= 0) return EMU_OK;
-  kv_reorder_kernel<<<8 * kNumSMs, 256, 0, st>>>(cache, src_idx, (int)outer, B, H, t_max, D, n_used_tokens);
+  kv_reorder_kernel<<<8 * kNumSMs, 256, 0, st>>>(cache, src_idx, (int)outer, B, Bcap, H, t_max, D, n_used_tokens);
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 

@@ -148,6 +148,7 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
 };
 static NcclApi g_nccl;
@@ -159,7 +160,8 @@ static bool nccl_load() {
   *(void**)(&g_nccl.CommInitRank) = dlsym(h, "ncclCommInitRank");
   *(void**)(&g_nccl.AllReduce) = dlsym(h, "ncclAllReduce");
   *(void**)(&g_nccl.CommDestroy) = dlsym(h, "ncclCommDestroy");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) return false;
+  *(void**)(&g_nccl.AllGather) = dlsym(h, "ncclAllGather");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather) return false;
   g_nccl.h = h;
   return true;
 }
@@ -168,6 +170,23 @@ int nccl_allreduce_bf16(EmuEngine* e, bf16* buf, size_t n, cudaStream_t st) {
   // ncclBfloat16 = 9, ncclSum = 0
   if (g_nccl.AllReduce(buf, buf, n, 9, 0, e->nccl_comm, st) != 0) return e->fail(EMU_ERR_NCCL, "ncclAllReduce failed");
   return EMU_OK;
+}
+
+// vocab-sharded logits: local [B, Vl] fp32 -> all ranks' shards [tp][B][Vl] -> logits [B, V]
+__global__ void logits_unshard_kernel(const float* __restrict__ g, float* out, int tp, int B, int Vl) {
+  const long total = (long)tp * B * Vl;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = i % Vl;
+    const int b = (i / Vl) % B;
+    const int r = i / ((long)Vl * B);
+    out[(long)b * tp * Vl + (long)r * Vl + v] = g[i];
+  }
+}
+int gather_logits(EmuEngine* e, const float* local, float* gathered, float* out, int B, cudaStream_t st) {
+  // ncclFloat32 = 7
+  if (g_nccl.AllGather(local, gathered, (size_t)B * e->Vl, 7, e->nccl_comm, st) != 0) return e->fail(EMU_ERR_NCCL, "ncclAllGather failed");
+  logits_unshard_kernel<<<2 * kNumSMs, 256, 0, st>>>(gathered, out, e->tp_size, B, e->Vl);
+  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
 }  // namespace emu
@@ -196,6 +215,14 @@ int EmuEngine::ensure(DevBuf& b, size_t bytes) {
 // ================================================================================================
 // life cycle
 // ================================================================================================
+extern "C" int emu_tp_head_range(int n_heads, int tp_size, int tp_rank, int* start, int* count) {
+  if (n_heads < 1 || tp_size < 1 || tp_rank < 0 || tp_rank >= tp_size || !start || !count) return EMU_ERR_INVALID;
+  const int base = n_heads / tp_size, rem = n_heads % tp_size;
+  *count = base + (tp_rank < rem ? 1 : 0);
+  *start = tp_rank * base + (tp_rank < rem ? tp_rank : rem);
+  return EMU_OK;
+}
+
 extern "C" int emu_nccl_unique_id(void* out128) {
   if (!nccl_load()) return EMU_ERR_NCCL;
   return g_nccl.GetUniqueId(out128) == 0 ? EMU_OK : EMU_ERR_NCCL;
@@ -215,12 +242,15 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
   e->tp_size = tp_size;
   const EmuConfig& c = e->cfg;
   if (c.llm_layers > 0) {
-    if (c.llm_heads % tp_size || c.llm_ffn % tp_size || c.llm_vocab % tp_size || c.llm_max_batch < 1 ||
+    if (c.llm_ffn % tp_size || c.llm_vocab % tp_size || c.llm_max_batch < 1 ||
         c.llm_max_batch > 8 || c.llm_hidden % 32 || c.llm_ffn % (32 * tp_size) || (c.llm_head_dim != 64 && c.llm_head_dim != 128)) {
       delete e;
       return EMU_ERR_UNSUPPORTED;
     }
-    e->Hl = c.llm_heads / tp_size;
+    // heads need not divide the TP degree (Emu2: 52 heads on 8 GPUs): every rank allocates ceil(H/tp) head slots,
+    // ranks past the remainder own one fewer real head and keep a zero-weight slot (exact: a zero head adds zero)
+    e->Hl = (c.llm_heads + tp_size - 1) / tp_size;
+    emu_tp_head_range(c.llm_heads, tp_size, tp_rank, &e->head_start, &e->head_count);
     e->Fl = c.llm_ffn / tp_size;
     e->Vl = c.llm_vocab / tp_size;
     e->layers.resize(c.llm_layers);
@@ -242,6 +272,8 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
     e->dec_attn_ws = (float*)e->dmalloc(attn_decode_workspace_bytes(Bm, e->Hl, c.llm_head_dim));
     e->dec_counters = (int*)e->dmalloc((size_t)Bm * e->Hl * sizeof(int));
     e->dec_logits_local = (float*)e->dmalloc((size_t)Bm * c.llm_vocab * sizeof(float));
+    e->dec_logits_shard = (float*)e->dmalloc((size_t)Bm * e->Vl * sizeof(float));
+    e->dec_logits_gather = (float*)e->dmalloc((size_t)Bm * c.llm_vocab * sizeof(float));
     if (!e->rope_cos || !e->rope_sin || !e->kv || !e->d_pos || !e->dec_h || !e->dec_q || !e->dec_attn || !e->dec_act ||
         !e->dec_tmp || !e->dec_attn_ws || !e->dec_counters || !e->dec_logits_local) {
       emu_engine_destroy(e);
@@ -358,17 +390,15 @@ static int load_llm(EmuEngine* e, const std::string& key, const bf16* src, const
   if (sub == "post_attention_layernorm.weight") return alloc_copy(e, &L.ln2, src, Hd, st);
   if (sub == "self_attn.q_proj.weight" || sub == "self_attn.k_proj.weight" || sub == "self_attn.v_proj.weight") {
     if (n != (long)c.llm_heads * D * Hd) return e->fail(EMU_ERR_INVALID, "qkv shape " + key);
-    if (!L.wqkv) L.wqkv = (bf16*)e->dmalloc((size_t)3 * Hl * D * Hd * 2);
-    if (!L.wqkv) return e->fail(EMU_ERR_NOMEM, "wqkv alloc");
+    EMU_TRY(alloc_zero(e, &L.wqkv, (size_t)3 * Hl * D * Hd, st));
     const int which = sub[10] == 'q' ? 0 : (sub[10] == 'k' ? 1 : 2);
     // q,k rows are pair-interleaved per head so a RoPE rotation pair is adjacent (see gemv.cu / elementwise.cu)
-    return pack_rows(L.wqkv, src, (long)Hl * D, Hd, Hd, Hd, (long)e->tp_rank * Hl * D, 0, which < 2 ? 1 : 0, D,
+    return pack_rows(L.wqkv, src, (long)e->head_count * D, Hd, Hd, Hd, (long)e->head_start * D, 0, which < 2 ? 1 : 0, D,
                      (long)which * Hl * D, 1, st);
   }
   if (sub == "self_attn.o_proj.weight") {
-    if (!L.wo) L.wo = (bf16*)e->dmalloc((size_t)Hd * Hl * D * 2);
-    if (!L.wo) return e->fail(EMU_ERR_NOMEM, "wo alloc");
-    return pack_rows(L.wo, src, Hd, Hl * D, (long)c.llm_heads * D, (long)Hl * D, 0, e->tp_rank * Hl * D, 0, D, 0, 1, st);
+    EMU_TRY(alloc_zero(e, &L.wo, (size_t)Hd * Hl * D, st));
+    return pack_rows(L.wo, src, Hd, e->head_count * D, (long)c.llm_heads * D, (long)Hl * D, 0, e->head_start * D, 0, D, 0, 1, st);
   }
   if (sub == "mlp.gate_proj.weight" || sub == "mlp.up_proj.weight") {
     if (n != (long)c.llm_ffn * Hd) return e->fail(EMU_ERR_INVALID, "mlp shape " + key);
@@ -719,10 +749,17 @@ extern "C" int emu_llm_prefill(EmuEngine* e, const void* inputs_embeds, const in
     g.W = e->lm_head; g.N = e->Vl; g.K = Hd;
     g.x = h + (size_t)(N - 1) * Hd; g.ldx = N * Hd; g.B = B;
     g.norm_w = e->final_norm; g.norm_eps = c.llm_rms_eps;
-    g.y = logits_last + (size_t)e->tp_rank * e->Vl; g.ldy = c.llm_vocab; g.out_fp32 = 1;
-    EMU_TRY(gemv_bf16(g, st));
+    g.out_fp32 = 1;
+    if (e->tp_size == 1) {
+      g.y = logits_last; g.ldy = c.llm_vocab;
+      EMU_TRY(gemv_bf16(g, st));
+    } else {
+      g.y = e->dec_logits_shard; g.ldy = e->Vl;
+      EMU_TRY(gemv_bf16(g, st));
+      EMU_TRY(gather_logits(e, e->dec_logits_shard, e->dec_logits_gather, logits_last, B, st));
+      count_launch(2);
+    }
     count_launch();
-    if (e->tp_size > 1) return e->fail(EMU_ERR_UNSUPPORTED, "TP logits gather not wired yet");
   }
   return EMU_OK;
 }
@@ -771,7 +808,7 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
     GemvArgs g;
     g.W = L.wgu; g.N = 2 * Fl; g.K = Hd; g.x = h; g.ldx = Hd; g.B = B;
     g.norm_w = L.ln2; g.norm_eps = c.llm_rms_eps; g.mode = EPI_SWIGLU; g.y = e->dec_act; g.ldy = Fl;
-    g.pdl = e->tp_size == 1 ? pdl : 0;
+    g.pdl = pdl;
     EMU_TRY(gemv_bf16(g, st));
     GemvArgs d;
     d.W = L.wdown; d.N = Hd; d.K = Fl; d.x = e->dec_act; d.ldx = Fl; d.B = B; d.pdl = pdl;
@@ -796,8 +833,16 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
     GemvArgs g;
     g.W = e->lm_head; g.N = e->Vl; g.K = Hd; g.x = h; g.ldx = Hd; g.B = B;
     g.norm_w = e->final_norm; g.norm_eps = c.llm_rms_eps;
-    g.y = lg + (size_t)e->tp_rank * e->Vl; g.ldy = c.llm_vocab; g.out_fp32 = 1; g.pdl = e->tp_size == 1 ? pdl : 0;
-    EMU_TRY(gemv_bf16(g, st));
+    g.out_fp32 = 1; g.pdl = pdl;
+    if (e->tp_size == 1) {
+      g.y = lg; g.ldy = c.llm_vocab;
+      EMU_TRY(gemv_bf16(g, st));
+    } else {
+      g.y = e->dec_logits_shard; g.ldy = e->Vl;
+      EMU_TRY(gemv_bf16(g, st));
+      EMU_TRY(gather_logits(e, e->dec_logits_shard, e->dec_logits_gather, lg, B, st));
+      nl += 2;
+    }
     ++nl;
     if (next_ids) {
       if (ban_id >= 0) {
@@ -823,15 +868,14 @@ extern "C" int emu_llm_decode(EmuEngine* e, const int32_t* token_ids, const void
   if (e->cur_len < 1) return e->fail(EMU_ERR_STATE, "decode before prefill");
   if (B != e->cache_B) return e->fail(EMU_ERR_STATE, "batch differs from cached batch");
   if (e->cur_len + 1 > c.llm_max_seq) return e->fail(EMU_ERR_INVALID, "KV cache full");
-  if (e->tp_size > 1 && (logits || next_ids)) return e->fail(EMU_ERR_UNSUPPORTED, "TP logits gather not wired yet");
   if (beam_src_idx) {
-    EMU_TRY(kv_reorder(e->kv, nullptr, beam_src_idx, B, (long)c.llm_layers * 2, e->cur_len, e->Hl, c.llm_head_dim,
+    EMU_TRY(kv_reorder(e->kv, c.llm_max_batch, beam_src_idx, B, (long)c.llm_layers * 2, e->cur_len, e->Hl, c.llm_head_dim,
                        c.llm_max_seq, st));
     count_launch();
   }
   int nl = 0;
   const char* no_graph = getenv("EMU_NO_GRAPH");  // debugging / parity switch: launch the step eagerly
-  const bool graphable = e->use_graphs && e->tp_size == 1 && !(no_graph && no_graph[0] == '1');
+  const bool graphable = e->use_graphs && !(no_graph && no_graph[0] == '1');  // NCCL collectives are graph-capturable
   if (!graphable) {
     EMU_TRY(decode_step_body(e, token_ids, embeds, B, logits, hidden, next_ids, ban_id, st, &nl));
     count_launch(nl);

@@ -44,7 +44,8 @@ struct EmuEngine {
   std::vector<void*> owned;  // every cudaMalloc the engine made
 
   // ---- LLaMA ----
-  int Hl = 0, Fl = 0, Vl = 0;  // local heads / ffn columns / vocab rows
+  int Hl = 0, Fl = 0, Vl = 0;  // local head slots / ffn columns / vocab rows
+  int head_start = 0, head_count = 0;  // real heads owned by this rank (head_count <= Hl)
   std::vector<emu::LlmLayer> layers;
   emu::bf16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
   emu::bf16 *rope_cos = nullptr, *rope_sin = nullptr;
@@ -59,6 +60,7 @@ struct EmuEngine {
   float* dec_attn_ws = nullptr;
   int* dec_counters = nullptr;
   float* dec_logits_local = nullptr;
+  float *dec_logits_shard = nullptr, *dec_logits_gather = nullptr;
   // prefill workspaces (grown on demand)
   emu::DevBuf pf_h, pf_xn, pf_qkv, pf_attn, pf_act, pf_tmp;
   // decode graphs keyed by the baked-in arguments

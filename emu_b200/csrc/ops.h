@@ -104,8 +104,8 @@ int vit_assemble(const bf16* patches, const bf16* cls, const bf16* pos, bf16* x,
                  cudaStream_t st);
 int vit_pool(const bf16* x /*[B,1+G*G,dim]*/, bf16* out /*[B,n_query,dim]*/, int B, int G, int dim, int stride,
              cudaStream_t st);
-int kv_reorder(bf16* cache, bf16* scratch, const int* src_idx, int B, long per_seq_elems, int n_used_tokens, int H,
-               int D, int t_max, cudaStream_t st);
+int kv_reorder(bf16* cache /*[outer][Bcap][H][t_max][D]*/, int Bcap, const int* src_idx, int B, long outer,
+               int n_used_tokens, int H, int D, int t_max, cudaStream_t st);
 int add_rows(const bf16* a, const bf16* b, bf16* out, long n, cudaStream_t st);
 
 }  // namespace emu

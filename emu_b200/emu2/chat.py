@@ -1,0 +1,129 @@
+"""Drop-in for the reference's ``emu.chat.EmuChatGeneration`` (Emu2/emu/chat.py:20-286): image transform, prompt
+assembly (plain / chat / grounding) and a call into ``EmuModel.generate`` — the host-side boundary of the
+image->text path.  Method names, argument order and defaults follow the reference."""
+import os.path as osp
+from typing import List, Optional
+
+import torch
+from PIL import Image
+
+from .conf import CLIPVisionCfg, TextDecoderCfg
+from .constants import (ASSISTANT_TOKEN, DEFAULT_EOS_TOKEN, DEFAULT_IMG_PLACEHOLDER, DEFAULT_VID_PLACEHOLDER,
+                        DEFAULT_VIDEO_TOKEN, EVA_IMAGE_SIZE, FAKE_VIDEO_END_TOKEN, GRD_SYMBOL, GROUND_SYSTEM_MESSAGE,
+                        OPENAI_DATASET_MEAN, OPENAI_DATASET_STD, SYSTEM_MESSAGE, USER_TOKEN)
+from .diffusion import image_transform
+from .emu import EmuModel
+
+
+class EmuChatGeneration:
+    def __init__(self, emu_model: EmuModel, eva_size=EVA_IMAGE_SIZE, eva_mean=OPENAI_DATASET_MEAN,
+                 eva_std=OPENAI_DATASET_STD, **kwargs):
+        self.emu_model = emu_model
+        self.eva_size, self.eva_mean, self.eva_std = eva_size, eva_mean, eva_std
+
+    def transform(self, img: Image.Image):
+        return image_transform(img, self.eva_size, self.eva_mean, self.eva_std)
+
+    # ---- Emu2/emu/chat.py:41-119 ----
+    @torch.no_grad()
+    def forward(self, inputs, is_grounding: bool = False, num_beams: int = 5, max_new_tokens: int = 10,
+                min_len: int = 1, do_sample: bool = False, penalty_alpha: Optional[float] = None,
+                top_p: Optional[float] = None, top_k: Optional[int] = None, temperature: Optional[float] = None,
+                length_penalty: float = -1, repetition_penalty: float = 1.0, synced_gpus: bool = False,
+                skip_special_tokens: bool = True, **kwargs):
+        assert isinstance(inputs, list), "inputs must be a list"
+        device, dtype = self.emu_model.device(), self.emu_model.dtype()
+        if isinstance(inputs[0], list):
+            assert len(inputs) % 2 == 1, "last message must be user input"
+            prep = self._prepare_chat_inputs(inputs, is_grounding, device, dtype)
+        else:
+            assert all(isinstance(i, (str, Image.Image)) for i in inputs), \
+                "input can't be list of list for normal generation"
+            prep = self._prepare_inputs(inputs, device, dtype)
+        text_prompt, image_prompt, video_prompt, image_placeholder, video_placeholder = prep
+        output = self.emu_model.generate(
+            text=text_prompt, image=image_prompt, video=video_prompt, image_placeholder=image_placeholder,
+            video_placeholder=video_placeholder, num_beams=num_beams, max_new_tokens=max_new_tokens, min_len=min_len,
+            do_sample=do_sample, penalty_alpha=penalty_alpha, top_p=top_p, top_k=top_k, temperature=temperature,
+            length_penalty=length_penalty, repetition_penalty=repetition_penalty, synced_gpus=synced_gpus,
+            skip_special_tokens=skip_special_tokens, **kwargs)
+        return output[0]
+
+    __call__ = forward
+
+    # ---- Emu2/emu/chat.py:121-157 ----
+    def _prepare_inputs(self, inputs, device=torch.device("cpu"), dtype=torch.float32,
+                        image_placeholder: str = DEFAULT_IMG_PLACEHOLDER, video_placeholder: str = DEFAULT_VID_PLACEHOLDER):
+        is_video = False
+        text_prompt, image_prompt, video_prompt = "", [], []
+        for x in inputs:
+            if isinstance(x, str) and x == FAKE_VIDEO_END_TOKEN:
+                is_video = False
+            elif isinstance(x, str):
+                if x == DEFAULT_VIDEO_TOKEN:
+                    is_video = True
+                text_prompt += x
+            elif is_video:
+                text_prompt += video_placeholder
+                video_prompt.append(self.transform(x))
+            else:
+                text_prompt += image_placeholder
+                image_prompt.append(self.transform(x))
+        image_prompt = torch.stack(image_prompt).to(device=device, dtype=dtype) if image_prompt else None
+        video_prompt = torch.stack(video_prompt).to(device=device, dtype=dtype) if video_prompt else None
+        return [text_prompt], image_prompt, video_prompt, image_placeholder, video_placeholder
+
+    # ---- Emu2/emu/chat.py:159-195 ----
+    def _prepare_chat_inputs(self, inputs, is_grounding: bool = False, device=torch.device("cpu"), dtype=torch.float32,
+                             image_placeholder: str = DEFAULT_IMG_PLACEHOLDER,
+                             video_placeholder: str = DEFAULT_VID_PLACEHOLDER):
+        text_prompt = GROUND_SYSTEM_MESSAGE if is_grounding else SYSTEM_MESSAGE
+        image_prompt, video_prompt = None, None
+        prev_r = None
+        for msg in inputs:
+            if prev_r == ASSISTANT_TOKEN:
+                text_prompt += f"{DEFAULT_EOS_TOKEN}{USER_TOKEN}: "
+                prev_r = USER_TOKEN
+            elif prev_r is None:
+                text_prompt += f" {USER_TOKEN}: "
+                prev_r = USER_TOKEN
+            else:
+                text_prompt += f" {ASSISTANT_TOKEN}: "
+                prev_r = ASSISTANT_TOKEN
+            text, image, video, _, _ = self._prepare_inputs(msg, device, dtype, image_placeholder, video_placeholder)
+            text_prompt += text[0]
+            if image is not None:
+                image_prompt = image if image_prompt is None else torch.cat([image_prompt, image])
+            if video is not None:
+                video_prompt = video if video_prompt is None else torch.cat([video_prompt, video])
+        text_prompt += f" {ASSISTANT_TOKEN}:"
+        if is_grounding:
+            text_prompt += GRD_SYMBOL
+        return [text_prompt], image_prompt, video_prompt, image_placeholder, video_placeholder
+
+    # ---- Emu2/emu/chat.py:197-232 ----
+    @classmethod
+    def from_config(cls, instruct: bool = False, llama_config_path: Optional[str] = None, tokenizer=None, **kwargs):
+        vc = CLIPVisionCfg(n_query=256, v_query=64) if instruct else CLIPVisionCfg()  # chat.py:215-232
+        tc = TextDecoderCfg(instruct=instruct) if llama_config_path is None else \
+            TextDecoderCfg(llama_config_path=llama_config_path, instruct=instruct)
+        return cls(emu_model=EmuModel(vc, tc, tokenizer=tokenizer, **kwargs))
+
+    @classmethod
+    def from_pretrained(cls, path: str, instruct: bool = False, dtype=torch.bfloat16, use_safetensors: bool = False,
+                        **kwargs):
+        ins = cls.from_config(instruct=instruct, **kwargs)
+        if use_safetensors:
+            from safetensors.torch import load_file
+            sd = load_file(path)
+        else:
+            sd = torch.load(path, map_location="cpu")
+        ins.emu_model.load_state_dict(sd, strict=True)
+        return ins
+
+    def multito(self, device_list):
+        """Layer-wise device placement of the reference (Emu2/emu/mixin.py) is replaced by one process per GPU with
+        tensor parallelism (tp_rank / tp_size of EmuModel); within one process this is a no-op."""
+        return self
+
+    multicuda = multito

@@ -71,6 +71,8 @@ int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size, const void
                       EmuEngine** out);
 void emu_engine_destroy(EmuEngine* e);
 const char* emu_last_error(EmuEngine* e);
+/* which real attention heads tensor-parallel rank `tp_rank` owns (heads need not divide tp_size: Emu2 has 52) */
+int emu_tp_head_range(int n_heads, int tp_size, int tp_rank, int* start, int* count);
 /* 128-byte ncclUniqueId for rank 0 to broadcast to the other ranks before emu_engine_create */
 int emu_nccl_unique_id(void* out128);
 

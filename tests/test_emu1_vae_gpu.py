@@ -28,7 +28,11 @@ def emu1_state_dict(vis, seed=0):
     sd["ln_visual.weight"] = 1 + 0.1 * torch.randn(W, generator=g)
     sd["ln_visual.bias"] = 0.05 * torch.randn(W, generator=g)
     sd["decoder.lm.stu_regress_head.weight"] = torch.randn(256, 256, generator=g) / 16
-    sd.update(D.random_state_dict(T.param_shapes(T5, W, 256, n_causal=8), seed=seed + 7))
+    cf = D.random_state_dict(T.param_shapes(T5, W, 256, n_causal=8), seed=seed + 7)
+    for k in cf:  # T5 attention is unscaled: the Mesh-TF init keeps q small so that the softmax is not saturated
+        if k.endswith("Attention.q.weight"):
+            cf[k] = cf[k] * 0.125
+    sd.update(cf)
     return sd
 
 

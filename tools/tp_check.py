@@ -1,0 +1,73 @@
+"""Tensor-parallel parity check: run under torchrun with N GPUs.
+
+Every rank builds the tiny Emu2 LLM with tp_size = WORLD_SIZE (NCCL communicator created inside libemu_b200.so from a
+unique id broadcast over torch.distributed), runs prefill + 4 decode steps, and rank 0 compares logits with the fp32
+CPU oracle.  Head count (3) is deliberately NOT divisible by 2 to exercise the zero-padded head slot.
+"""
+import ctypes
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from helpers import StubTokenizer, make_emu2_state_dict  # noqa: E402
+from emu_b200 import _lib  # noqa: E402
+from oracle import emu_oracle as O  # noqa: E402
+
+VIS = dict(image_size=56, patch_size=14, width=128, layers=1, head_width=32, mlp_ratio=4.0, n_query=4, v_query=4)
+LLAMA = dict(hidden_size=384, num_hidden_layers=2, num_attention_heads=3, intermediate_size=1024, rms_norm_eps=1e-6,
+             max_position_embeddings=256, vocab_size=32000, rope_theta=10000.0)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        raw = ctypes.create_string_buffer(128)
+        _lib.check(_lib.load().emu_nccl_unique_id(raw))
+        buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    uid = bytes(buf.cpu().numpy().tobytes())
+
+    from emu_b200.emu2.conf import CLIPVisionCfg, TextDecoderCfg
+    from emu_b200.emu2.emu import EmuModel
+    sd = make_emu2_state_dict(vision=VIS, llama=LLAMA, vocab=32272 if world in (1, 2, 4, 8) else 32272)
+    m = EmuModel(CLIPVisionCfg(**VIS), TextDecoderCfg(), tokenizer=StubTokenizer(), llama_config=LLAMA, max_batch=2,
+                 max_seq=64, tp_rank=rank, tp_size=world, nccl_uid=uid)
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(100, 30000, (2, 9), generator=g)
+    mask = torch.ones_like(ids)
+    mask[1, :3] = 0
+    emb = torch.nn.functional.embedding(ids, sd["decoder.lm.model.embed_tokens.weight"])
+    toks, logit_list = O.generate_greedy(sd, emb, mask, layers=2, heads=3, max_new_tokens=5, min_len=5, return_logits=True)
+    e_emb = m.engine.llm_embed(ids.cuda())
+    m.engine.llm_reset()
+    _, lg = m.engine.llm_prefill(e_emb, mask.cuda(), hf_positions=True, want_logits=True)
+    errs = [O.rel_err(lg.cpu(), logit_list[0])]
+    out = torch.empty_like(lg)
+    for s in range(1, len(logit_list)):
+        m.engine.llm_decode(token_ids=toks[:, s - 1].to(torch.int32).cuda().contiguous(), logits=out, B=2)
+        errs.append(O.rel_err(out.cpu(), logit_list[s]))
+    worst = torch.tensor([max(errs)], device="cuda")
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("TP%d logits rel err per step: %s" % (world, ["%.2e" % e for e in errs]), flush=True)
+    ok = float(worst) < 3e-2
+    dist.barrier()
+    dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+    if rank == 0:
+        print("TP_CHECK_OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()
