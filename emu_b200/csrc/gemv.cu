@@ -22,10 +22,16 @@
 // mma.sync.m16n8k16, so batch 1..8 (greedy .. 5-beam search) all run at the same bandwidth-bound speed.
 // Epilogues: bias / residual / SwiGLU / RoPE + KV-cache append.  Launched with programmatic dependent launch: the
 // ring is filled before griddepcontrol.wait, so HBM keeps streaming while the previous kernel drains.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ops.h"
 
 namespace emu {
+
+int gemv_tma_bf16(const GemvArgs& a, cudaStream_t st);  // gemv_tma.cu
+int gemv_tma_init();
+int gemv_reg_bf16(const GemvArgs& a, cudaStream_t st);
 
 constexpr int kGemvWarps = 8;
 constexpr int kGemvThreads = kGemvWarps * 32;
@@ -325,7 +331,11 @@ static int ensure_ws() {
   if (cudaMemset(g_counters, 0, (size_t)kWsTiles * sizeof(int)) != cudaSuccess) return EMU_ERR_CUDA;
   return EMU_OK;
 }
-int gemv_init() { return ensure_ws(); }
+int gemv_init() {
+  int rc = ensure_ws();
+  if (rc) return rc;
+  return gemv_tma_init();
+}
 
 template <int RT, bool KFULL>
 static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t st) {
@@ -348,7 +358,23 @@ static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t 
   return cudaLaunchKernelEx(&cfg, gemv_kernel<RT, KFULL>, p) == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
+// dispatcher: TMA-fed kernel whenever the shape fits, register-ring kernel otherwise (EMU_GEMV=reg forces the latter)
 int gemv_bf16(const GemvArgs& a, cudaStream_t st) {
+  if (a.B < 1 || a.B > 8 || a.N < 1 || a.K < 32 || (a.K % 32) || (a.ldx % 8)) return EMU_ERR_INVALID;
+  if ((a.mode == EPI_SWIGLU || a.mode == GEMV_ROPE_QKV) && (a.N % 16)) return EMU_ERR_INVALID;
+  static int force_reg = -1;
+  if (force_reg < 0) {
+    const char* v = getenv("EMU_GEMV");
+    force_reg = (v && v[0] == 'r') ? 1 : 0;
+  }
+  if (!force_reg) {
+    const int rc = gemv_tma_bf16(a, st);
+    if (rc != EMU_ERR_UNSUPPORTED) return rc;
+  }
+  return gemv_reg_bf16(a, st);
+}
+
+int gemv_reg_bf16(const GemvArgs& a, cudaStream_t st) {
   if (a.B < 1 || a.B > 8 || a.N < 1 || a.K < 32 || (a.K % 32) || (a.ldx % 8)) return EMU_ERR_INVALID;
   if ((a.mode == EPI_SWIGLU || a.mode == GEMV_ROPE_QKV) && (a.N % 16)) return EMU_ERR_INVALID;
   const int tiles = (a.N + 15) / 16;
