@@ -118,6 +118,9 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # reference / cpu_baseline arm: the oracle port of the reference's CPU path on a bounded sample
 # ------------------------------------------------------------------------------------------------
+_CPU_SD_CACHE = {}
+
+
 def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, ctx=75, threads=None, budget_s=25.0):
     """Time `tokens` single-token decode steps of `layers_sampled` real-shape LLaMA layers + lm_head in bf16 on the
     host cores with the oracle (oracle/emu_oracle.llama_forward, KV cache), extrapolate to all layers -> tok/s."""
@@ -126,8 +129,9 @@ def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, ctx=75, threads=Non
     torch.set_num_threads(threads)
     H, F, nh = lc["hidden_size"], lc["intermediate_size"], lc["num_attention_heads"]
     g = torch.Generator().manual_seed(0)
-    sd = {}
-    for l in range(layers_sampled):
+    key = (H, F, nh, vocab, layers_sampled)
+    sd = _CPU_SD_CACHE.get(key, {})
+    for l in range(layers_sampled if not sd else 0):
         p = f"decoder.lm.model.layers.{l}."
         for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
             sd[p + f"self_attn.{n}.weight"] = (torch.randn(H, H, generator=g) * 0.02).to(torch.bfloat16)
@@ -136,8 +140,10 @@ def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, ctx=75, threads=Non
         sd[p + "mlp.down_proj.weight"] = (torch.randn(H, F, generator=g) * 0.02).to(torch.bfloat16)
         sd[p + "input_layernorm.weight"] = torch.ones(H, dtype=torch.bfloat16)
         sd[p + "post_attention_layernorm.weight"] = torch.ones(H, dtype=torch.bfloat16)
-    sd["decoder.lm.model.norm.weight"] = torch.ones(H, dtype=torch.bfloat16)
-    sd["decoder.lm.lm_head.weight"] = (torch.randn(vocab, H, generator=g) * 0.02).to(torch.bfloat16)
+    if key not in _CPU_SD_CACHE:
+        sd["decoder.lm.model.norm.weight"] = torch.ones(H, dtype=torch.bfloat16)
+        sd["decoder.lm.lm_head.weight"] = (torch.randn(vocab, H, generator=g) * 0.02).to(torch.bfloat16)
+        _CPU_SD_CACHE[key] = sd
     cache = O.KVCache(layers_sampled)
     with torch.no_grad():
         x = (torch.randn(1, ctx, H, generator=g) * 0.02).to(torch.bfloat16)

@@ -13,6 +13,8 @@
 //   * ONE CTA per SM (grid = 148, ~100 KB smem, 64 regs): the next kernel's CTA fits beside it, so with PDL its ring is
 //     already full when this kernel drains — HBM never idles across kernel boundaries.
 // Ragged N and K tails cost nothing (TMA zero-fills out-of-bounds rows/columns).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -26,7 +28,7 @@ constexpr int kTRT = 2;                 // 16-row tiles per chunk
 constexpr int kTRows = 16 * kTRT;       // 32 rows
 constexpr int kTCols = 256;             // columns per chunk (4 TMA tiles of 64)
 constexpr int kTStageBytes = kTRows * kTCols * 2;  // 16 KB
-constexpr int kTStages = 5;
+constexpr int kTStages = 10;  // ring slots carved; p.nstages of them are used
 constexpr int kTMaxParts = 8;
 constexpr int kTWsGroups = 8192;
 
@@ -127,13 +129,13 @@ __device__ __noinline__ void gemv_tma_flush(const GemvTmaParams* sp, float* red,
   consumer_bar();
 }
 
-__global__ void __launch_bounds__(kTThreads, 1) gemv_tma_kernel(const __grid_constant__ CUtensorMap tmW,
+__global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_constant__ CUtensorMap tmW,
                                                                 const GemvTmaParams p) {
   const GemvArgs& a = p.a;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;                                                   // kTStages x 16 KB
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + kTStages * kTStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + p.nstages * kTStageBytes);
   uint64_t* empty_bar = full_bar + kTStages;
   float* red = reinterpret_cast<float*>(empty_bar + kTStages);            // [8 warps][kTRT*128]
   float* fin = red + kTW * kTRT * 128;                                    // [kTRT*128]
@@ -312,6 +314,11 @@ int gemv_tma_init() {
   if (cudaMemset(g_tcounters, 0, (size_t)kTWsGroups * sizeof(int)) != cudaSuccess) return EMU_ERR_CUDA;
   if (cudaFuncSetAttribute(gemv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
     return EMU_ERR_CUDA;
+  // ask for the largest shared-memory carve-out so that this kernel's CTA and its PDL successor's CTA (2 x ~105 KB)
+  // can be resident on one SM at the same time
+  if (cudaFuncSetAttribute(gemv_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) !=
+      cudaSuccess)
+    return EMU_ERR_CUDA;
   return EMU_OK;
 }
 
@@ -320,6 +327,10 @@ int gemv_tma_bf16(const GemvArgs& a, cudaStream_t st) {
   if (a.K % 8 || (reinterpret_cast<uintptr_t>(a.W) & 15)) return EMU_ERR_UNSUPPORTED;
   const int groups = (a.N + kTRows - 1) / kTRows;
   if (groups > kTWsGroups) return EMU_ERR_UNSUPPORTED;
+  if (!g_tws) {  // first use must happen outside stream capture (the engine calls gemv_init() at create)
+    int rc = gemv_tma_init();
+    if (rc) return rc;
+  }
   GemvTmaParams p;
   p.a = a;
   p.kpad = (a.K + kTCols - 1) / kTCols * kTCols;
@@ -331,14 +342,23 @@ int gemv_tma_bf16(const GemvArgs& a, cudaStream_t st) {
   const size_t xs_bytes = (size_t)a.B * p.ldxs * 2;
   // the ring buffers are carved for kTStages; a CTA with a wide x uses fewer so that this kernel (<= ~110 KB) and its
   // PDL successor still fit one SM together
-  p.nstages = xs_bytes > 24 * 1024 ? 4 : kTStages;
-  const size_t smem = 1024 + (size_t)kTStages * kTStageBytes + 2 * kTStages * 8 + (size_t)(kTW + 1) * kTRT * 128 * 4 +
-                     xs_bytes + 64 - (size_t)(kTStages - p.nstages) * 0;
-  if (smem > 200 * 1024) return EMU_ERR_UNSUPPORTED;
-  if (!g_tws) {
-    int rc = gemv_tma_init();
-    if (rc) return rc;
+  static int env_stages = -1;
+  if (env_stages < 0) {
+    const char* v = getenv("EMU_GEMV_STAGES");
+    env_stages = v ? atoi(v) : 0;
   }
+  // default 8 stages = 128 KB in flight per SM.  Measured (profiles/r01_kernel_bench_tma_stages.txt): 8 stages reach
+  // 6.3 TB/s on the large projections and 182 us per decoder layer chained, 5 stages (which would let this CTA and its
+  // PDL successor co-reside) only 200 us: depth of prefetch beats co-residency
+  p.nstages = env_stages > 0 ? env_stages : 8;
+  if (p.nstages > kTStages) p.nstages = kTStages;
+  size_t smem;
+  for (;;) {  // shrink the ring until the CTA fits (wide x at batch > 1)
+    smem = 1024 + (size_t)p.nstages * kTStageBytes + 2 * kTStages * 8 + (size_t)(kTW + 1) * kTRT * 128 * 4 + xs_bytes + 64;
+    if (smem <= 200 * 1024 || p.nstages <= 3) break;
+    --p.nstages;
+  }
+  if (smem > 200 * 1024) return EMU_ERR_UNSUPPORTED;
   long grid = kNumSMs;
   if (grid > p.total) grid = p.total;
   const long max_grid = (long)groups * (kTMaxParts - 3);

@@ -49,3 +49,40 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def chain_bench(B=1, layers=8, iters=5):
+    """One decoder layer's four GEMVs back to back (PDL chained), distinct weights per layer so nothing hits in L2."""
+    H, F = 6656, 17920
+    Ws = []
+    for _ in range(layers):
+        Ws.append([torch.randn(3 * H, H, device="cuda", dtype=torch.bfloat16) * 0.02,
+                   torch.randn(H, H, device="cuda", dtype=torch.bfloat16) * 0.02,
+                   torch.randn(2 * F, H, device="cuda", dtype=torch.bfloat16) * 0.02,
+                   torch.randn(H, F, device="cuda", dtype=torch.bfloat16) * 0.02])
+    x = torch.randn(B, H, device="cuda", dtype=torch.bfloat16)
+    xf = torch.randn(B, F, device="cuda", dtype=torch.bfloat16)
+    nw = torch.ones(H, device="cuda", dtype=torch.bfloat16)
+
+    def run():
+        for w in Ws:
+            _lib.op_gemv(w[0], x, norm_w=nw, pdl=True)
+            _lib.op_gemv(w[1], x, residual=x, pdl=True)
+            _lib.op_gemv(w[2], x, norm_w=nw, mode=2, pdl=True)
+            _lib.op_gemv(w[3], xf, residual=x, pdl=True)
+    run()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(iters):
+        run()
+    ev1.record()
+    torch.cuda.synchronize()
+    us = ev0.elapsed_time(ev1) * 1000 / (iters * layers)
+    nbytes = 2 * (4 * H * H + 3 * H * F)
+    print("chain B=%d: %.1f us per layer (4 GEMVs), %.0f GB/s" % (B, us, nbytes / us / 1e3), flush=True)
+
+
+if __name__ == "__main__" and os.environ.get("EMU_CHAIN", "1") == "1":
+    chain_bench(1)
+    chain_bench(5)
