@@ -316,6 +316,7 @@ extern "C" void emu_engine_destroy(EmuEngine* e) {
   cudaDeviceSynchronize();
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->mega) mega_destroy(e->mega);
   if (e->unet) unet_destroy(e->unet);
   if (e->vae) vae_destroy(e->vae);
   if (e->cformer) cformer_destroy(e->cformer);
@@ -872,6 +873,15 @@ extern "C" int emu_llm_decode(EmuEngine* e, const int32_t* token_ids, const void
     EMU_TRY(kv_reorder(e->kv, c.llm_max_batch, beam_src_idx, B, (long)c.llm_layers * 2, e->cur_len, e->Hl, c.llm_head_dim,
                        c.llm_max_seq, st));
     count_launch();
+  }
+  // preferred path: the whole step in one persistent cooperative kernel (decode_mega.cu)
+  {
+    const int rc = decode_mega_step(e, token_ids, embeds, B, logits, hidden, next_ids, ban_id, st);
+    if (rc == EMU_OK) {
+      e->cur_len += 1;
+      return EMU_OK;
+    }
+    if (rc != EMU_ERR_UNSUPPORTED) return rc;
   }
   int nl = 0;
   const char* no_graph = getenv("EMU_NO_GRAPH");  // debugging / parity switch: launch the step eagerly

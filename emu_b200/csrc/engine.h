@@ -69,6 +69,7 @@ struct EmuEngine {
   std::map<GraphKey, int> graph_nodes;
   bool use_graphs = true;
   cudaStream_t cap_stream = nullptr;
+  void* mega = nullptr;  // persistent decode-step kernel state (decode_mega.cu)
 
   // ---- ViT ----
   std::vector<emu::VitBlock> vit;
@@ -95,6 +96,9 @@ namespace emu {
 // load-time helpers shared by the sub-model files
 int to_bf16_device(EmuEngine* e, const void* src, int dtype, size_t n, bf16** out, bool* temp, cudaStream_t st);
 int nccl_allreduce_bf16(EmuEngine* e, bf16* buf, size_t n, cudaStream_t st);
+int decode_mega_step(EmuEngine* e, const int32_t* token_ids, const void* embeds, int B, float* logits, void* hidden,
+                     int32_t* next_ids, int ban_id, cudaStream_t st);
+void mega_destroy(void* p);
 
 // sub-model entry points
 int unet_load_tensor(EmuEngine* e, const std::string& key, const bf16* src, const int64_t* shape, int ndim, cudaStream_t st);

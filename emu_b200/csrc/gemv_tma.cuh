@@ -1,0 +1,267 @@
+// emu_b200 — device-side building blocks of the TMA-fed skinny GEMM, shared by the one-GEMV kernel (gemv_tma.cu) and
+// the persistent decode-step kernel (decode_mega.cu).  See gemv_tma.cu for the design notes.
+#pragma once
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace emu {
+
+int make_tmap_2d(CUtensorMap* out, const void* base, long rows, long cols, long ld, int box_rows);  // gemm_tc.cu
+
+constexpr int kTW = 8;                  // consumer warps
+constexpr int kTThreads = (kTW + 1) * 32;  // + 1 producer warp
+constexpr int kTRT = 2;                 // 16-row tiles per chunk
+constexpr int kTRows = 16 * kTRT;       // 32 rows
+constexpr int kTCols = 256;             // columns per chunk (4 TMA tiles of 64)
+constexpr int kTStageBytes = kTRows * kTCols * 2;  // 16 KB
+constexpr int kTStages = 10;  // ring slots carved; p.nstages of them are used
+constexpr int kTMaxParts = 8;
+constexpr int kTWsGroups = 8192;
+
+struct GemvTmaParams {
+  GemvArgs a;
+  int ldxs;      // smem row stride of staged x (elements), = Kpad + 8
+  int kpad;      // K rounded up to 256
+  int cpt;       // chunks per row group
+  int nstages;   // ring depth actually used (<= kTStages; fewer when x is wide so two kernels still co-reside)
+  long total;    // total chunks
+  float* ws;     // [groups][kTMaxParts][kTRT*128]
+  int* counters;
+};
+
+static __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// finish k-segment [kc_lo, kc_hi] of row group grp (consumer threads only; `red` already holds per-warp partials)
+static __device__ __noinline__ void gemv_tma_flush(const GemvTmaParams* sp, float* red, float* fin, int* s_last_p, int grp,
+                                            int kc_lo, int kc_hi) {
+  const GemvTmaParams& p = *sp;
+  const GemvArgs& a = p.a;
+  const int N = a.N, B = a.B, CPT = p.cpt;
+  constexpr int nval = kTRT * 128;
+  const long G = gridDim.x;
+  const int tid = threadIdx.x;  // < 256
+  consumer_bar();
+  const bool whole = (kc_lo == 0 && kc_hi == CPT - 1);
+  bool do_epilogue = whole;
+  float v = 0.f;
+#pragma unroll
+  for (int w = 0; w < kTW; ++w) v += red[w * nval + tid];
+  if (whole) {
+    fin[tid] = v;
+  } else {
+    const long first_chunk = (long)grp * CPT;
+    const int first_owner = (int)(((first_chunk + 1) * G - 1) / p.total);
+    const int last_owner = (int)(((first_chunk + CPT) * G - 1) / p.total);
+    const int nparts = last_owner - first_owner + 1;
+    const int my = (int)blockIdx.x - first_owner;
+    float* wt = p.ws + ((long)grp * kTMaxParts) * nval;
+    wt[my * nval + tid] = v;
+    __threadfence();
+    consumer_bar();
+    if (tid == 0) {
+      const int prev = atomicAdd(&p.counters[grp], 1);
+      *s_last_p = (prev == nparts - 1);
+      if (prev == nparts - 1) p.counters[grp] = 0;
+    }
+    consumer_bar();
+    do_epilogue = *s_last_p != 0;
+    if (do_epilogue) {
+      __threadfence();
+      float s = 0.f;
+      for (int q = 0; q < nparts; ++q) s += __ldcg(&wt[q * nval + tid]);  // fixed order: deterministic
+      fin[tid] = s;
+    }
+  }
+  if (do_epilogue) {
+    consumer_bar();
+    const int rt = tid >> 7, r = tid & 15, b = (tid >> 4) & 7;
+    const float* f = fin + rt * 128;
+    const int nrow = (grp * kTRT + rt) * 16 + r;
+    if (b < B && nrow < N) {
+      if (a.mode == EPI_NONE) {
+        float o = f[r * 8 + b];
+        if (a.bias) o += __bfloat162float(a.bias[nrow]);
+        if (a.residual)
+          o = round_bf16(o) + __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(a.residual) + (long)b * a.ldr + nrow) << 16);
+        if (a.out_fp32) reinterpret_cast<float*>(a.y)[(long)b * a.ldy + nrow] = o;
+        else reinterpret_cast<bf16*>(a.y)[(long)b * a.ldy + nrow] = __float2bfloat16_rn(o);
+      } else if (a.mode == EPI_SWIGLU) {
+        if (!(r & 1)) {
+          const float gate = round_bf16(f[r * 8 + b]), up = round_bf16(f[(r + 1) * 8 + b]);
+          reinterpret_cast<bf16*>(a.y)[(long)b * a.ldy + (nrow >> 1)] = __float2bfloat16_rn(round_bf16(silu(gate)) * up);
+        }
+      } else {  // GEMV_ROPE_QKV
+        const int D = a.head_dim, H = a.n_heads;
+        const int hh = nrow / D, i = nrow - hh * D;
+        const int slot = a.pos[b];
+        if (hh < 2 * H) {
+          if (!(r & 1)) {
+            const float x1 = round_bf16(f[r * 8 + b]), x2 = round_bf16(f[(r + 1) * 8 + b]);
+            const int rp = slot - (a.pos_off ? a.pos_off[b] : 0);
+            const float c = __bfloat162float(a.rope_cos[(long)rp * (D / 2) + (i >> 1)]);
+            const float s = __bfloat162float(a.rope_sin[(long)rp * (D / 2) + (i >> 1)]);
+            const float o1 = round_bf16(x1 * c) + round_bf16(-x2 * s);
+            const float o2 = round_bf16(x2 * c) + round_bf16(x1 * s);
+            bf16* dst;
+            if (hh < H) dst = reinterpret_cast<bf16*>(a.y) + (long)b * a.ldy + nrow;
+            else dst = a.k_cache + (((long)b * H + (hh - H)) * a.t_max + slot) * D + i;
+            *reinterpret_cast<uint32_t*>(dst) = pack_bf16(o1, o2);
+          }
+        } else {
+          a.v_cache[(((long)b * H + (hh - 2 * H)) * a.t_max + slot) * D + i] = __float2bfloat16_rn(f[r * 8 + b]);
+        }
+      }
+    }
+  }
+  consumer_bar();
+}
+
+
+// ---- producer: stream this CTA's chunk range [c0, c1) of one weight matrix through the ring ----
+static __device__ __forceinline__ void tma_produce(const CUtensorMap* tm, int cpt, long c0, long c1, uint8_t* ring,
+                                                   uint64_t* full_bar, uint64_t* empty_bar, int nstages, int& stage,
+                                                   uint32_t& phase) {
+  int grp = (int)(c0 / cpt), kc = (int)(c0 % cpt);
+  for (long i = c0; i < c1; ++i) {
+    mbar_wait(&empty_bar[stage], phase ^ 1);
+    uint8_t* dst = ring + stage * kTStageBytes;
+    mbar_expect_tx(&full_bar[stage], kTStageBytes);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      tma_load_2d(dst + j * (kTRows * 128), tm, &full_bar[stage], kc * kTCols + j * 64, grp * kTRows);
+    if (++stage == nstages) { stage = 0; phase ^= 1; }
+    if (++kc == cpt) { kc = 0; ++grp; }
+  }
+}
+
+// ---- consumers: stage x (optionally RMS-normalised, zero padded to kpad) into shared memory ----
+static __device__ __forceinline__ void tma_stage_x(const GemvTmaParams& p, bf16* xs, float (*s_ss)[8], float* s_rstd) {
+  const GemvArgs& a = p.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = a.K, B = a.B;
+  const int vec_per_row = K >> 3, vec_pad = p.kpad >> 3;
+  if (a.norm_w != nullptr) {
+    float ss[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) ss[b] = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const uint4* src = reinterpret_cast<const uint4*>(a.x + (long)b * a.ldx);
+      float s = 0.f;
+      for (int i = threadIdx.x; i < vec_per_row; i += 256) {
+        const uint4 v = __ldcg(src + i);  // activations may have been produced by other CTAs of this very kernel
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float lo = bf16_lo(w4[j]), hi = bf16_hi(w4[j]);
+          s += lo * lo + hi * hi;
+        }
+      }
+      ss[b] = warp_sum(s);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int b = 0; b < 8; ++b) s_ss[warp][b] = ss[b];
+    }
+    consumer_bar();
+    if (threadIdx.x < 8) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kTW; ++w) tot += s_ss[w][threadIdx.x];
+      s_rstd[threadIdx.x] = rsqrtf(tot / (float)K + a.norm_eps);
+    }
+    consumer_bar();
+  }
+  for (int b = 0; b < B; ++b) {
+    const float rstd = a.norm_w ? s_rstd[b] : 1.f;
+    const uint4* src = reinterpret_cast<const uint4*>(a.x + (long)b * a.ldx);
+    const uint4* wsrc = reinterpret_cast<const uint4*>(a.norm_w);
+    uint4* dst = reinterpret_cast<uint4*>(xs + (long)b * p.ldxs);
+    for (int i = threadIdx.x; i < vec_pad; i += 256) {
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (i < vec_per_row) {
+        const uint4 v = __ldcg(src + i);
+        if (a.norm_w) {
+          const uint4 w = wsrc[i];
+          const uint32_t v4[4] = {v.x, v.y, v.z, v.w}, w4[4] = {w.x, w.y, w.z, w.w};
+          uint32_t o4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
+            o4[j] = pack_bf16(round_bf16(bf16_lo(v4[j]) * rstd) * bf16_lo(w4[j]),
+                              round_bf16(bf16_hi(v4[j]) * rstd) * bf16_hi(w4[j]));
+          o = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        } else {
+          o = v;
+        }
+      }
+      dst[i] = o;
+    }
+  }
+  consumer_bar();
+}
+
+// ---- consumers: pull this CTA's chunks [c0, c1) out of the ring, mma them against xs, finish row groups ----
+static __device__ __forceinline__ void tma_consume(const GemvTmaParams* sp, long c0, long c1, uint8_t* ring,
+                                                   uint64_t* full_bar, uint64_t* empty_bar, float* red, float* fin,
+                                                   const bf16* xs, int* s_last, int& stage, uint32_t& phase) {
+  const GemvTmaParams& p = *sp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int B = p.a.B, CPT = p.cpt;
+  const int n = (int)(c1 - c0);
+  float acc[kTRT][4];
+#pragma unroll
+  for (int rt = 0; rt < kTRT; ++rt)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[rt][q] = 0.f;
+  // fragment addressing inside a 128B-swizzled [32 rows x 64 cols] TMA tile
+  const int tile_j = warp >> 1;                   // which 64-column tile of the chunk this warp reads
+  const int cbase = (warp & 1) * 4;               // first logical 16-byte chunk of this warp's 32 columns
+  const int lrow = lane & 15, lhalf = lane >> 4;  // ldmatrix.x4 lane -> (row, k-half)
+  const bool has_x = g < B;
+  const bf16* xrow = xs + (long)g * p.ldxs + warp * 32 + 2 * t;
+  int cp_grp = (int)(c0 / CPT), cp_kc = (int)(c0 % CPT);
+  int seg_lo = cp_kc;
+  for (int i = 0; i < n; ++i) {
+    mbar_wait(&full_bar[stage], phase);
+    const uint32_t tbase = smem_u32(ring + stage * kTStageBytes + tile_j * (kTRows * 128));
+    const bf16* xk = xrow + cp_kc * kTCols;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t bfr[2] = {0u, 0u};
+      if (has_x) {
+        bfr[0] = *reinterpret_cast<const uint32_t*>(xk + ks * 16);
+        bfr[1] = *reinterpret_cast<const uint32_t*>(xk + ks * 16 + 8);
+      }
+#pragma unroll
+      for (int rt = 0; rt < kTRT; ++rt) {
+        const int r = rt * 16 + lrow;
+        const int c = cbase + ks * 2 + lhalf;
+        uint32_t af[4];
+        ldmatrix_x4(af, tbase + r * 128 + ((c ^ (r & 7)) << 4));
+        mma_bf16_16816(acc[rt], af, bfr);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+    const bool grp_done = (cp_kc == CPT - 1) || (i == n - 1);
+    if (grp_done) {
+#pragma unroll
+      for (int rt = 0; rt < kTRT; ++rt) {
+        float* r = red + (warp * kTRT + rt) * 128;
+        r[g * 8 + 2 * t] = acc[rt][0];
+        r[g * 8 + 2 * t + 1] = acc[rt][1];
+        r[(g + 8) * 8 + 2 * t] = acc[rt][2];
+        r[(g + 8) * 8 + 2 * t + 1] = acc[rt][3];
+        acc[rt][0] = acc[rt][1] = acc[rt][2] = acc[rt][3] = 0.f;
+      }
+      gemv_tma_flush(sp, red, fin, s_last, cp_grp, seg_lo, cp_kc);
+    }
+    if (++cp_kc == CPT) { cp_kc = 0; ++cp_grp; }
+    if (grp_done) seg_lo = cp_kc;
+  }
+}
+
+}  // namespace emu
