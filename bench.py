@@ -438,13 +438,12 @@ def run_cuda(args):
     emb[ids_dev == 32003] = model._project_up(e.reshape(-1, e.shape[-1]))
     eng.llm_reset()
     _, logits = eng.llm_prefill(emb, mask_dev, hf_positions=True, want_logits=True)
-    out = torch.empty(NEW_TOKENS, 1, dtype=torch.int32, device="cuda")
-    out[0] = logits.argmax(-1).to(torch.int32)
+    ping = [logits.argmax(-1).to(torch.int32), torch.empty(1, dtype=torch.int32, device="cuda")]
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(NEW_TOKENS)]
     torch.cuda.synchronize()
     evs[0].record()
     for s in range(1, NEW_TOKENS):
-        eng.llm_decode(token_ids=out[s - 1], next_ids=out[s], ban_id=2, B=1)
+        eng.llm_decode(token_ids=ping[(s - 1) & 1], next_ids=ping[s & 1], ban_id=2, B=1)
         evs[s].record()
     torch.cuda.synchronize()
     step_ms = sorted(evs[s - 1].elapsed_time(evs[s]) for s in range(1, NEW_TOKENS))

@@ -60,6 +60,7 @@ struct MegaCtl {
   int ban_id;
   int* pos_rw;
   int nstages;
+  unsigned long long* prof;  // optional [nphases][2] globaltimer stamps of CTA 0 (EMU_MEGA_PROF=1)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -71,14 +72,15 @@ __device__ __forceinline__ float ldcg_bf16(const bf16* p) {
   return __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(p)) << 16);
 }
 
-// all consumer threads of all CTAs: nothing after the call is executed before every CTA has finished what precedes it
+// all consumer threads of all CTAs: nothing after the call is executed before every CTA has finished what precedes it.
+// bar.sync orders the CTA's writes before thread 0's release-add; the acquire-load + bar.sync order everybody's
+// later reads after it (PTX memory model cumulativity) — no separate membar needed on the critical path.
 __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned target) {
   consumer_bar();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    while (ld_acquire_u32(bar) < target) __nanosleep(32);
-    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    while (ld_acquire_u32(bar) < target) {
+    }
   }
   consumer_bar();
 }
@@ -261,8 +263,9 @@ __global__ void __launch_bounds__(kTThreads, 1) decode_mega_kernel(const MegaCtl
       for (int ph = 0; ph < c.nphases; ++ph) {
         const MegaPhase* P = &c.phases[ph];
         if (P->type != MP_GEMV) continue;
-        const long total = P->g.total;
-        const long c0 = (long)blockIdx.x * total / G, c1 = ((long)blockIdx.x + 1) * total / G;
+        const long total = P->g.total, ge = P->g.geff;
+        if ((long)blockIdx.x >= ge) continue;  // this matrix is shared by the first `geff` CTAs only
+        const long c0 = (long)blockIdx.x * total / ge, c1 = ((long)blockIdx.x + 1) * total / ge;
         tma_produce(&c.maps[P->tmap], P->g.cpt, c0, c1, ring, full_bar, empty_bar, c.nstages, stage, phase);
       }
     }
@@ -275,6 +278,11 @@ __global__ void __launch_bounds__(kTThreads, 1) decode_mega_kernel(const MegaCtl
   for (int ph = 0; ph < c.nphases; ++ph) {
     const MegaPhase* P = &c.phases[ph];
     if (ph > 0) grid_sync(c.bar, (unsigned)(++epoch * G));
+    if (c.prof && blockIdx.x == 0 && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      c.prof[2 * ph] = t;
+    }
     switch (P->type) {
       case MP_EMBED: {
         for (int b = blockIdx.x; b < c.B; b += (int)G) {
@@ -288,10 +296,12 @@ __global__ void __launch_bounds__(kTThreads, 1) decode_mega_kernel(const MegaCtl
       case MP_GEMV: {
         if (tid == 0) s_params = P->g;
         consumer_bar();
-        const long total = s_params.total;
-        const long c0 = (long)blockIdx.x * total / G, c1 = ((long)blockIdx.x + 1) * total / G;
-        tma_stage_x(s_params, xs, s_ss, s_rstd);
-        tma_consume(&s_params, c0, c1, ring, full_bar, empty_bar, red, fin, xs, &s_last, stage, phase);
+        const long total = s_params.total, ge = s_params.geff;
+        if ((long)blockIdx.x < ge) {
+          const long c0 = (long)blockIdx.x * total / ge, c1 = ((long)blockIdx.x + 1) * total / ge;
+          tma_stage_x(s_params, xs, s_ss, s_rstd);
+          tma_consume(&s_params, c0, c1, ring, full_bar, empty_bar, red, fin, xs, &s_last, stage, phase);
+        }
       } break;
       case MP_ATTN: {
         const int items = c.B * c.H * c.nsplit;
@@ -346,6 +356,11 @@ __global__ void __launch_bounds__(kTThreads, 1) decode_mega_kernel(const MegaCtl
         if (blockIdx.x == 0 && tid < 8) c.pos_rw[tid] += 1;  // slot of the next token
       } break;
     }
+    if (c.prof && blockIdx.x == 0 && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      c.prof[2 * ph + 1] = t;
+    }
   }
 }
 
@@ -370,6 +385,7 @@ struct MegaState {
   int* gemv_counters = nullptr;
   bool attr_set = false;
   int disabled = -1;
+  unsigned long long* d_prof = nullptr;
 };
 
 static MegaState* mega_state(EmuEngine* e) {
@@ -377,6 +393,21 @@ static MegaState* mega_state(EmuEngine* e) {
   return (MegaState*)e->mega;
 }
 void mega_destroy(void* p) { delete (MegaState*)p; }
+
+// debugging aid: copy CTA 0's per-phase timestamps of the last step to the host (ns); returns the phase count
+extern "C" int emu_debug_mega_profile(EmuEngine* e, unsigned long long* out, int* types, int max_phases) {
+  if (!e || !e->mega) return 0;
+  MegaState* ms = (MegaState*)e->mega;
+  if (!ms->d_prof || ms->plans.empty()) return 0;
+  const MegaPlan& pl = ms->plans.begin()->second;
+  const int n = pl.nphases < max_phases ? pl.nphases : max_phases;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, ms->d_prof, (size_t)n * 16, cudaMemcpyDeviceToHost);
+  std::vector<MegaPhase> ph(n);
+  cudaMemcpy(ph.data(), pl.d_phases, (size_t)n * sizeof(MegaPhase), cudaMemcpyDeviceToHost);
+  for (int i = 0; i < n; ++i) types[i] = ph[i].type * 100 + (ph[i].type == 0 ? ph[i].g.a.mode : 0);
+  return n;
+}
 
 static bf16* kv_slab(EmuEngine* e, int layer, int kv) {
   const EmuConfig& c = e->cfg;
@@ -396,6 +427,10 @@ static void fill_gemv(GemvTmaParams& g, int N, int K, const bf16* x, int ldx, in
   g.nstages = nstages;
   const int groups = (N + kTRows - 1) / kTRows;
   g.total = (long)groups * g.cpt;
+  long geff = kNumSMs;
+  if (geff > g.total) geff = g.total;
+  if (geff > (long)groups * (kTMaxParts - 3)) geff = (long)groups * (kTMaxParts - 3);
+  g.geff = (int)geff;
   g.ws = ws;
   g.counters = counters;
 }
@@ -405,8 +440,12 @@ int decode_mega_step(EmuEngine* e, const int32_t* token_ids, const void* embeds,
                      int32_t* next_ids, int ban_id, cudaStream_t st) {
   MegaState* ms = mega_state(e);
   {
-    const char* v = getenv("EMU_NO_MEGA");  // read every call: tests flip it to cover both paths
-    ms->disabled = (v && v[0] == '1') ? 1 : 0;
+    // Opt-in (EMU_MEGA=1): measured on B200 the grid barriers (~4.8 us x 302 per step) cost as much as the launch
+    // boundaries they replace (12.2 ms vs 11.6 ms per token for the CUDA-graphed multi-kernel step), see DESIGN.md.
+    // EMU_NO_MEGA=1 always wins.  Read every call: tests flip both to cover both paths.
+    const char* on = getenv("EMU_MEGA");
+    const char* off = getenv("EMU_NO_MEGA");
+    ms->disabled = (on && on[0] == '1' && !(off && off[0] == '1')) ? 0 : 1;
   }
   const EmuConfig& c = e->cfg;
   const int Hd = c.llm_hidden, D = c.llm_head_dim, Hl = e->Hl, Fl = e->Fl;
@@ -457,8 +496,10 @@ int decode_mega_step(EmuEngine* e, const int32_t* token_ids, const void* embeds,
     ms->attr_set = true;
   }
 
-  auto key = std::make_tuple(B, (const void*)token_ids, embeds, (const void*)logits, (const void*)hidden,
-                             (const void*)next_ids, ban_id);
+  // the plan only bakes in the logits buffer and which outputs exist; token/embeds/next-id pointers travel in MegaCtl
+  const float* lg_key = logits ? logits : e->dec_logits_local;
+  auto key = std::make_tuple(B, (const void*)lg_key, (const void*)nullptr, (const void*)nullptr,
+                             (const void*)(hidden ? e : nullptr), (const void*)((logits || next_ids) ? e : nullptr), 0);
   auto it = ms->plans.find(key);
   if (it == ms->plans.end()) {
     MegaPlan pl;
@@ -560,6 +601,10 @@ int decode_mega_step(EmuEngine* e, const int32_t* token_ids, const void* embeds,
   ctl.hidden = Hd; ctl.final_norm = e->final_norm; ctl.eps = c.llm_rms_eps; ctl.hidden_out = (bf16*)hidden;
   ctl.logits = logits ? logits : e->dec_logits_local; ctl.vocab = c.llm_vocab; ctl.next_ids = next_ids;
   ctl.ban_id = ban_id; ctl.pos_rw = e->d_pos; ctl.nstages = pl.nstages;
+  if (getenv("EMU_MEGA_PROF")) {
+    if (!ms->d_prof && cudaMalloc((void**)&ms->d_prof, 4096 * 16) != cudaSuccess) return e->fail(EMU_ERR_NOMEM, "prof alloc");
+    ctl.prof = pl.nphases <= 4096 ? ms->d_prof : nullptr;
+  }
   if (cudaMemsetAsync(ms->d_bar, 0, 4, st) != cudaSuccess) return e->fail(EMU_ERR_CUDA, "mega barrier reset");
   void* args[] = {(void*)&ctl};
   cudaError_t ce = cudaLaunchCooperativeKernel((void*)decode_mega_kernel, dim3(kNumSMs), dim3(kTThreads), args, pl.smem, st);

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_con
   __shared__ GemvTmaParams s_params;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long G = gridDim.x;
+  const long G = p.geff;  // == gridDim.x for this kernel
   const long c0 = (long)blockIdx.x * p.total / G, c1 = ((long)blockIdx.x + 1) * p.total / G;
   if (threadIdx.x == 0) {
     s_params = p;
@@ -117,6 +117,7 @@ int gemv_tma_bf16(const GemvArgs& a, cudaStream_t st) {
   if (grid > p.total) grid = p.total;
   const long max_grid = (long)groups * (kTMaxParts - 3);
   if (grid > max_grid) grid = max_grid;
+  p.geff = (int)grid;
   CUtensorMap tm;
   if (make_tmap_2d(&tm, a.W, a.N, a.K, a.K, kTRows) != EMU_OK) return EMU_ERR_UNSUPPORTED;
   cudaLaunchConfig_t cfg{};

@@ -25,7 +25,8 @@ struct GemvTmaParams {
   int ldxs;      // smem row stride of staged x (elements), = Kpad + 8
   int kpad;      // K rounded up to 256
   int cpt;       // chunks per row group
-  int nstages;   // ring depth actually used (<= kTStages; fewer when x is wide so two kernels still co-reside)
+  int nstages;   // ring depth actually used (<= kTStages)
+  int geff;      // number of CTAs that share this matrix's chunks (<= gridDim.x); CTAs >= geff get none
   long total;    // total chunks
   float* ws;     // [groups][kTMaxParts][kTRT*128]
   int* counters;
@@ -40,7 +41,7 @@ static __device__ __noinline__ void gemv_tma_flush(const GemvTmaParams* sp, floa
   const GemvArgs& a = p.a;
   const int N = a.N, B = a.B, CPT = p.cpt;
   constexpr int nval = kTRT * 128;
-  const long G = gridDim.x;
+  const long G = p.geff;
   const int tid = threadIdx.x;  // < 256
   consumer_bar();
   const bool whole = (kc_lo == 0 && kc_hi == CPT - 1);

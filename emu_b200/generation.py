@@ -22,11 +22,17 @@ def greedy_search(engine, inputs_embeds, attention_mask, max_new_tokens, eos_tok
     if min_length > 0:
         logits[:, eos_token_id] = float("-inf")
     out = torch.empty(max_new_tokens, B, dtype=torch.int32, device=dev)
-    out[0] = logits.argmax(-1).to(torch.int32)
+    # two fixed token buffers used alternately, so the engine sees only two argument sets (CUDA graphs / plans are
+    # keyed by their pointers); each step's ids are also copied into `out` device-to-device
+    ping = [torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.int32, device=dev)]
+    ping[0].copy_(logits.argmax(-1))
+    out[0].copy_(ping[0])
     n_done = 1
     for step in range(1, max_new_tokens):
         ban = eos_token_id if step < min_length else -1
-        engine.llm_decode(token_ids=out[step - 1], next_ids=out[step], ban_id=ban, B=B)
+        src, dst = ping[(step - 1) & 1], ping[step & 1]
+        engine.llm_decode(token_ids=src, next_ids=dst, ban_id=ban, B=B)
+        out[step].copy_(dst)
         n_done = step + 1
         if check_every and step % check_every == 0:
             if bool((out[:n_done] == eos_token_id).any(0).all()):

@@ -163,8 +163,9 @@ def test_decode_paths_agree(model, gold):
     ids, mask = gold["gen_input_ids"].cuda(), gold["gen_attention_mask"].cuda()
     emb = model.engine.llm_embed(ids)
     outs = {}
-    for name, env in (("mega", {"EMU_NO_MEGA": "0", "EMU_NO_GRAPH": "0"}), ("graph", {"EMU_NO_MEGA": "1", "EMU_NO_GRAPH": "0"}),
-                      ("eager", {"EMU_NO_MEGA": "1", "EMU_NO_GRAPH": "1"})):
+    for name, env in (("mega", {"EMU_MEGA": "1", "EMU_NO_MEGA": "0", "EMU_NO_GRAPH": "0"}),
+                      ("graph", {"EMU_MEGA": "0", "EMU_NO_MEGA": "1", "EMU_NO_GRAPH": "0"}),
+                      ("eager", {"EMU_MEGA": "0", "EMU_NO_MEGA": "1", "EMU_NO_GRAPH": "1"})):
         os.environ.update(env)
         model.engine.llm_reset()
         _, lg = model.engine.llm_prefill(emb, mask, hf_positions=True, want_logits=True)
@@ -175,8 +176,8 @@ def test_decode_paths_agree(model, gold):
             model.engine.llm_decode(token_ids=tok, logits=buf, next_ids=nxt, B=2)
             tok = nxt.clone()
         outs[name] = (buf.clone(), nxt.clone())
-    os.environ.pop("EMU_NO_GRAPH", None)
-    os.environ.pop("EMU_NO_MEGA", None)
+    for k in ("EMU_NO_GRAPH", "EMU_NO_MEGA", "EMU_MEGA"):
+        os.environ.pop(k, None)
     assert torch.equal(outs["graph"][0], outs["eager"][0])
     assert O.rel_err(outs["mega"][0], outs["graph"][0]) < 1e-2
     assert torch.equal(outs["mega"][1].cpu(), outs["mega"][0].argmax(-1).to(torch.int32).cpu())
