@@ -121,11 +121,16 @@ def measured_peaks():
 _CPU_SD_CACHE = {}
 
 
+_CPU_BEST_THREADS = None
+
+
 def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, ctx=75, threads=None, budget_s=25.0):
     """Time `tokens` single-token decode steps of `layers_sampled` real-shape LLaMA layers + lm_head in bf16 on the
     host cores with the oracle (oracle/emu_oracle.llama_forward, KV cache), extrapolate to all layers -> tok/s."""
     from oracle import emu_oracle as O
-    threads = threads or os.cpu_count()
+    global _CPU_BEST_THREADS
+    probe = threads is None and _CPU_BEST_THREADS is None
+    threads = threads or _CPU_BEST_THREADS or os.cpu_count()
     torch.set_num_threads(threads)
     H, F, nh = lc["hidden_size"], lc["intermediate_size"], lc["num_attention_heads"]
     g = torch.Generator().manual_seed(0)
@@ -149,6 +154,24 @@ def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, ctx=75, threads=Non
         x = (torch.randn(1, ctx, H, generator=g) * 0.02).to(torch.bfloat16)
         mask = torch.ones(1, ctx, dtype=torch.long)
         O.llama_forward(sd, x, mask, layers=layers_sampled, heads=nh, cache=cache)  # prefill (untimed)
+        if probe:
+            # torch's CPU bf16 matrix-vector kernels do not scale to every thread count: give the reference its best
+            # setting (all cores, half, a quarter ...) from a one-layer probe, once per process
+            best = None
+            e = (torch.randn(1, 1, H, generator=g) * 0.02).to(torch.bfloat16)
+            w = sd["decoder.lm.model.layers.0.mlp.gate_proj.weight"]
+            cands = sorted({max(1, os.cpu_count() // d) for d in (1, 2, 4, 8, 16)}, reverse=True)
+            for t in cands:
+                torch.set_num_threads(t)
+                torch.nn.functional.linear(e, w)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    torch.nn.functional.linear(e, w)
+                dt = time.perf_counter() - t0
+                if best is None or dt < best[0]:
+                    best = (dt, t)
+            threads = _CPU_BEST_THREADS = best[1]
+            torch.set_num_threads(threads)
         per_tok = []
         t_start = time.time()
         for i in range(tokens + 1):
@@ -168,8 +191,9 @@ def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, ctx=75, threads=Non
     head_s = sum(b for _, b in per_tok) / len(per_tok)
     tok_s = 1.0 / (layer_s * lc["num_hidden_layers"] + head_s)
     sample = ("%d real-shape LLaMA-33B decoder layers (h=%d, ffn=%d, %d heads) + lm_head, bf16, %d decode steps at "
-              "ctx %d via oracle/emu_oracle.py, per-layer time extrapolated x%d layers (ViT/prefill excluded)" %
-              (layers_sampled, H, F, nh, len(per_tok), ctx, lc["num_hidden_layers"]))
+              "ctx %d via oracle/emu_oracle.py, per-layer time extrapolated x%d layers (ViT/prefill excluded); torch threads = %d of %d host "
+              "cores (fastest of a thread-count probe)" %
+              (layers_sampled, H, F, nh, len(per_tok), ctx, lc["num_hidden_layers"], threads, os.cpu_count()))
     return tok_s, threads, sample
 
 
@@ -196,7 +220,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -503,12 +527,32 @@ def run_cuda(args):
         "cpu_baseline": cpu,
         "denoise": denoise,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route fd 1 to stderr for the run (NCCL and other native libraries print banners to stdout); the one JSON line
+    goes to the real stdout through emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

@@ -418,6 +418,16 @@ int attn_prefill(const AttnArgs& a, cudaStream_t st) {
   if ((a.q_ts % 8) || (a.k_ts % 8) || (a.v_ts % 8) || (a.q_hs % 8) || (a.k_hs % 8) || (a.v_hs % 8) ||
       (a.q_bs % 8) || (a.k_bs % 8) || (a.v_bs % 8) || (a.o_ts % 2) || (a.o_hs % 2) || (a.o_bs % 2))
     return EMU_ERR_INVALID;
+  // dense problems go to the tcgen05 kernel (attention_tc.cu); EMU_ATTN=legacy forces this file's mma.sync kernel
+  static int legacy = -1;
+  if (legacy < 0) {
+    const char* v = getenv("EMU_ATTN");
+    legacy = (v && v[0] == 'l') ? 1 : 0;
+  }
+  if (!legacy) {
+    const int rc = attn_prefill_tc(a, st);
+    if (rc != EMU_ERR_UNSUPPORTED) return rc;
+  }
   if (a.D <= 32) return launch_fa<32>(a, st);
   if (a.D <= 64) return launch_fa<64>(a, st);
   if (a.D <= 96) return launch_fa<96>(a, st);

@@ -172,6 +172,33 @@ int nccl_allreduce_bf16(EmuEngine* e, bf16* buf, size_t n, cudaStream_t st) {
   return EMU_OK;
 }
 
+// host-buffer helpers used once at engine creation to swap CUDA IPC handles (tp_exchange.cu)
+static int nccl_allgather_bytes(EmuEngine* e, const void* src, void* dst, size_t bytes) {
+  char* d = nullptr;
+  if (cudaMalloc((void**)&d, bytes * (e->tp_size + 1)) != cudaSuccess) return EMU_ERR_NOMEM;
+  int rc = EMU_OK;
+  if (cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = EMU_ERR_CUDA;
+  // ncclInt8 = 0
+  if (!rc && g_nccl.AllGather(d, d + bytes, bytes, 0, e->nccl_comm, nullptr) != 0) rc = EMU_ERR_NCCL;
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = EMU_ERR_CUDA;
+  if (!rc && cudaMemcpy(dst, d + bytes, bytes * e->tp_size, cudaMemcpyDeviceToHost) != cudaSuccess) rc = EMU_ERR_CUDA;
+  cudaFree(d);
+  return rc;
+}
+static int nccl_allreduce_min_int(EmuEngine* e, int* v) {
+  int* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(int)) != cudaSuccess) return EMU_ERR_NOMEM;
+  int rc = EMU_OK;
+  if (cudaMemcpy(d, v, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) rc = EMU_ERR_CUDA;
+  // ncclInt32 = 2, ncclMin = 3
+  if (!rc && g_nccl.AllReduce(d, d, 1, 2, 3, e->nccl_comm, nullptr) != 0) rc = EMU_ERR_NCCL;
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = EMU_ERR_CUDA;
+  if (!rc && cudaMemcpy(v, d, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rc = EMU_ERR_CUDA;
+  cudaFree(d);
+  return rc;
+}
+int tp_setup(EmuEngine* e) { return tp_exchange_setup(e, nccl_allgather_bytes, nccl_allreduce_min_int); }
+
 // vocab-sharded logits: local [B, Vl] fp32 -> all ranks' shards [tp][B][Vl] -> logits [B, V]
 __global__ void logits_unshard_kernel(const float* __restrict__ g, float* out, int tp, int B, int Vl) {
   const long total = (long)tp * B * Vl;
@@ -272,7 +299,8 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
     e->dec_attn_ws = (float*)e->dmalloc(attn_decode_workspace_bytes(Bm, e->Hl, c.llm_head_dim));
     e->dec_counters = (int*)e->dmalloc((size_t)Bm * e->Hl * sizeof(int));
     e->dec_logits_local = (float*)e->dmalloc((size_t)Bm * c.llm_vocab * sizeof(float));
-    e->dec_logits_shard = (float*)e->dmalloc((size_t)Bm * e->Vl * sizeof(float));
+    e->dec_logits_shard = (float*)e->dmalloc(((size_t)Bm * e->Vl + 4) * sizeof(float));
+    e->dec_part = (float*)e->dmalloc((size_t)Bm * c.llm_hidden * sizeof(float));
     e->dec_logits_gather = (float*)e->dmalloc((size_t)Bm * c.llm_vocab * sizeof(float));
     if (!e->rope_cos || !e->rope_sin || !e->kv || !e->d_pos || !e->dec_h || !e->dec_q || !e->dec_attn || !e->dec_act ||
         !e->dec_tmp || !e->dec_attn_ws || !e->dec_counters || !e->dec_logits_local) {
@@ -302,6 +330,10 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
       emu_engine_destroy(e);
       return EMU_ERR_NCCL;
     }
+    if (c.llm_layers > 0 && emu::tp_setup(e) != EMU_OK) {
+      emu_engine_destroy(e);
+      return EMU_ERR_NCCL;
+    }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) {
     emu_engine_destroy(e);
@@ -321,6 +353,7 @@ extern "C" void emu_engine_destroy(EmuEngine* e) {
   if (e->vae) vae_destroy(e->vae);
   if (e->cformer) cformer_destroy(e->cformer);
   for (void* p : e->owned) cudaFree(p);
+  tp_exchange_teardown(e);
   if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->nccl_comm);
   delete e;
 }
@@ -765,6 +798,25 @@ extern "C" int emu_llm_prefill(EmuEngine* e, const void* inputs_embeds, const in
   return EMU_OK;
 }
 
+// tensor-parallel tail of a row-parallel projection (o_proj / down_proj) in the decode loop: h += sum over ranks of W_r x_r.
+// Preferred: fp32 partial -> NVLink peer-memory push + flag + fixed-order reduce in ONE kernel (tp_exchange.cu);
+// otherwise NCCL all-reduce of the bf16 partial + add.
+static int row_parallel_tail(EmuEngine* e, GemvArgs& g, bf16* h, int B, int Hd, cudaStream_t st, int* nl) {
+  if (e->tp_p2p) {
+    g.y = e->dec_part; g.ldy = Hd; g.out_fp32 = 1;
+    EMU_TRY(gemv_bf16(g, st));
+    EMU_TRY(tp_reduce_add(e, e->dec_part, h, (long)B * Hd, g.pdl, st));
+    *nl += 1;
+    return EMU_OK;
+  }
+  g.y = e->dec_tmp; g.ldy = Hd;
+  EMU_TRY(gemv_bf16(g, st));
+  EMU_TRY(nccl_allreduce_bf16(e, e->dec_tmp, (size_t)B * Hd, st));
+  EMU_TRY(add_rows(h, e->dec_tmp, h, (long)B * Hd, st));
+  *nl += 2;
+  return EMU_OK;
+}
+
 // the kernels of one decode step (captured into a CUDA graph by emu_llm_decode)
 static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* embeds, int B, float* logits,
                             void* hidden, int32_t* next_ids, int ban_id, cudaStream_t st, int* n_launch) {
@@ -800,11 +852,7 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
       o.residual = h; o.ldr = Hd; o.y = h; o.ldy = Hd;
       EMU_TRY(gemv_bf16(o, st));
     } else {
-      o.y = e->dec_tmp; o.ldy = Hd;
-      EMU_TRY(gemv_bf16(o, st));
-      EMU_TRY(nccl_allreduce_bf16(e, e->dec_tmp, (size_t)B * Hd, st));
-      EMU_TRY(add_rows(h, e->dec_tmp, h, (long)B * Hd, st));
-      nl += 2;
+      EMU_TRY(row_parallel_tail(e, o, h, B, Hd, st, &nl));
     }
     GemvArgs g;
     g.W = L.wgu; g.N = 2 * Fl; g.K = Hd; g.x = h; g.ldx = Hd; g.B = B;
@@ -817,11 +865,7 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
       d.residual = h; d.ldr = Hd; d.y = h; d.ldy = Hd;
       EMU_TRY(gemv_bf16(d, st));
     } else {
-      d.y = e->dec_tmp; d.ldy = Hd;
-      EMU_TRY(gemv_bf16(d, st));
-      EMU_TRY(nccl_allreduce_bf16(e, e->dec_tmp, (size_t)B * Hd, st));
-      EMU_TRY(add_rows(h, e->dec_tmp, h, (long)B * Hd, st));
-      nl += 2;
+      EMU_TRY(row_parallel_tail(e, d, h, B, Hd, st, &nl));
     }
     nl += 5;
   }
@@ -841,8 +885,13 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
     } else {
       g.y = e->dec_logits_shard; g.ldy = e->Vl;
       EMU_TRY(gemv_bf16(g, st));
-      EMU_TRY(gather_logits(e, e->dec_logits_shard, e->dec_logits_gather, lg, B, st));
-      nl += 2;
+      if (e->tp_p2p) {
+        EMU_TRY(tp_gather_logits(e, e->dec_logits_shard, lg, B, pdl, st));
+        nl += 1;
+      } else {
+        EMU_TRY(gather_logits(e, e->dec_logits_shard, e->dec_logits_gather, lg, B, st));
+        nl += 2;
+      }
     }
     ++nl;
     if (next_ids) {

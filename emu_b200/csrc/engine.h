@@ -40,6 +40,11 @@ struct EmuEngine {
   EmuConfig cfg{};
   int tp_rank = 0, tp_size = 1;
   void* nccl_comm = nullptr;
+  // NVLink peer-memory exchange for the decode loop (tp_exchange.cu); tp_peer[r] = rank r's exchange buffer mapped here
+  bool tp_p2p = false;
+  float* tp_comm = nullptr;
+  float* tp_peer[8] = {};
+  float* dec_part = nullptr;  // this rank's fp32 partial of a row-parallel projection [Bmax, hidden]
   std::string err;
   std::vector<void*> owned;  // every cudaMalloc the engine made
 
@@ -96,6 +101,11 @@ namespace emu {
 // load-time helpers shared by the sub-model files
 int to_bf16_device(EmuEngine* e, const void* src, int dtype, size_t n, bf16** out, bool* temp, cudaStream_t st);
 int nccl_allreduce_bf16(EmuEngine* e, bf16* buf, size_t n, cudaStream_t st);
+int tp_exchange_setup(EmuEngine* e, int (*allgather_bytes)(EmuEngine*, const void*, void*, size_t),
+                      int (*allreduce_min_int)(EmuEngine*, int*));
+void tp_exchange_teardown(EmuEngine* e);
+int tp_reduce_add(EmuEngine* e, const float* part, bf16* h, long n_elem, int pdl, cudaStream_t st);
+int tp_gather_logits(EmuEngine* e, const float* shard, float* logits, int B, int pdl, cudaStream_t st);
 int decode_mega_step(EmuEngine* e, const int32_t* token_ids, const void* embeds, int B, float* logits, void* hidden,
                      int32_t* next_ids, int ban_id, cudaStream_t st);
 void mega_destroy(void* p);

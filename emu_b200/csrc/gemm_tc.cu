@@ -329,6 +329,40 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, int NB, int H, int W, int
   return r == CUDA_SUCCESS ? EMU_OK : EMU_ERR_CUDA;
 }
 
+// strided [B, N, H, D] bf16 view (attention operands) as a 4-D map; box = {64 d, box_rows tokens, 1 head, 1 batch}.
+// Dimensions are ordered by stride (head-before-token when heads are interleaved inside a token row, as in fused QKV
+// outputs); *head_first tells the kernel which coordinate order to use.  Head-dim padding and rows past N read as zero.
+int make_tmap_bnhd(CUtensorMap* out, const void* base, int D, long N, int H, int B, long ts, long hs, long bs, int box_rows,
+                   int* head_first) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return EMU_ERR_CUDA;
+  if ((ts % 8) || (hs % 8) || (bs % 8) || (reinterpret_cast<uintptr_t>(base) & 15)) return EMU_ERR_INVALID;
+  const bool hf = hs < ts;
+  *head_first = hf ? 1 : 0;
+  cuuint64_t bstride = bs > 0 ? (cuuint64_t)bs * 2 : 16;
+  cuuint64_t tstride = ts > 0 ? (cuuint64_t)ts * 2 : 16;
+  cuuint64_t hstride = hs > 0 ? (cuuint64_t)hs * 2 : 16;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4];
+  dims[0] = (cuuint64_t)D;
+  box[0] = 64;
+  if (hf) {
+    dims[1] = (cuuint64_t)H; dims[2] = (cuuint64_t)N; strides[0] = hstride; strides[1] = tstride;
+    box[1] = 1; box[2] = (cuuint32_t)box_rows;
+  } else {
+    dims[1] = (cuuint64_t)N; dims[2] = (cuuint64_t)H; strides[0] = tstride; strides[1] = hstride;
+    box[1] = (cuuint32_t)box_rows; box[2] = 1;
+  }
+  dims[3] = (cuuint64_t)B;
+  strides[2] = bstride;
+  box[3] = 1;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? EMU_OK : EMU_ERR_CUDA;
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;

@@ -89,6 +89,7 @@ struct AttnArgs {
   const float* bias = nullptr;    // [H, Nq, Nk] additive (T5 relative position bias) or null
 };
 int attn_prefill(const AttnArgs& a, cudaStream_t st);
+int attn_prefill_tc(const AttnArgs& a, cudaStream_t st);  // attention_tc.cu; EMU_ERR_UNSUPPORTED -> use attn_prefill's own kernel
 
 // ---- elementwise.cu ----
 int rmsnorm(const bf16* x, const bf16* w, bf16* y, int rows, int cols, float eps, int t5_style, cudaStream_t st);

@@ -116,6 +116,40 @@ def test_attn_prefill(cuda, B, Nq, Nk, H, D, causal):
     assert O.rel_err(out, ref) < TOL_BF16
 
 
+@pytest.mark.parametrize("B,Nq,Nk,H,D,causal,qscale,fused", [
+    (2, 512, 512, 3, 64, False, 1.0, True), (1, 1024, 1024, 2, 64, False, 6.0, False), (2, 300, 400, 2, 128, True, 1.0, False),
+    (1, 640, 640, 2, 128, True, 6.0, True), (1, 130, 700, 2, 64, False, 1.0, False), (1, 4096, 4096, 1, 64, False, 3.0, True),
+    (1, 1025, 1025, 2, 112, False, 6.0, True), (2, 256, 64, 2, 64, False, 1.0, False),
+])
+def test_attn_prefill_tc(cuda, B, Nq, Nk, H, D, causal, qscale, fused):
+    """tcgen05 flash attention (attention_tc.cu): multi-tile, ragged, causal with Nk > Nq and left padding, large score
+    ranges (exercises the lazy max / TMEM rescale path), and head-interleaved fused-QKV strides."""
+    from emu_b200 import _lib
+    if fused and Nq == Nk:
+        qkv = _rand((B, Nq, 3, H, D), 27)
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    else:
+        q, k, v = _rand((B, Nq, H, D), 20), _rand((B, Nk, H, D), 21), _rand((B, Nk, H, D), 22)
+    q = (q.float() * qscale).to(torch.bfloat16)
+    kv_start = torch.tensor([0, 7][:B], dtype=torch.int32) if causal else None
+    ref = O.op_attention(q, k, v, D ** -0.5, causal=causal, kv_start=kv_start)
+    if fused and Nq == Nk:
+        dq = (qkv.float() * torch.tensor([qscale, 1.0, 1.0]).view(1, 1, 3, 1, 1)).to(torch.bfloat16).cuda()
+        qc, kc, vc = dq[:, :, 0], dq[:, :, 1], dq[:, :, 2]
+    else:
+        qc, kc, vc = q.cuda(), k.cuda(), v.cuda()
+    out = _lib.op_attn_prefill(qc, kc, vc, D ** -0.5, causal=causal,
+                               kv_start=None if kv_start is None else kv_start.cuda()).cpu()
+    if kv_start is not None:
+        for b in range(B):
+            s = int(kv_start[b]) - (Nk - Nq)
+            if s > 0:
+                out[b, :s] = 0
+                ref[b, :s] = 0
+    assert torch.isfinite(out.float()).all()
+    assert O.rel_err(out, ref) < TOL_BF16
+
+
 def test_attn_prefill_bias(cuda):
     from emu_b200 import _lib
     B, N, H, D = 2, 32, 12, 64

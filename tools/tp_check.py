@@ -56,6 +56,11 @@ def main():
     for s in range(1, len(logit_list)):
         m.engine.llm_decode(token_ids=toks[:, s - 1].to(torch.int32).cuda().contiguous(), logits=out, B=2)
         errs.append(O.rel_err(out.cpu(), logit_list[s]))
+        # every rank must hold bitwise identical logits (fixed-order reduction), or greedy tokens could diverge
+        ref0 = out.clone()
+        dist.broadcast(ref0, 0)
+        if not torch.equal(ref0, out):
+            errs.append(1e9)
     worst = torch.tensor([max(errs)], device="cuda")
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)
     if rank == 0:
