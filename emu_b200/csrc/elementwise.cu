@@ -162,16 +162,26 @@ int embed_gather(const bf16* table, const int* ids, bf16* out, int n, int dim, c
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
-// first-max argmax per row of fp32 logits (greedy decoding)
-__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ logits, int cols, int* out) {
-  __shared__ float sv[8];
-  __shared__ int si[8];
+// first-max argmax per row of fp32 logits (greedy decoding): one 1024-thread CTA per row, 16-byte loads
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int cols, int* out) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
   const float* row = logits + (long)blockIdx.x * cols;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
-    const float v = row[i];
+  auto take = [&](float v, int i) {
     if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  };
+  if ((cols & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const int n4 = cols >> 2;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = __ldcg(r4 + i);
+      take(v.x, 4 * i); take(v.y, 4 * i + 1); take(v.z, 4 * i + 2); take(v.w, 4 * i + 3);
+    }
+  } else {
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) take(row[i], i);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -181,14 +191,20 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ l
   }
   if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w)
-      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
-    out[blockIdx.x] = bi;
+  if (threadIdx.x < 32) {
+    best = sv[threadIdx.x];
+    bi = si[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = bi;
   }
 }
 int argmax_rows(const float* logits, int rows, int cols, int* out_idx, cudaStream_t st) {
-  argmax_kernel<<<rows, 256, 0, st>>>(logits, cols, out_idx);
+  argmax_kernel<<<rows, 1024, 0, st>>>(logits, cols, out_idx);
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 

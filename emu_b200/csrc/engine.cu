@@ -80,8 +80,9 @@ __global__ void rope_table_kernel(bf16* cos_t, bf16* sin_t, int max_pos, int hal
 __global__ void set_int_kernel(int* p, int n, int v) {
   if (threadIdx.x < n) p[threadIdx.x] = v;
 }
-__global__ void advance_pos_kernel(int* p, int n) {
+__global__ void advance_pos_kernel(int* p, int n, unsigned* tp_step) {
   if (threadIdx.x < n) p[threadIdx.x] += 1;
+  if (tp_step && threadIdx.x == 0) *tp_step += 1;  // decode-step counter behind the tensor-parallel exchange flags
 }
 // start[b] = number of leading zeros in mask row b; posoff[b] = hf ? start[b] : 0
 __global__ void mask_start_kernel(const int* __restrict__ mask, int N, int* start, int* posoff, int hf, int base) {
@@ -801,7 +802,21 @@ extern "C" int emu_llm_prefill(EmuEngine* e, const void* inputs_embeds, const in
 // tensor-parallel tail of a row-parallel projection (o_proj / down_proj) in the decode loop: h += sum over ranks of W_r x_r.
 // Preferred: fp32 partial -> NVLink peer-memory push + flag + fixed-order reduce in ONE kernel (tp_exchange.cu);
 // otherwise NCCL all-reduce of the bf16 partial + add.
-static int row_parallel_tail(EmuEngine* e, GemvArgs& g, bf16* h, int B, int Hd, cudaStream_t st, int* nl) {
+static int row_parallel_tail(EmuEngine* e, GemvArgs& g, bf16* h, int B, int Hd, int idx, cudaStream_t st, int* nl) {
+  if (e->tp_p2p && e->tp_ll) {
+    // fused: the GEMV epilogue itself pushes {value, flag} words to every rank; a small kernel polls + reduces
+    GemvArgs f = g;
+    f.ldy = Hd;
+    if (tp_ll_prepare(e, f, idx) == EMU_OK) {
+      const int rc = gemv_bf16(f, st);
+      if (rc == EMU_OK) {
+        EMU_TRY(tp_ll_reduce(e, h, (long)B * Hd, idx, g.pdl, st));
+        *nl += 1;
+        return EMU_OK;
+      }
+      if (rc != EMU_ERR_UNSUPPORTED) return rc;
+    }
+  }
   if (e->tp_p2p) {
     g.y = e->dec_part; g.ldy = Hd; g.out_fp32 = 1;
     EMU_TRY(gemv_bf16(g, st));
@@ -852,7 +867,7 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
       o.residual = h; o.ldr = Hd; o.y = h; o.ldy = Hd;
       EMU_TRY(gemv_bf16(o, st));
     } else {
-      EMU_TRY(row_parallel_tail(e, o, h, B, Hd, st, &nl));
+      EMU_TRY(row_parallel_tail(e, o, h, B, Hd, 2 * l, st, &nl));
     }
     GemvArgs g;
     g.W = L.wgu; g.N = 2 * Fl; g.K = Hd; g.x = h; g.ldx = Hd; g.B = B;
@@ -865,7 +880,7 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
       d.residual = h; d.ldr = Hd; d.y = h; d.ldy = Hd;
       EMU_TRY(gemv_bf16(d, st));
     } else {
-      EMU_TRY(row_parallel_tail(e, d, h, B, Hd, st, &nl));
+      EMU_TRY(row_parallel_tail(e, d, h, B, Hd, 2 * l + 1, st, &nl));
     }
     nl += 5;
   }
@@ -903,7 +918,7 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
       ++nl;
     }
   }
-  advance_pos_kernel<<<1, 32, 0, st>>>(e->d_pos, 8);
+  advance_pos_kernel<<<1, 32, 0, st>>>(e->d_pos, 8, tp_step_counter(e));
   ++nl;
   *n_launch = nl;
   return EMU_OK;

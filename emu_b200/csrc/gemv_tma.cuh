@@ -81,7 +81,16 @@ static __device__ __noinline__ void gemv_tma_flush(const GemvTmaParams* sp, floa
     const float* f = fin + rt * 128;
     const int nrow = (grp * kTRT + rt) * 16 + r;
     if (b < B && nrow < N) {
-      if (a.mode == EPI_NONE) {
+      if (a.mode == EPI_NONE && a.ll_n > 0) {
+        // fused tensor-parallel push: {value, flag} words are self-validating, so no fence / separate flag round trip
+        const unsigned flag = __ldcg(a.ll_step) * 256u + (unsigned)a.ll_idx + 1u;
+        const unsigned bits = __float_as_uint(f[r * 8 + b]);
+        const size_t off = ((size_t)(a.ll_idx & 1) * a.ll_n + a.ll_rank) * a.ll_slot_elems + (size_t)b * a.ldy + nrow;
+        for (int pr = 0; pr < a.ll_n; ++pr)
+          asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(a.ll_peer[pr]) + off), "r"(bits),
+                       "r"(flag)
+                       : "memory");
+      } else if (a.mode == EPI_NONE) {
         float o = f[r * 8 + b];
         if (a.bias) o += __bfloat162float(a.bias[nrow]);
         if (a.residual)

@@ -64,6 +64,13 @@ struct GemvArgs {
   bf16* v_cache = nullptr;
   int t_max = 0;
   int pdl = 0;  // launch with programmatic dependent launch
+  // Tensor-parallel fused exchange (tp_exchange.cu), mode == EPI_NONE only: instead of writing y, the epilogue stores
+  // every fp32 output as an 8-byte {value, flag} word straight into each rank's receive slot over NVLink
+  // (flag = *ll_step * 256 + ll_idx + 1, slot = parity ll_idx & 1, source ll_rank); ll_n == 0 disables.
+  void* ll_peer[8] = {};
+  int ll_n = 0, ll_rank = 0, ll_idx = 0;
+  long ll_slot_elems = 0;
+  const unsigned* ll_step = nullptr;
 };
 constexpr int GEMV_ROPE_QKV = 16;
 int gemv_bf16(const GemvArgs& a, cudaStream_t st);

@@ -31,7 +31,7 @@ constexpr int kTpThreads = 256;
 struct TpLayout {
   size_t red_slot;     // floats per reduce slot  (Bmax * hidden)
   size_t gat_slot;     // floats per gather slot  (Bmax * Vl)
-  size_t red_off, gat_off, flag_red_off, flag_gat_off, seq_off, total;  // in floats / 4-byte words
+  size_t red_off, gat_off, flag_red_off, flag_gat_off, seq_off, ll_off, step_off, total;  // in floats / 4-byte words
 };
 static TpLayout tp_layout(int n, int bmax, int hidden, int vl) {
   TpLayout L;
@@ -42,7 +42,9 @@ static TpLayout tp_layout(int n, int bmax, int hidden, int vl) {
   L.flag_red_off = L.gat_off + 2 * (size_t)n * L.gat_slot;
   L.flag_gat_off = L.flag_red_off + (size_t)8 * kTpMaxCtas;
   L.seq_off = L.flag_gat_off + (size_t)8 * kTpMaxCtas;
-  L.total = L.seq_off + 2 * kTpMaxCtas;
+  L.ll_off = (L.seq_off + 2 * kTpMaxCtas + 3) / 4 * 4;  // {value, flag} words: 2 floats per element
+  L.step_off = L.ll_off + 2 * 2 * (size_t)n * L.red_slot;
+  L.total = L.step_off + 4;
   return L;
 }
 
@@ -154,6 +156,41 @@ __global__ void __launch_bounds__(kTpThreads) tp_gather_logits_kernel(TpPeers pe
   }
 }
 
+// consumer of the fused push (GemvArgs::ll_*): poll the {value, flag} words of all ranks, reduce in rank order, add to h
+__global__ void __launch_bounds__(kTpThreads) tp_ll_reduce_kernel(const uint4* __restrict__ ll, const unsigned* step, int idx,
+                                                                  int rank, int n, size_t slot_elems, bf16* h, long n_elem,
+                                                                  int pdl) {
+  if (pdl) {
+    pdl_launch_dependents();
+    pdl_wait();  // the step counter and h are only stable once every earlier kernel of the stream has retired
+  }
+  const unsigned flag = __ldcg(step) * 256u + (unsigned)idx + 1u;
+  const uint4* base = ll + ((size_t)(idx & 1) * n * slot_elems) / 2;
+  const long n2 = n_elem >> 1;
+  for (long i = (long)blockIdx.x * kTpThreads + threadIdx.x; i < n2; i += (long)gridDim.x * kTpThreads) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = 0; r < n; ++r) {
+      const uint4* p = base + ((size_t)r * slot_elems) / 2 + i;
+      uint4 v;
+      unsigned long long t0 = 0;
+      for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        if (v.y == flag && v.w == flag) break;
+        if (t0 == 0) t0 = globaltimer_ns();
+        else if (globaltimer_ns() - t0 > 20000000000ull) {
+          printf("emu_b200: tensor-parallel exchange timed out (rank %d waiting for rank %d, exchange %d)\n", rank, r, idx);
+          __trap();
+        }
+      }
+      a0 += __uint_as_float(v.x);
+      a1 += __uint_as_float(v.z);
+    }
+    uint32_t hv = reinterpret_cast<uint32_t*>(h)[i];
+    hv = pack_bf16(bf16_lo(hv) + round_bf16(a0), bf16_hi(hv) + round_bf16(a1));
+    reinterpret_cast<uint32_t*>(h)[i] = hv;
+  }
+}
+
 static int tp_grid(long n_elem) {
   long g = (n_elem / 4 + kTpThreads - 1) / kTpThreads;
   if (g < 1) g = 1;
@@ -183,6 +220,34 @@ int tp_reduce_add(EmuEngine* e, const float* part, bf16* h, long n_elem, int pdl
   size_t data_off = L.red_off, slot = L.red_slot, flag_off = L.flag_red_off, seq_off = L.seq_off;
   void* args[] = {&peers, &rank, &n, &part, &h, &n_elem, &data_off, &slot, &flag_off, &seq_off, &pdl};
   return launch_pdl((const void*)tp_reduce_add_kernel, dim3(tp_grid(n_elem)), args, pdl, st);
+}
+
+// fill the fused-push fields of a row-parallel GEMV (exchange index idx = 2*layer + {0: o_proj, 1: down_proj})
+int tp_ll_prepare(EmuEngine* e, GemvArgs& g, int idx) {
+  if (!e->tp_p2p || !e->tp_ll) return EMU_ERR_UNSUPPORTED;
+  const TpLayout L = tp_layout(e->tp_size, e->cfg.llm_max_batch, e->cfg.llm_hidden, e->Vl);
+  for (int r = 0; r < e->tp_size; ++r) g.ll_peer[r] = e->tp_peer[r] + L.ll_off;
+  g.ll_n = e->tp_size; g.ll_rank = e->tp_rank; g.ll_idx = idx;
+  g.ll_slot_elems = (long)L.red_slot;
+  g.ll_step = reinterpret_cast<const unsigned*>(e->tp_peer[e->tp_rank] + L.step_off);
+  return EMU_OK;
+}
+unsigned* tp_step_counter(EmuEngine* e) {
+  if (!e->tp_p2p) return nullptr;
+  const TpLayout L = tp_layout(e->tp_size, e->cfg.llm_max_batch, e->cfg.llm_hidden, e->Vl);
+  return reinterpret_cast<unsigned*>(e->tp_peer[e->tp_rank] + L.step_off);
+}
+int tp_ll_reduce(EmuEngine* e, bf16* h, long n_elem, int idx, int pdl, cudaStream_t st) {
+  if (!e->tp_p2p || (n_elem & 1)) return EMU_ERR_STATE;
+  const TpLayout L = tp_layout(e->tp_size, e->cfg.llm_max_batch, e->cfg.llm_hidden, e->Vl);
+  const uint4* ll = reinterpret_cast<const uint4*>(e->tp_peer[e->tp_rank] + L.ll_off);
+  const unsigned* step = reinterpret_cast<const unsigned*>(e->tp_peer[e->tp_rank] + L.step_off);
+  int rank = e->tp_rank, n = e->tp_size;
+  size_t slot = L.red_slot;
+  void* args[] = {&ll, &step, &idx, &rank, &n, &slot, &h, &n_elem, &pdl};
+  long g = (n_elem / 2 + kTpThreads - 1) / kTpThreads;
+  if (g > kTpMaxCtas) g = kTpMaxCtas;
+  return launch_pdl((const void*)tp_ll_reduce_kernel, dim3((unsigned)g), args, pdl, st);
 }
 
 int tp_gather_logits(EmuEngine* e, const float* shard, float* logits, int B, int pdl, cudaStream_t st) {
@@ -247,6 +312,10 @@ int tp_exchange_setup(EmuEngine* e, int (*allgather_bytes)(EmuEngine*, const voi
   }
   e->tp_comm = buf;
   e->tp_p2p = true;
+  {
+    const char* ll = getenv("EMU_TP_LL");
+    e->tp_ll = !(ll && atoi(ll) == 0);
+  }
   if (getenv("EMU_TP_DEBUG")) fprintf(stderr, "emu_b200: rank %d/%d NVLink peer exchange enabled\n", e->tp_rank, n);
   return EMU_OK;
 }
