@@ -122,6 +122,7 @@ _CPU_SD_CACHE = {}
 
 
 _CPU_BEST_THREADS = None
+NCU_TRAFFIC_RATIO = (477.327 + 6.566) / 477.102  # profiles/r01_ncu_full_gemv_tma_gateup.txt
 
 
 def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, ctx=75, threads=None, budget_s=25.0):
@@ -311,7 +312,7 @@ def unet_param_shapes(cfg):
     return out
 
 
-def run_denoise(steps=50, warm_loops=1, timed_loops=1, batch=1, hw=128, seed=0):
+def run_denoise(steps=50, warm_loops=1, timed_loops=1, batch=1, hw=128, seed=0, profile=False):
     """50 Euler steps of the Emu2-Gen denoise loop (CFG, guidance 3, 1024x1024 -> latent 128x128) on random-init weights
     of the published UNet topology; returns (steps_per_s, ms_per_step, launches_per_step)."""
     from emu_b200 import _lib
@@ -352,11 +353,15 @@ def run_denoise(steps=50, warm_loops=1, timed_loops=1, batch=1, hw=128, seed=0):
     l0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if profile:  # ncu --profile-from-start off: capture only the timed loop (tools/ncu_unet.py)
+        torch.cuda.profiler.start()
     ev0.record()
     for _ in range(timed_loops):
         loop()
     ev1.record()
     torch.cuda.synchronize()
+    if profile:
+        torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1) / (timed_loops * steps)
     launches = (_lib.launch_count() - l0) / (timed_loops * steps)
     finite = bool(torch.isfinite(lat).all())
@@ -519,9 +524,13 @@ def run_cuda(args):
                 "d2h_bytes_per_step": int(NEW_TOKENS * 8)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "gemv_kernel (the weight-streaming launches of one decode step; "
-                     ">99% of the CUDA-graphed step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "gemv_tma_kernel (the weight-streaming launches of one decode step; "
+                     ">95% of the CUDA-graphed step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src,
+                     # ncu --set full on the gate/up launch (profiles/r01_ncu_full_gemv_tma_gateup.txt): dram read
+                     # 477.3 MB + write 6.5 MB for 477.1 MB of weights -> x1.014 of the algorithmic bytes, per step here
+                     "traffic": alg_bytes * NCU_TRAFFIC_RATIO, "traffic_source": "ncu dram bytes / algorithmic bytes of "
+                     "the gate_up launch (x%.3f), scaled to the step" % NCU_TRAFFIC_RATIO,
                      "decode_step_ms": step_ms_avg, "decode_step_ms_p50": step_ms[len(step_ms) // 2],
                      "algorithmic_bytes_per_step": alg_bytes},
         "cpu_baseline": cpu,

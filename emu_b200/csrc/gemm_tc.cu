@@ -13,6 +13,8 @@
 //   warps 2..5  : epilogue — tcgen05.ld accumulator rows to registers, fused bias / GELU / residual /
 //                 SwiGLU / GEGLU, bf16 or fp32 stores
 // A and W are both K-major, so neither operand needs a transpose anywhere in the model.
+#include <type_traits>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -24,9 +26,13 @@ constexpr int kGemmThreads = 192;
 
 template <int BN>
 struct GemmSmem {
+  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN: multiple of 32 (epilogue chunks) within the tcgen05 N range");
   static constexpr int kStageBytes = (BM + BN) * BK * 2;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kFit = (227 * 1024 - 1024 - 256) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;  // 8 / 8 / 7 / 6 / 5 / 5 / 4 for BN = 64 .. 256
   static constexpr int kBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // two accumulator stages; tcgen05.alloc wants a power of two
+  static constexpr uint32_t kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
 };
 
 struct GemmParams {
@@ -52,7 +58,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr int kStages = GemmSmem<BN>::kStages;
   constexpr int kStageBytes = GemmSmem<BN>::kStageBytes;
-  constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator stages (256 or 512 columns)
+  constexpr uint32_t kTmemCols = GemmSmem<BN>::kTmemCols;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -378,12 +384,40 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
+// Tile width: minimise  waves(BN) x time-per-tile(BN)  over the instantiated widths.  Per K=16 step a tile costs
+// max(tensor pipe: 128*BN/256 cycles, shared-memory operand reads: (128 + BN) * 32 B at 128 B/cycle); odd widths such
+// as 160 exist because e.g. M=2048, N=1280 is 160 tiles at BN=128 (two waves on 148 SMs, the second 8 % full) but 128
+// tiles at BN=160 (one wave).
 static int pick_bn(int M, int N) {
-  // prefer the widest tile that still yields >= one wave of CTAs
+  static const int cand[] = {256, 224, 192, 160, 128, 96, 64};
   const long tm = (M + BM - 1) / BM;
-  if (tm * ((N + 255) / 256) >= kNumSMs) return 256;
-  if (tm * ((N + 127) / 128) >= kNumSMs / 2) return 128;
-  return 64;
+  int best = 128;
+  double best_cost = 1e30;
+  for (int bn : cand) {
+    const long tiles = tm * ((N + bn - 1) / bn);
+    const long waves = (tiles + kNumSMs - 1) / kNumSMs;
+    const double mma = 128.0 * bn / 256.0, smem = (128.0 + bn) * 32.0 / 128.0;
+    const double cost = (double)waves * (mma > smem ? mma : smem) + 4.0 * waves;  // + per-tile fixed overhead
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+template <typename F>
+static int dispatch_bn(int bn, F&& f) {
+  switch (bn) {
+    case 256: return f(std::integral_constant<int, 256>());
+    case 224: return f(std::integral_constant<int, 224>());
+    case 192: return f(std::integral_constant<int, 192>());
+    case 160: return f(std::integral_constant<int, 160>());
+    case 128: return f(std::integral_constant<int, 128>());
+    case 96: return f(std::integral_constant<int, 96>());
+    case 64: return f(std::integral_constant<int, 64>());
+  }
+  return EMU_ERR_INVALID;
 }
 
 int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& e,
@@ -404,12 +438,7 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
   if (rc) return rc;
   rc = make_tmap_2d(&tmB, W, N, K, ldw, bn);
   if (rc) return rc;
-  switch (bn) {
-    case 256: return launch_gemm<256>(tmA, tmB, p, st);
-    case 128: return launch_gemm<128>(tmA, tmB, p, st);
-    case 64: return launch_gemm<64>(tmA, tmB, p, st);
-  }
-  return EMU_ERR_INVALID;
+  return dispatch_bn(bn, [&](auto w) { return launch_gemm<decltype(w)::value>(tmA, tmB, p, st); });
 }
 
 // 3x3 stride-1 pad-1 convolution on NHWC bf16 as an implicit GEMM. Wk is [Cout, 9*Cin] with k = (r*3+s)*Cin + c.
@@ -432,12 +461,7 @@ int conv3x3_bf16(const bf16* X, int NB, int H, int W, int Cin, const bf16* Wk, i
   if (rc) return rc;
   rc = make_tmap_2d(&tmB, Wk, Cout, 9L * Cin, 9L * Cin, bn);
   if (rc) return rc;
-  switch (bn) {
-    case 256: return launch_gemm<256>(tmA, tmB, p, st);
-    case 128: return launch_gemm<128>(tmA, tmB, p, st);
-    case 64: return launch_gemm<64>(tmA, tmB, p, st);
-  }
-  return EMU_ERR_INVALID;
+  return dispatch_bn(bn, [&](auto w) { return launch_gemm<decltype(w)::value>(tmA, tmB, p, st); });
 }
 
 }  // namespace emu

@@ -25,6 +25,7 @@ def _rand(shape, seed, scale=1.0):
 @pytest.mark.parametrize("M,N,K,bn", [
     (128, 128, 64, 128), (1, 64, 64, 64), (75, 320, 192, 0), (1025, 5376, 1792, 0), (300, 1000, 584, 64),
     (257, 768, 1408, 128), (4096, 640, 640, 256), (64, 6656, 1792, 0), (513, 264, 72, 0),
+    (2048, 1280, 1280, 0), (2048, 1280, 640, 160), (300, 1000, 584, 96), (700, 900, 320, 192), (257, 1344, 256, 224),
 ])
 def test_gemm_plain(cuda, M, N, K, bn):
     from emu_b200 import _lib
