@@ -10,8 +10,9 @@
 //                 kStages-deep ring of 128B-swizzled shared-memory stages, completion on mbarriers
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, M=128, N=BN, K=16),
 //                 fp32 accumulators double-buffered in TMEM so the epilogue of tile i overlaps tile i+1
-//   warps 2..5  : epilogue — tcgen05.ld accumulator rows to registers, fused bias / GELU / residual /
-//                 SwiGLU / GEGLU, bf16 or fp32 stores
+//   warps 2..9  : epilogue — tcgen05.ld accumulator rows to registers (two warps per TMEM lane quarter, alternating
+//                 32-column chunks), fused bias / GELU / residual / SwiGLU / GEGLU with 16-byte operand loads
+//                 prefetched ahead of the accumulator, bf16 or fp32 stores
 // A and W are both K-major, so neither operand needs a transpose anywhere in the model.
 #include <type_traits>
 
@@ -22,7 +23,7 @@ namespace emu {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 
 template <int BN>
 struct GemmSmem {
@@ -86,7 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     mbar_fence_init();
   }
@@ -160,18 +161,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue warps (2..9) =====================
+    // warp w owns TMEM lane quarter (w & 3) — the hardware restriction — and every second 32-column chunk
+    // (chunk parity = (w - 2) >> 2), so two warps per SM sub-partition share a tile's epilogue.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile % tiles_m, tn = tile / tiles_m;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       // output row owned by this thread
       long row;
       const int r_in_tile = q * 32 + lane;
-      bool row_ok;
       if (p.conv) {
         const int tiles_w = p.W / p.tw, tiles_h = p.H / p.th;
         const int w0 = (tm % tiles_w) * p.tw;
@@ -179,33 +180,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int img = tm / (tiles_w * tiles_h);
         const int hh = h0 + r_in_tile / p.tw, ww = w0 + r_in_tile % p.tw;
         row = ((long)img * p.H + hh) * p.W + ww;
-        row_ok = row < p.M;
       } else {
         row = (long)tm * BM + r_in_tile;
-        row_ok = row < p.M;
       }
+      const bool row_ok = row < p.M;
       const bool pair = (p.epi == EPI_SWIGLU || p.epi == EPI_GEGLU);
+      // 16-byte paths need aligned rows; everything in the models is, ragged shapes take the scalar path
+      const bool vec_res = p.residual != nullptr && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+      const bool vec_b2 = p.bias2 != nullptr && (p.N % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.bias2) & 15) == 0);
+      const bool vec_bias = p.bias != nullptr && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+      // operands that do not depend on the accumulator are fetched BEFORE waiting for the MMAs of this tile
+      uint4 rsd_v[4] = {}, b2_v[4] = {};
+      auto prefetch = [&](int c) {
+        const int col0 = tn * BN + c * 32;
+        if (!row_ok || col0 + 32 > p.N) return;
+        if (vec_res) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rsd_v[i] = __ldg(src + i);
+        }
+        if (vec_b2) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.bias2 + (row / p.bias2_rows) * p.N + col0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) b2_v[i] = __ldg(src + i);
+        }
+      };
+      prefetch(half);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
         tmem_ld_32x32(taddr, v);
         tmem_ld_wait();
         const int col0 = tn * BN + c * 32;
+        uint4 rsd_c[4], b2_c[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { rsd_c[i] = rsd_v[i]; b2_c[i] = b2_v[i]; }
+        if (c + 2 < BN / 32) prefetch(c + 2);  // next chunk's operands fly while this one is processed
         if (row_ok && col0 < p.N) {
+          const bool full = col0 + 32 <= p.N;
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
           if (p.bias != nullptr) {
+            if (full && vec_bias) {
+              const uint4* bsrc = reinterpret_cast<const uint4*>(p.bias + col0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) f[i] += __bfloat162float(p.bias[col0 + i]);
+              for (int i = 0; i < 4; ++i) {
+                const uint4 b = __ldg(bsrc + i);
+                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { f[8 * i + 2 * j] += bf16_lo(bw[j]); f[8 * i + 2 * j + 1] += bf16_hi(bw[j]); }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) f[i] += __bfloat162float(p.bias[col0 + i]);
+            }
           }
           if (p.bias2 != nullptr) {
-            const bf16* b2 = p.bias2 + (row / p.bias2_rows) * p.N + col0;
+            if (full && vec_b2) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) f[i] = round_bf16(f[i]) + __bfloat162float(b2[i]);
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t bw[4] = {b2_c[i].x, b2_c[i].y, b2_c[i].z, b2_c[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  f[8 * i + 2 * j] = round_bf16(f[8 * i + 2 * j]) + bf16_lo(bw[j]);
+                  f[8 * i + 2 * j + 1] = round_bf16(f[8 * i + 2 * j + 1]) + bf16_hi(bw[j]);
+                }
+              }
+            } else {
+              const bf16* b2 = p.bias2 + (row / p.bias2_rows) * p.N + col0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) f[i] = round_bf16(f[i]) + __bfloat162float(b2[i]);
+            }
           }
           if (pair) {
             // interleaved (a_j, b_j) column pairs -> one output column j
@@ -215,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 16; ++i) {
               const float a = round_bf16(f[2 * i]), b = round_bf16(f[2 * i + 1]);
               if (p.epi == EPI_SWIGLU) o[i] = round_bf16(silu(a)) * b;
-              else o[i] = a * round_bf16(gelu_erf(b));
+              else o[i] = a * round_bf16(gelu_erf_fast(b));
             }
             const int oc0 = col0 >> 1;
             bf16* dst = reinterpret_cast<bf16*>(p.C) + row * p.ldc + oc0;
@@ -232,20 +283,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             if (p.epi == EPI_GELU) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = gelu_erf(round_bf16(f[i]));
+              for (int i = 0; i < 32; ++i) f[i] = gelu_erf_fast(round_bf16(f[i]));
             } else if (p.epi == EPI_RELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
             }
             if (p.residual != nullptr) {
-              const bf16* rsd = p.residual + row * p.ldr + col0;
+              if (full && vec_res) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) f[i] = round_bf16(f[i]) + __bfloat162float(rsd[i]);
+                for (int i = 0; i < 4; ++i) {
+                  const uint32_t rw[4] = {rsd_c[i].x, rsd_c[i].y, rsd_c[i].z, rsd_c[i].w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    f[8 * i + 2 * j] = round_bf16(f[8 * i + 2 * j]) + bf16_lo(rw[j]);
+                    f[8 * i + 2 * j + 1] = round_bf16(f[8 * i + 2 * j + 1]) + bf16_hi(rw[j]);
+                  }
+                }
+              } else {
+                const bf16* rsd = p.residual + row * p.ldr + col0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) f[i] = round_bf16(f[i]) + __bfloat162float(rsd[i]);
+              }
             }
             if (p.out_fp32) {
               float* dst = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
-              if (col0 + 32 <= p.N && (p.ldc % 4 == 0)) {
+              if (full && (p.ldc % 4 == 0)) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                   reinterpret_cast<float4*>(dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
@@ -255,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             } else {
               bf16* dst = reinterpret_cast<bf16*>(p.C) + row * p.ldc + col0;
-              if (col0 + 32 <= p.N && (p.ldc % 8 == 0)) {
+              if (full && (p.ldc % 8 == 0)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   uint4 w;

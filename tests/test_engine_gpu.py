@@ -91,8 +91,8 @@ def _teacher_forced_logprobs(sd, emb, mask, toks):
 def test_generate_greedy_tokens_vs_reference(model, gold, sd):
     """Random-init logits are nearly flat, so a bf16-level perturbation may legitimately pick the other side of a
     near tie.  Accept a free-running greedy sequence iff, under the fp32 reference model teacher-forced on that
-    very sequence, every chosen token is within the numerical noise margin of the reference argmax; rows whose
-    choices never hit a near tie must reproduce the reference ids exactly."""
+    very sequence, every chosen token is within the numerical noise margin of the reference argmax; and every row must
+    reproduce the reference ids exactly up to its first near-tie flip (the whole row if there is none)."""
     ids = model.generate_from_ids(gold["gen_input_ids"], gold["gen_attention_mask"], image=gold["image"].cuda(),
                                   num_beams=1, max_new_tokens=12, min_len=1).cpu()
     ref = gold["gen_ids_greedy"]
@@ -102,9 +102,11 @@ def test_generate_greedy_tokens_vs_reference(model, gold, sd):
     best = lp.max(-1)[0]
     margin = 3e-2 * lp.abs().max()          # same budget as the logits parity tests
     assert bool((best - chosen <= margin).all()), (best - chosen)
-    exact_rows = (best - chosen == 0).all(1)
-    assert bool(exact_rows.any())
-    assert torch.equal(ids[exact_rows], ref[exact_rows])
+    n_new = lp.shape[1]
+    for b in range(ids.shape[0]):
+        flips = (best[b] - chosen[b] > 0).nonzero()
+        k = int(flips[0]) if flips.numel() else n_new
+        assert torch.equal(ids[b, :k], ref[b, :k]), (b, k, ids[b], ref[b])
 
 
 def test_generate_greedy_matches_bf16_oracle(model, gold, sd):

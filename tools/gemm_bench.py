@@ -8,8 +8,11 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from emu_b200 import _lib  # noqa: E402
 
-GEMMS = [  # name, M, N, K, epi
+GEMMS = [  # name, M, N, K, epi  (epi -1 = bias + residual epilogue)
     ("unet L2 attn q/o (1024 tok x2)", 2048, 1280, 1280, 0),
+    ("unet L2 attn o +bias+residual", 2048, 1280, 1280, -1),
+    ("unet L2 ff2 +bias+residual", 2048, 1280, 5120, -1),
+    ("unet L1 attn o +bias+residual", 8192, 640, 640, -1),
     ("unet L2 qkv", 2048, 3840, 1280, 0),
     ("unet L2 geglu ff1", 2048, 10240, 1280, _lib.EPI_GEGLU),
     ("unet L2 ff2", 2048, 1280, 5120, 0),
@@ -52,6 +55,12 @@ def main():
     for name, M, N, K, epi in GEMMS:
         A = (torch.randn(M, K, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
         W = (torch.randn(N, K, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+        if epi == -1:
+            bias = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+            res = torch.randn(M, N, generator=g, device="cuda").to(torch.bfloat16)
+            ms = timeit(lambda: _lib.op_gemm(A, W, bias=bias, residual=res))
+            print("%-36s M=%5d N=%5d K=%5d  %7.3f ms %7.1f TFLOP/s" % (name, M, N, K, ms, 2.0 * M * N * K / ms / 1e9), flush=True)
+            continue
         ms = timeit(lambda: _lib.op_gemm(A, W, epi=epi))
         extra = ""
         if os.environ.get("GEMM_BENCH_SWEEP"):
