@@ -58,6 +58,7 @@ struct AtParams {
   int Nq, Nk, D;  // D = real head dim (<= DT)
   int causal;
   float scale_log2;  // scale * log2(e)
+  int pdl;
   int q_hf, k_hf, v_hf;  // tensor-map coordinate order: 1 = (d, head, token, batch), 0 = (d, token, head, batch)
 };
 
@@ -155,6 +156,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     mbar_fence_init();
   }
+  if (p.pdl) pdl_launch_dependents();
   if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -164,6 +166,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0 && nbmax > 0) {
+      if (p.pdl) pdl_wait();  // Q/K/V are the predecessor's output; all stores of this kernel happen after these loads
       mbar_expect_tx(q_full, 2 * C::kQBytes);
       for (int t = 0; t < 2; ++t)
         for (int c = 0; c < C::kDC; ++c)
@@ -378,9 +381,9 @@ int launch_attn_tc(const AttnArgs& a, cudaStream_t st) {
   p.out = a.out; p.o_bs = a.o_bs; p.o_ts = a.o_ts; p.o_hs = a.o_hs;
   p.kv_start = a.kv_start; p.Nq = a.Nq; p.Nk = a.Nk; p.D = a.D; p.causal = a.causal;
   p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.pdl = g_pdl_chain;
   dim3 grid((a.Nq + 255) / 256, a.H, a.B);
-  attn_tc_kernel<DT, BN><<<grid, kAtThreads, C::kSmem, st>>>(tq, tk, tv, p);
-  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+  return launch_kernel(attn_tc_kernel<DT, BN>, grid, dim3(kAtThreads), C::kSmem, st, p.pdl, tq, tk, tv, p);
 }
 
 }  // namespace

@@ -15,9 +15,13 @@ namespace emu {
 constexpr int kGnChunks = 64;  // partial-sum slots per image
 
 __global__ void __launch_bounds__(512) gn_partial_kernel(const bf16* __restrict__ x, float* __restrict__ part, int HW,
-                                                         int C, int groups) {
+                                                         int C, int groups, int pdl) {
   // grid (kGnChunks, NB); part[((b*kGnChunks + chunk)*groups + g)*2 + {0,1}] = {sum, sumsq}
   __shared__ float stage[512 * 16];  // per-thread {sum[8], sumsq[8]}
+  if (pdl) {
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   const int chunk = blockIdx.x, b = blockIdx.y;
   const int cpg = C / groups;
   const int p0 = (int)((long)HW * chunk / kGnChunks), p1 = (int)((long)HW * (chunk + 1) / kGnChunks);
@@ -69,8 +73,12 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(const bf16* __restrict_
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ part,
                                                        const bf16* __restrict__ w, const bf16* __restrict__ bsh,
                                                        bf16* __restrict__ y, int HW, int C, int groups, float eps,
-                                                       int do_silu) {
+                                                       int do_silu, int pdl) {
   extern __shared__ float st[];  // [groups*2] mean, rstd
+  if (pdl) {
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   const int b = blockIdx.y;
   const int cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
@@ -117,14 +125,18 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
 int groupnorm_nhwc(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* scratch, int NB, int HW, int C,
                    int groups, float eps, int do_silu, cudaStream_t st) {
   if (C % 8 || C % groups || C > 4096) return EMU_ERR_INVALID;
-  gn_partial_kernel<<<dim3(kGnChunks, NB), 512, 0, st>>>(x, scratch, HW, C, groups);
+  const int pdl = g_pdl_chain;
+  {
+    const int rc = launch_kernel(gn_partial_kernel, dim3(kGnChunks, NB), dim3(512), 0, st, pdl, x, scratch, HW, C, groups, pdl);
+    if (rc) return rc;
+  }
   const long total = (long)HW * (C >> 3);
   int gx = (int)((total + 255) / 256);
   const int cap = (4 * kNumSMs + NB - 1) / NB;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  gn_apply_kernel<<<dim3(gx, NB), 256, groups * 2 * sizeof(float), st>>>(x, scratch, w, b, y, HW, C, groups, eps, do_silu);
-  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+  return launch_kernel(gn_apply_kernel, dim3(gx, NB), dim3(256), groups * 2 * sizeof(float), st, pdl, x, scratch, w, b, y, HW,
+                       C, groups, eps, do_silu, pdl);
 }
 size_t groupnorm_scratch_bytes(int NB, int groups) { return (size_t)NB * kGnChunks * groups * 2 * sizeof(float); }
 
@@ -174,7 +186,11 @@ int silu_rows(const bf16* x, bf16* y, long n, cudaStream_t st) {
 
 // copy [rows, cols] (src stride lds) into dst at column offset (dst stride ldd); used for channel concat
 __global__ void copy_cols_kernel(const bf16* __restrict__ src, bf16* dst, long rows, int cols, int lds, int ldd,
-                                 int col_off) {
+                                 int col_off, int pdl) {
+  if (pdl) {
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   const int vc = cols >> 3;
   const long total = rows * vc;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -185,8 +201,8 @@ __global__ void copy_cols_kernel(const bf16* __restrict__ src, bf16* dst, long r
 }
 int copy_cols(const bf16* src, bf16* dst, long rows, int cols, int lds, int ldd, int col_off, cudaStream_t st) {
   if ((cols | lds | ldd | col_off) % 8) return EMU_ERR_INVALID;
-  copy_cols_kernel<<<4 * kNumSMs, 256, 0, st>>>(src, dst, rows, cols, lds, ldd, col_off);
-  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+  return launch_kernel(copy_cols_kernel, dim3(4 * kNumSMs), dim3(256), 0, st, g_pdl_chain, src, dst, rows, cols, lds, ldd,
+                       col_off, g_pdl_chain);
 }
 
 // nearest-neighbour 2x upsample, NHWC

@@ -1,10 +1,23 @@
 // emu_b200 — bandwidth-bound glue kernels of the generate path (norms, RoPE + KV-cache writes, embedding gather,
 // argmax, ViT patch gather / CLS+pos assembly / average pooling, beam KV reorder).  All are 16-byte vectorised,
 // one pass over the data, fp32 math with the reference's bf16 rounding points.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ops.h"
 
 namespace emu {
+
+thread_local int g_pdl_chain = 0;
+PdlScope::PdlScope(int on) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* v = getenv("EMU_NO_PDL");
+    disabled = (v && atoi(v) != 0) ? 1 : 0;
+  }
+  prev = g_pdl_chain;
+  g_pdl_chain = (on && !disabled) ? 1 : 0;
+}
 
 // ----------------------------------------------------------------------------------------------
 // RMSNorm (HF LlamaRMSNorm / T5LayerNorm — Emu1/models/modeling_t5.py:318-331): one CTA per row
@@ -102,9 +115,78 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
   }
 }
 
+// rows of <= 2048 elements: one WARP per row, the row lives in registers (one global read, no block barriers)
+__global__ void __launch_bounds__(256) layernorm_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                             const bf16* __restrict__ b, const bf16* residual, bf16* y,
+                                                             int rows, int cols, float eps, int pdl) {
+  if (pdl) {
+    pdl_launch_dependents();
+    pdl_wait();
+  }
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = cols >> 3;
+  const uint4* src = reinterpret_cast<const uint4*>(x + row * cols);
+  uint4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = i < nv ? src[i] : make_uint4(0, 0, 0, 0);
+    const uint32_t v4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += bf16_lo(v4[j]) + bf16_hi(v4[j]);
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (lane + 32 * k < nv) {
+      const uint32_t v4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = bf16_lo(v4[j]) - mean, hi = bf16_hi(v4[j]) - mean;
+        s2 += lo * lo + hi * hi;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(s2) / (float)cols + eps);
+  const uint4* wsrc = reinterpret_cast<const uint4*>(w);
+  const uint4* bsrc = reinterpret_cast<const uint4*>(b);
+  const uint4* rsrc = residual ? reinterpret_cast<const uint4*>(residual + row * cols) : nullptr;
+  uint4* dst = reinterpret_cast<uint4*>(y + row * cols);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nv) {
+      const uint4 ww = __ldg(wsrc + i);
+      const uint4 bb = bsrc ? __ldg(bsrc + i) : make_uint4(0, 0, 0, 0);
+      const uint4 rr = rsrc ? rsrc[i] : make_uint4(0, 0, 0, 0);
+      const uint32_t v4[4] = {v[k].x, v[k].y, v[k].z, v[k].w}, w4[4] = {ww.x, ww.y, ww.z, ww.w},
+                     b4[4] = {bb.x, bb.y, bb.z, bb.w}, r4[4] = {rr.x, rr.y, rr.z, rr.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float lo = (bf16_lo(v4[j]) - mean) * rstd * bf16_lo(w4[j]) + bf16_lo(b4[j]);
+        float hi = (bf16_hi(v4[j]) - mean) * rstd * bf16_hi(w4[j]) + bf16_hi(b4[j]);
+        if (rsrc) {
+          lo = round_bf16(lo) + bf16_lo(r4[j]);
+          hi = round_bf16(hi) + bf16_hi(r4[j]);
+        }
+        o[j] = pack_bf16(lo, hi);
+      }
+      dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 int layernorm(const bf16* x, const bf16* w, const bf16* b, const bf16* residual, bf16* y, int rows, int cols, float eps,
               cudaStream_t st) {
   if (cols % 8) return EMU_ERR_INVALID;
+  if (cols <= 2048)
+    return launch_kernel(layernorm_warp_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, g_pdl_chain, x, w, b, residual, y,
+                         rows, cols, eps, g_pdl_chain);
   layernorm_kernel<<<rows, 256, 0, st>>>(x, w, b, residual, y, cols, eps);
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }

@@ -547,6 +547,7 @@ extern "C" int emu_vit_forward(EmuEngine* e, const void* image, int B, void* out
   const EmuConfig& c = e->cfg;
   if (c.vit_layers < 1) return e->fail(EMU_ERR_STATE, "engine has no ViT");
   cudaStream_t st = (cudaStream_t)stream;
+  PdlScope pdl_chain(1);
   const int W = c.vit_width, G = c.vit_image / c.vit_patch, Np = G * G, N = Np + 1, Hh = c.vit_heads, D = W / Hh;
   const long M = (long)B * N;
   if (!e->vit_wpatch || !e->vit_bpatch || !e->vit_cls || !e->vit_pos) return e->fail(EMU_ERR_STATE, "ViT stem weights missing");
@@ -699,6 +700,7 @@ extern "C" int emu_llm_prefill(EmuEngine* e, const void* inputs_embeds, const in
   EMU_TRY(llm_ready(e));
   const EmuConfig& c = e->cfg;
   cudaStream_t st = (cudaStream_t)stream;
+  PdlScope pdl_chain(1);
   if (B > c.llm_max_batch) return e->fail(EMU_ERR_INVALID, "batch exceeds llm_max_batch");
   if (e->cur_len + N > c.llm_max_seq) return e->fail(EMU_ERR_INVALID, "sequence exceeds llm_max_seq");
   if (e->cur_len > 0 && B != e->cache_B) return e->fail(EMU_ERR_STATE, "batch differs from cached batch");

@@ -52,6 +52,7 @@ struct GemmParams {
   // K index = tap * Cin + c.  tile rows = th x tw spatial patch (th*tw == 128)
   int conv;        // 0 = plain 2-D A, 1 = 3x3 conv (pad 1), 2 = 3x3 conv stride 2 is NOT handled here
   int H, W, Cin, tw, th;
+  int pdl;  // launched with programmatic dependent launch: griddepcontrol.wait before touching activations
 };
 
 template <int BN>
@@ -91,6 +92,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_fence_init();
   }
+  if (p.pdl) pdl_launch_dependents();  // the next kernel of the chain may start its own prologue now
   if (warp == 1) tmem_alloc(tmem_base_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -100,6 +102,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (p.pdl) pdl_wait();  // activations (A) come from the predecessor; everything above overlapped its tail
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -166,6 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // (chunk parity = (w - 2) >> 2), so two warps per SM sub-partition share a tile's epilogue.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    if (p.pdl) pdl_wait();  // residual / bias2 are predecessor outputs and C may alias a buffer it still reads
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -443,8 +447,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_tc_kernel<BN><<<grid, kGemmThreads, GemmSmem<BN>::kBytes, st>>>(tmA, tmB, p);
-  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+  return launch_kernel(gemm_tc_kernel<BN>, dim3(grid), dim3(kGemmThreads), GemmSmem<BN>::kBytes, st, p.pdl, tmA, tmB, p);
 }
 
 // Tile width: minimise  waves(BN) x time-per-tile(BN)  over the instantiated widths.  Per K=16 step a tile costs
@@ -494,7 +497,7 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
   p.M = M; p.N = N; p.K = K;
   p.C = e.C; p.ldc = e.ldc; p.bias = e.bias; p.residual = e.residual; p.ldr = e.ldr;
   p.bias2 = e.bias2; p.bias2_rows = e.bias2_rows > 0 ? e.bias2_rows : 1;
-  p.epi = e.mode; p.out_fp32 = e.out_fp32; p.conv = 0;
+  p.epi = e.mode; p.out_fp32 = e.out_fp32; p.conv = 0; p.pdl = g_pdl_chain;
   const int bn = e.force_bn ? e.force_bn : pick_bn(M, N);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(&tmA, A, M, K, lda, BM);
@@ -516,7 +519,7 @@ int conv3x3_bf16(const bf16* X, int NB, int H, int W, int Cin, const bf16* Wk, i
   p.M = NB * H * W; p.N = Cout; p.K = 9 * Cin;
   p.C = e.C; p.ldc = e.ldc; p.bias = e.bias; p.residual = e.residual; p.ldr = e.ldr;
   p.bias2 = e.bias2; p.bias2_rows = e.bias2_rows > 0 ? e.bias2_rows : 1;
-  p.epi = e.mode; p.out_fp32 = e.out_fp32;
+  p.epi = e.mode; p.out_fp32 = e.out_fp32; p.pdl = g_pdl_chain;
   p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tw = tw; p.th = th;
   const int bn = e.force_bn ? e.force_bn : pick_bn(p.M, Cout);
   CUtensorMap tmA, tmB;

@@ -98,6 +98,32 @@ struct AttnArgs {
 int attn_prefill(const AttnArgs& a, cudaStream_t st);
 int attn_prefill_tc(const AttnArgs& a, cudaStream_t st);  // attention_tc.cu; EMU_ERR_UNSUPPORTED -> use attn_prefill's own kernel
 
+// ---- programmatic dependent launch for kernel chains (UNet / ViT / prefill) ----
+// While a PdlScope is alive on this thread, the PDL-aware launchers (GEMM / conv, tcgen05 attention, LayerNorm,
+// GroupNorm, copy_cols) launch with cudaLaunchAttributeProgrammaticStreamSerialization: the kernel's prologue (CTA launch,
+// barrier init, TMEM allocation, tensor-map prefetch) overlaps the predecessor's tail, and the kernel executes
+// griddepcontrol.wait before it touches anything a predecessor wrote.  EMU_NO_PDL=1 disables.
+extern thread_local int g_pdl_chain;
+struct PdlScope {
+  int prev;
+  explicit PdlScope(int on);
+  ~PdlScope() { g_pdl_chain = prev; }
+};
+template <typename... KArgs, typename... Args>
+inline int launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...) == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+}
+
 // ---- elementwise.cu ----
 int rmsnorm(const bf16* x, const bf16* w, bf16* y, int rows, int cols, float eps, int t5_style, cudaStream_t st);
 int layernorm(const bf16* x, const bf16* w, const bf16* b, const bf16* residual, bf16* y, int rows, int cols, float eps,

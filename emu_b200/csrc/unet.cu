@@ -368,6 +368,7 @@ static int unet_core(Ctx& c, UNetModel* m, const bf16* x_in, const float* t_dev,
   const int nb = cf.n_blocks, lpb = cf.layers_per_block, B2 = c.B2;
   const int* boc = cf.block_out_channels;
   const int temb = boc[0] * 4;
+  PdlScope pdl_chain(1);  // ~1000 short kernels per forward: overlap every prologue with its predecessor's tail
   // ---- time / added-condition embeddings ----
   BUF(te_in, "te_in", (size_t)B2 * boc[0]);
   BUF(te_mid, "te_mid", (size_t)B2 * temb);
