@@ -45,7 +45,12 @@ struct Lin { bf16 *w = nullptr, *b = nullptr; int out = 0, in = 0; };
 struct Conv { bf16 *w = nullptr, *b = nullptr; int cout = 0, cin = 0 /*padded to 8*/, k = 3; };
 struct Norm { bf16 *w = nullptr, *b = nullptr; int c = 0; };
 struct ResnetW { Norm n1, n2; Conv c1, c2, sc; Lin temb; bool has_sc = false; int cin = 0, cout = 0; };
-struct TBlockW { Norm n1, n2, n3; bf16 *wqkv = nullptr, *wq2 = nullptr, *wkv2 = nullptr; Lin o1, o2, ff1, ff2; };
+struct TBlockW {
+  Norm n1, n2, n3;
+  bf16 *wqkv = nullptr, *wq2 = nullptr, *wkv2 = nullptr;
+  Lin o1, o2, ff1, ff2;
+  long kv_off = -1;  // column offset of this block's [k | v] in the batched cross-attention projection (unet.cu)
+};
 struct TransW { Norm gn; Lin pin, pout; std::vector<TBlockW> blocks; int c = 0; };
 
 enum LoadKind { LK_COPY = 0, LK_CONV3 = 1, LK_ROWS = 2, LK_GEGLU_W = 3, LK_GEGLU_B = 4 };
@@ -74,6 +79,8 @@ struct Ctx {
   int groups;
   float gn_eps;
   int nl = 0;
+  const bf16* kv_all = nullptr;  // [B2*L, kv_ld]: every transformer block's cross-attention K|V, projected in ONE GEMM
+  long kv_ld = 0;
   bf16* buf(const char* name, size_t elems);
 };
 #define BUF(var, name, elems)               \

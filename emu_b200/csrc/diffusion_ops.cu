@@ -94,31 +94,46 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
     st[g * 2 + 1] = rsqrtf(var + eps);
   }
   __syncthreads();
+  // every thread owns ONE 8-channel vector (its affine constants live in registers) and walks down the pixels
   const int vecC = C >> 3;
-  const long total = (long)HW * vecC;
-  const bf16* xb = x + (long)b * HW * C;
-  bf16* yb = y + (long)b * HW * C;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int cv = idx % vecC;
-    const long pix = idx / vecC;
-    const uint4 v = *reinterpret_cast<const uint4*>(xb + pix * C + cv * 8);
+  const int nthreads = gridDim.x * blockDim.x;
+  const int stride = (nthreads / vecC) * vecC;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gtid >= stride) return;
+  const int cv = gtid % vecC;
+  float mu[8], sc[8], wt[8], sh[8];
+  {
     const uint4 wv = *reinterpret_cast<const uint4*>(w + cv * 8);
     const uint4 bv = *reinterpret_cast<const uint4*>(bsh + cv * 8);
-    const uint32_t xv[4] = {v.x, v.y, v.z, v.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
-    uint32_t o[4];
+    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = cv * 8 + 2 * j;
-      const int g0 = c / cpg, g1 = (c + 1) / cpg;
-      float lo = (bf16_lo(xv[j]) - st[g0 * 2]) * st[g0 * 2 + 1] * bf16_lo(ww[j]) + bf16_lo(bb[j]);
-      float hi = (bf16_hi(xv[j]) - st[g1 * 2]) * st[g1 * 2 + 1] * bf16_hi(ww[j]) + bf16_hi(bb[j]);
+      const int g0 = c / cpg, g1 = (c + 1) / cpg;  // an 8-channel vector may straddle two groups
+      mu[2 * j] = st[g0 * 2]; mu[2 * j + 1] = st[g1 * 2];
+      sc[2 * j] = st[g0 * 2 + 1]; sc[2 * j + 1] = st[g1 * 2 + 1];
+      wt[2 * j] = bf16_lo(ww[j]); wt[2 * j + 1] = bf16_hi(ww[j]);
+      sh[2 * j] = bf16_lo(bb[j]); sh[2 * j + 1] = bf16_hi(bb[j]);
+    }
+  }
+  const bf16* xb = x + (long)b * HW * C + cv * 8;
+  bf16* yb = y + (long)b * HW * C + cv * 8;
+  const int pstep = stride / vecC;
+  for (long pix = gtid / vecC; pix < HW; pix += pstep) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xb + pix * C);
+    const uint32_t xv[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo = (bf16_lo(xv[j]) - mu[2 * j]) * sc[2 * j] * wt[2 * j] + sh[2 * j];
+      float hi = (bf16_hi(xv[j]) - mu[2 * j + 1]) * sc[2 * j + 1] * wt[2 * j + 1] + sh[2 * j + 1];
       if (do_silu) {  // F.silu(group_norm(x)) with the bf16 rounding of the norm output in between
         lo = silu(round_bf16(lo));
         hi = silu(round_bf16(hi));
       }
       o[j] = pack_bf16(lo, hi);
     }
-    *reinterpret_cast<uint4*>(yb + pix * C + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(yb + pix * C) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -134,7 +149,7 @@ int groupnorm_nhwc(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* 
   int gx = (int)((total + 255) / 256);
   const int cap = (4 * kNumSMs + NB - 1) / NB;
   if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
+  if (gx < ((C >> 3) + 255) / 256) gx = ((C >> 3) + 255) / 256;  // at least one thread per 8-channel vector
   return launch_kernel(gn_apply_kernel, dim3(gx, NB), dim3(256), groups * 2 * sizeof(float), st, pdl, x, scratch, w, b, y, HW,
                        C, groups, eps, do_silu, pdl);
 }

@@ -37,6 +37,11 @@ struct UNetModel {
   std::map<StepKey, int> warmed;
   float* step_params = nullptr;  // device [4]: sigma, sigma_next, guidance, timestep
   int n_launch = 0;
+  // all cross-attention to_k / to_v weights stacked row-wise: the context is the same for every block, so ONE
+  // [B2*L, sum 2C] GEMM at the top of the forward replaces 70 tiny per-block launches (same arithmetic per element)
+  bf16* kv_all_w = nullptr;
+  long kv_all_n = 0;
+  bool kv_all_ready = false;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -228,6 +233,7 @@ int load_by_spec(EmuEngine* e, const SpecMap& specs, const char* what, const std
 int unet_load_tensor(EmuEngine* e, const std::string& key, const bf16* src, const int64_t* shape, int ndim,
                      cudaStream_t st) {
   if (!e->unet) return e->fail(EMU_ERR_STATE, "emu_unet_configure must be called before loading unet.* tensors");
+  e->unet->kv_all_ready = false;  // re-stack the cross-attention weights on the next forward
   return load_by_spec(e, e->unet->specs, "unet", key, src, shape, ndim, st);
 }
 
@@ -342,12 +348,17 @@ static int transformer2d(Ctx& c, const TransW& t, const bf16* x, bf16* y, int NB
     GemmEpilogue e2;
     e2.C = qkv; e2.ldc = C;
     EMU_TRY(gemm_bf16(n, C, b.wq2, C, (int)M, C, C, e2, c.st));
-    GemmEpilogue e3;
-    e3.C = kv; e3.ldc = 2 * C;
-    EMU_TRY(gemm_bf16(ctxv, cd, b.wkv2, cd, NB * L, 2 * C, cd, e3, c.st));
     AttnArgs x2;
     x2.q = qkv; x2.q_bs = (long)T * C; x2.q_ts = C; x2.q_hs = 64;
-    x2.k = kv; x2.v = kv + C; x2.k_bs = x2.v_bs = (long)L * 2 * C; x2.k_ts = x2.v_ts = 2 * C; x2.k_hs = x2.v_hs = 64;
+    if (c.kv_all && b.kv_off >= 0) {
+      x2.k = c.kv_all + b.kv_off; x2.v = x2.k + C;
+      x2.k_bs = x2.v_bs = (long)L * c.kv_ld; x2.k_ts = x2.v_ts = c.kv_ld; x2.k_hs = x2.v_hs = 64;
+    } else {
+      GemmEpilogue e3;
+      e3.C = kv; e3.ldc = 2 * C;
+      EMU_TRY(gemm_bf16(ctxv, cd, b.wkv2, cd, NB * L, 2 * C, cd, e3, c.st));
+      x2.k = kv; x2.v = kv + C; x2.k_bs = x2.v_bs = (long)L * 2 * C; x2.k_ts = x2.v_ts = 2 * C; x2.k_hs = x2.v_hs = 64;
+    }
     x2.out = att; x2.o_bs = (long)T * C; x2.o_ts = C; x2.o_hs = 64;
     x2.B = NB; x2.H = Hh; x2.Nq = T; x2.Nk = L; x2.D = 64; x2.scale = scale;
     EMU_TRY(attn_prefill(x2, c.st));
@@ -356,9 +367,51 @@ static int transformer2d(Ctx& c, const TransW& t, const bf16* x, bf16* y, int NB
     EMU_TRY(layernorm(h, b.n3.w, b.n3.b, nullptr, n, (int)M, C, 1e-5f, c.st));
     EMU_TRY(lin_rows(c, n, (int)M, b.ff1, ff, nullptr, EPI_GEGLU));
     EMU_TRY(lin_rows(c, ff, (int)M, b.ff2, h, h));
-    c.nl += 8;
+    c.nl += (c.kv_all && b.kv_off >= 0) ? 7 : 8;
   }
   return lin_rows(c, h, (int)M, t.pout, y, x);
+}
+
+// stack every block's [to_k; to_v] rows into one matrix (done once after the weights are loaded, outside graph capture)
+static int unet_stack_kv(EmuEngine* e, UNetModel* m, cudaStream_t st) {
+  if (m->kv_all_ready) return EMU_OK;
+  const int cd = m->cfg.cross_attention_dim;
+  std::vector<TBlockW*> blocks;
+  std::vector<int> widths;
+  auto visit = [&](TransW& t) {
+    for (TBlockW& b : t.blocks) {
+      blocks.push_back(&b);
+      widths.push_back(2 * t.c);
+    }
+  };
+  for (auto& v : m->down_att) for (TransW& t : v) visit(t);
+  visit(m->mid_att);
+  for (auto& v : m->up_att) for (TransW& t : v) visit(t);
+  long n = 0;
+  for (int w : widths) n += w;
+  if (n == 0) {
+    m->kv_all_ready = true;
+    return EMU_OK;
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return EMU_OK;  // never allocate / restack inside a capture: keep the per-block path
+  if (m->kv_all_n != n || !m->kv_all_w) {
+    m->kv_all_w = (bf16*)e->dmalloc((size_t)n * cd * 2);
+    if (!m->kv_all_w) return e->fail(EMU_ERR_NOMEM, "cross-attention weight stack alloc failed");
+    m->kv_all_n = n;
+  }
+  long off = 0;
+  for (size_t i = 0; i < blocks.size(); ++i) {
+    if (!blocks[i]->wkv2) return e->fail(EMU_ERR_STATE, "unet cross-attention weights missing");
+    if (cudaMemcpyAsync(m->kv_all_w + off * cd, blocks[i]->wkv2, (size_t)widths[i] * cd * 2, cudaMemcpyDeviceToDevice, st) !=
+        cudaSuccess)
+      return e->fail(EMU_ERR_CUDA, "cross-attention weight stack copy failed");
+    blocks[i]->kv_off = off;
+    off += widths[i];
+  }
+  m->kv_all_ready = true;
+  return EMU_OK;
 }
 
 // UNet2DConditionModel.forward on NHWC input [B2, h, w, cin_pad]; t_dev [B2] fp32; returns eps in `eps` [B2*h*w, ld 8]
@@ -369,6 +422,18 @@ static int unet_core(Ctx& c, UNetModel* m, const bf16* x_in, const float* t_dev,
   const int* boc = cf.block_out_channels;
   const int temb = boc[0] * 4;
   PdlScope pdl_chain(1);  // ~1000 short kernels per forward: overlap every prologue with its predecessor's tail
+  EMU_TRY(unet_stack_kv(c.e, m, c.st));
+  c.kv_all = nullptr;
+  if (m->kv_all_ready && m->kv_all_n > 0) {
+    BUF(kv_all, "kv_all", (size_t)B2 * L * m->kv_all_n);
+    GemmEpilogue ek;
+    ek.C = kv_all; ek.ldc = (int)m->kv_all_n;
+    EMU_TRY(gemm_bf16(ctxv, cf.cross_attention_dim, m->kv_all_w, cf.cross_attention_dim, B2 * L, (int)m->kv_all_n,
+                      cf.cross_attention_dim, ek, c.st));
+    ++c.nl;
+    c.kv_all = kv_all;
+    c.kv_ld = m->kv_all_n;
+  }
   // ---- time / added-condition embeddings ----
   BUF(te_in, "te_in", (size_t)B2 * boc[0]);
   BUF(te_mid, "te_mid", (size_t)B2 * temb);
