@@ -402,7 +402,7 @@ def run_cuda(args):
     n_query = vc.n_query
     prompt_len = 2 + n_query + 1 + N_TEXT
     model = EmuModel(vc, TextDecoderCfg(), tokenizer=synthetic.SyntheticTokenizer(vocab), llama_config=lc,
-                     max_batch=1, max_seq=prompt_len + NEW_TOKENS + 8, tp_rank=rank, tp_size=world, nccl_uid=uid)
+                     max_batch=5, max_seq=prompt_len + NEW_TOKENS + 8, tp_rank=rank, tp_size=world, nccl_uid=uid)
     synthetic.load_random_weights(model, vc, lc, vocab, seed=0)
 
     g = torch.Generator().manual_seed(1234)
@@ -429,11 +429,14 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     def timed(resident, steps):
+        return timed_fn(lambda: one_step(resident), steps)
+
+    def timed_fn(fn, steps):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
         for _ in range(steps):
-            toks = one_step(resident)
+            toks = fn()
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -477,6 +480,22 @@ def run_cuda(args):
     torch.cuda.synchronize()
     step_ms = sorted(evs[s - 1].elapsed_time(evs[s]) for s in range(1, NEW_TOKENS))
     step_ms_avg = sum(step_ms) / len(step_ms)
+
+    # secondary: the reference's default decoding — 5 beams, length_penalty -1 — same prompt and length
+    beam5 = None
+    if not args.no_beam and world == 1:
+        try:
+            def beam_gen():
+                return model.generate_from_ids(ids_dev, mask_dev, image=image_dev, num_beams=5, max_new_tokens=NEW_TOKENS,
+                                               min_len=NEW_TOKENS, length_penalty=-1)
+            beam_gen()
+            ms_b, tb = timed_fn(beam_gen, 1)
+            beam5 = {"metric": "emu2_img2text_beam5_tok_per_s", "value": tb.shape[1] / (ms_b / 1000.0), "unit": "tok/s",
+                     "new_tokens": int(tb.shape[1]), "ms": ms_b,
+                     "config": "num_beams=5, length_penalty=-1 (reference default), batch 1 -> 5 cache rows, "
+                               "device-side emu_beam_topk per step, host beam bookkeeping on [1,10] tensors"}
+        except Exception as ex:
+            beam5 = {"metric": "emu2_img2text_beam5_tok_per_s", "value": None, "error": repr(ex)}
     ctx_avg = prompt_len + NEW_TOKENS / 2.0
     alg_bytes = (llm_bytes_per_token(lc, vocab) + kv_bytes_per_ctx_token(lc) * ctx_avg) / world
     peak, peak_src = measured_peaks()
@@ -535,6 +554,7 @@ def run_cuda(args):
                      "algorithmic_bytes_per_step": alg_bytes},
         "cpu_baseline": cpu,
         "denoise": denoise,
+        "beam5": beam5,
     }
     emit(line)
     if world > 1:
@@ -570,6 +590,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny plumbing config (debug only; never a bench number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-denoise", action="store_true", help="skip the Emu2-Gen denoise-loop measurement")
+    ap.add_argument("--no-beam", action="store_true", help="skip the secondary 5-beam measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

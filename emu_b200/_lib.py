@@ -57,7 +57,7 @@ class EmuVAEConfig(C.Structure):
 
 # every symbol declared in include/emu_b200.h (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
+    "emu_beam_topk", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
     "emu_vit_forward", "emu_llm_reset", "emu_llm_embed", "emu_llm_prefill", "emu_llm_decode", "emu_llm_cur_len",
     "emu_project", "emu_cformer_forward", "emu_unet_configure", "emu_unet_forward", "emu_denoise_step",
     "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
@@ -204,6 +204,13 @@ class Engine:
     def cur_len(self):
         return self.lib.emu_llm_cur_len(self.h)
 
+    def beam_topk(self, logits, running_scores, batch, beams, keep, ban_id=-1, prev_tokens=None, repetition_penalty=1.0):
+        if ban_id is None:
+            ban_id = -1
+        lg = logits if (logits.dtype == torch.float32 and logits.is_contiguous()) else logits.float().contiguous()
+        return op_beam_topk(lg, running_scores, batch, beams, keep, ban_id=int(ban_id), prev_tokens=prev_tokens,
+                            repetition_penalty=float(repetition_penalty))
+
     # ---- Emu1 Causal-Former ----
     def cformer_forward(self, vit_tokens, n_queries, out_dim):
         B, Nv, _ = vit_tokens.shape
@@ -325,6 +332,23 @@ def op_attn_prefill(q, k, v, scale, causal=False, kv_start=None, bias=None):
                                  1 if causal else 0, _ptr(kv_start), _ptr(bias), _stream())
     check(rc)
     return out
+
+
+def op_beam_topk(logits, running_scores, batch, beams, keep, ban_id=-1, prev_tokens=None, repetition_penalty=1.0):
+    """logits [batch*beams, V] fp32 (overwritten), running_scores [batch, beams] fp32 -> (scores [batch, keep] fp32,
+    flat indices [batch, keep] int64 = beam*V + token), HF _beam_search step semantics."""
+    require_cuda()
+    lib = load()
+    V = logits.shape[-1]
+    assert logits.dtype == torch.float32 and logits.is_contiguous()
+    rs = running_scores.to(torch.float32).contiguous().view(-1) if running_scores is not None else None
+    prev = prev_tokens.to(torch.int64).contiguous() if prev_tokens is not None and prev_tokens.numel() else None
+    out_lp = torch.empty(batch, keep, dtype=torch.float32, device=logits.device)
+    out_idx = torch.empty(batch, keep, dtype=torch.int32, device=logits.device)
+    check(lib.emu_beam_topk(_ptr(logits), _ptr(rs), batch, beams, V, keep, ban_id, _ptr(prev),
+                            prev.shape[1] if prev is not None else 0, C.c_float(repetition_penalty), _ptr(out_lp),
+                            _ptr(out_idx), _stream()))
+    return out_lp, out_idx.to(torch.int64)
 
 
 def op_attn_decode(q, k_cache, v_cache, pos, start, scale, max_len):

@@ -397,7 +397,7 @@ int attn_prefill_tc(const AttnArgs& a, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(a.q) & 15) || (reinterpret_cast<uintptr_t>(a.k) & 15) || (reinterpret_cast<uintptr_t>(a.v) & 15))
     return EMU_ERR_UNSUPPORTED;
   if (a.H > 65535 || a.B > 65535) return EMU_ERR_UNSUPPORTED;
-  if (a.D <= 64) return launch_attn_tc<64, 128>(a, st);
+  if (a.D <= 64) return a.Nk <= 64 ? launch_attn_tc<64, 64>(a, st) : launch_attn_tc<64, 128>(a, st);  // cross-attn: 64 keys
   return launch_attn_tc<128, 64>(a, st);
 }
 

@@ -14,6 +14,7 @@
 //                 32-column chunks), fused bias / GELU / residual / SwiGLU / GEGLU with 16-byte operand loads
 //                 prefetched ahead of the accumulator, bf16 or fp32 stores
 // A and W are both K-major, so neither operand needs a transpose anywhere in the model.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -55,7 +56,10 @@ struct GemmParams {
   int pdl;  // launched with programmatic dependent launch: griddepcontrol.wait before touching activations
 };
 
-template <int BN>
+// CL = thread-block cluster size along M (1 or 2).  With CL == 2 the two CTAs of a cluster work on vertically adjacent
+// output tiles (same weight columns): each loads HALF of the W tile and TMA-multicasts it into both CTAs' shared memory,
+// so W crosses the L2->SM fabric once per pair — the fabric, not the tensor pipe, bounds the BN <= 160 tiles.
+template <int BN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr int kStages = GemmSmem<BN>::kStages;
@@ -75,7 +79,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int tiles_m = (p.M + BM - 1) / BM;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
+  // work units: one tile (CL == 1) or one vertical tile pair (CL == 2; a ragged last pair computes a dummy tile whose
+  // loads are out of bounds = zeros and whose rows fail the epilogue's row check, keeping the pair in lock step)
+  const int units_m = (tiles_m + CL - 1) / CL;
+  const int num_tiles = units_m * tiles_n;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
   const int kblocks_per_tap = p.conv ? (p.Cin + BK - 1) / BK : (p.K + BK - 1) / BK;
   const int num_kb = p.conv ? 9 * kblocks_per_tap : kblocks_per_tap;
 
@@ -84,7 +93,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);  // one tcgen05.commit arrival from every CTA that reads the multicast stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -95,7 +104,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (p.pdl) pdl_launch_dependents();  // the next kernel of the chain may start its own prologue now
   if (warp == 1) tmem_alloc(tmem_base_slot, kTmemCols);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast at them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -105,8 +115,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.pdl) pdl_wait();  // activations (A) come from the predecessor; everything above overlapped its tail
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile % tiles_m, tn = tile / tiles_m;
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+        const int tm = (tile % units_m) * CL + crank, tn = tile / units_m;
         int img = 0, h0 = 0, w0 = 0;
         if (p.conv) {
           const int tiles_w = p.W / p.tw, tiles_h = p.H / p.th;
@@ -119,14 +129,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + BM * BK * 2;
           mbar_expect_tx(&full_bar[stage], kStageBytes);
+          int kcol;
           if (p.conv) {
             const int tap = kb / kblocks_per_tap, cb = kb % kblocks_per_tap;
             const int r = tap / 3, s = tap % 3;
             tma_load_4d(sa, &tmA, &full_bar[stage], cb * BK, w0 + s - 1, h0 + r - 1, img);
-            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + cb * BK, tn * BN);
+            kcol = tap * p.Cin + cb * BK;
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, tm * BM);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, tn * BN);
+            kcol = kb * BK;
+          }
+          if (CL > 1) {
+            // my half of the W tile, written to the same offset in both CTAs; the peer supplies the other half
+            constexpr int kHalf = BN / CL;
+            tma_load_2d_mc(sb + crank * kHalf * BK * 2, &tmB, &full_bar[stage], kcol, tn * BN + crank * kHalf,
+                           (uint16_t)((1u << CL) - 1));
+          } else {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kcol, tn * BN);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -140,7 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -156,7 +175,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr>>4) field
             umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          // frees the smem stage when these MMAs retire — in every CTA of the cluster (the peer's producer overwrites
+          // half of OUR stage, so it must see our consumption too)
+          if (CL > 1) umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CL) - 1));
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
@@ -172,8 +194,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.pdl) pdl_wait();  // residual / bias2 are predecessor outputs and C may alias a buffer it still reads
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile % tiles_m, tn = tile / tiles_m;
+    for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+      const int tm = (tile % units_m) * CL + crank, tn = tile / units_m;
       // output row owned by this thread
       long row;
       const int r_in_tile = q * 32 + lane;
@@ -187,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {
         row = (long)tm * BM + r_in_tile;
       }
-      const bool row_ok = row < p.M;
+      const bool row_ok = row < p.M && tm < tiles_m;
       const bool pair = (p.epi == EPI_SWIGLU || p.epi == EPI_GEGLU);
       // 16-byte paths need aligned rows; everything in the models is, ragged shapes take the scalar path
       const bool vec_res = p.residual != nullptr && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
@@ -348,7 +370,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // nobody leaves while the peer can still multicast into / arrive on its shared memory
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -436,18 +459,68 @@ int make_tmap_bnhd(CUtensorMap* out, const void* base, int D, long N, int H, int
   return r == CUDA_SUCCESS ? EMU_OK : EMU_ERR_CUDA;
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+template <int BN, int CL>
+static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
+  static int max_ctas = kNumSMs;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kBytes) !=
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kBytes) !=
         cudaSuccess)
       return EMU_ERR_CUDA;
+    if (CL > 1) {
+      // how many clusters can be resident at once (GPC boundaries may leave an SM without a partner)
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(kNumSMs / CL * CL);
+      q.blockDim = dim3(kGemmThreads);
+      q.dynamicSmemBytes = GemmSmem<BN>::kBytes;
+      cudaLaunchAttribute a[1];
+      a[0].id = cudaLaunchAttributeClusterDimension;
+      a[0].val.clusterDim.x = CL; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+      q.attrs = a;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, CL>, &q) == cudaSuccess && n > 0) max_ctas = n * CL;
+      else cudaGetLastError();
+      if (max_ctas > kNumSMs) max_ctas = kNumSMs / CL * CL;
+    }
     attr_set = true;
   }
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  return launch_kernel(gemm_tc_kernel<BN>, dim3(grid), dim3(kGemmThreads), GemmSmem<BN>::kBytes, st, p.pdl, tmA, tmB, p);
+  const int units = (((p.M + BM - 1) / BM + CL - 1) / CL) * ((p.N + BN - 1) / BN);
+  int grid = units * CL < max_ctas ? units * CL : max_ctas;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = GemmSmem<BN>::kBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (p.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, tmA, tmB, p) == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+}
+
+// cluster (W multicast) whenever there are at least two tile rows; force: 1024 = off, 2048 = on (tests / A-B runs)
+static bool use_cluster(int M, int force) {
+  static int env = -1;
+  if (env < 0) {
+    const char* v = getenv("EMU_GEMM_CLUSTER");
+    env = v ? atoi(v) : 1;
+  }
+  if (force & 1024) return false;
+  const int tiles_m = (M + BM - 1) / BM;
+  if (force & 2048) return tiles_m >= 1;
+  if (!env) return false;
+  return tiles_m >= 2 && (tiles_m % 2 == 0 || tiles_m >= 7);
 }
 
 // Tile width: minimise  waves(BN) x time-per-tile(BN)  over the instantiated widths.  Per K=16 step a tile costs
@@ -498,13 +571,17 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
   p.C = e.C; p.ldc = e.ldc; p.bias = e.bias; p.residual = e.residual; p.ldr = e.ldr;
   p.bias2 = e.bias2; p.bias2_rows = e.bias2_rows > 0 ? e.bias2_rows : 1;
   p.epi = e.mode; p.out_fp32 = e.out_fp32; p.conv = 0; p.pdl = g_pdl_chain;
-  const int bn = e.force_bn ? e.force_bn : pick_bn(M, N);
+  const int bn = (e.force_bn & 1023) ? (e.force_bn & 1023) : pick_bn(M, N);
+  const bool cl = use_cluster(M, e.force_bn);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmB, W, N, K, ldw, bn);
+  rc = make_tmap_2d(&tmB, W, N, K, ldw, cl ? bn / 2 : bn);
   if (rc) return rc;
-  return dispatch_bn(bn, [&](auto w) { return launch_gemm<decltype(w)::value>(tmA, tmB, p, st); });
+  return dispatch_bn(bn, [&](auto w) {
+    constexpr int kBN = decltype(w)::value;
+    return cl ? launch_gemm_cl<kBN, 2>(tmA, tmB, p, st) : launch_gemm_cl<kBN, 1>(tmA, tmB, p, st);
+  });
 }
 
 // 3x3 stride-1 pad-1 convolution on NHWC bf16 as an implicit GEMM. Wk is [Cout, 9*Cin] with k = (r*3+s)*Cin + c.
@@ -521,13 +598,17 @@ int conv3x3_bf16(const bf16* X, int NB, int H, int W, int Cin, const bf16* Wk, i
   p.bias2 = e.bias2; p.bias2_rows = e.bias2_rows > 0 ? e.bias2_rows : 1;
   p.epi = e.mode; p.out_fp32 = e.out_fp32; p.pdl = g_pdl_chain;
   p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tw = tw; p.th = th;
-  const int bn = e.force_bn ? e.force_bn : pick_bn(p.M, Cout);
+  const int bn = (e.force_bn & 1023) ? (e.force_bn & 1023) : pick_bn(p.M, Cout);
+  const bool cl = use_cluster(p.M, e.force_bn);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_nhwc(&tmA, X, NB, H, W, Cin, tw, th);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmB, Wk, Cout, 9L * Cin, 9L * Cin, bn);
+  rc = make_tmap_2d(&tmB, Wk, Cout, 9L * Cin, 9L * Cin, cl ? bn / 2 : bn);
   if (rc) return rc;
-  return dispatch_bn(bn, [&](auto w) { return launch_gemm<decltype(w)::value>(tmA, tmB, p, st); });
+  return dispatch_bn(bn, [&](auto w) {
+    constexpr int kBN = decltype(w)::value;
+    return cl ? launch_gemm_cl<kBN, 2>(tmA, tmB, p, st) : launch_gemm_cl<kBN, 1>(tmA, tmB, p, st);
+  });
 }
 
 }  // namespace emu

@@ -128,16 +128,25 @@ def beam_search(engine, inputs_embeds, attention_mask, num_beams, max_new_tokens
 
     cur_len = 0
     while True:
-        log_probs = torch.log_softmax(logits.float(), dim=-1)
-        if repetition_penalty != 1.0 and cur_len > 0:
-            prev = running_seq[:, :, :cur_len].reshape(Bt * nb, cur_len)
-            sc = torch.gather(log_probs, 1, prev)
-            sc = torch.where(sc < 0, sc * repetition_penalty, sc / repetition_penalty)
-            log_probs = log_probs.scatter(1, prev, sc)
-        if cur_len < min_length:
-            log_probs[:, eos_token_id] = float("-inf")
-        log_probs = log_probs.view(Bt, nb, V) + running_scores[:, :, None]
-        topk_lp, topk_i = torch.topk(log_probs.view(Bt, nb * V), k=keep)
+        if hasattr(engine, "beam_topk"):
+            # device-side step (emu_beam_topk): log_softmax + processors + running score + top-2*beams in the library
+            prev = None
+            if repetition_penalty != 1.0 and cur_len > 0:
+                prev = running_seq[:, :, :cur_len].reshape(Bt * nb, cur_len)
+            topk_lp, topk_i = engine.beam_topk(logits, running_scores, Bt, nb, keep,
+                                               ban_id=eos_token_id if cur_len < min_length else -1, prev_tokens=prev,
+                                               repetition_penalty=repetition_penalty)
+        else:  # engines without the op (the CPU oracle stub used by tests/test_generation_cpu.py)
+            log_probs = torch.log_softmax(logits.float(), dim=-1)
+            if repetition_penalty != 1.0 and cur_len > 0:
+                prev = running_seq[:, :, :cur_len].reshape(Bt * nb, cur_len)
+                sc = torch.gather(log_probs, 1, prev)
+                sc = torch.where(sc < 0, sc * repetition_penalty, sc / repetition_penalty)
+                log_probs = log_probs.scatter(1, prev, sc)
+            if cur_len < min_length:
+                log_probs[:, eos_token_id] = float("-inf")
+            log_probs = log_probs.view(Bt, nb, V) + running_scores[:, :, None]
+            topk_lp, topk_i = torch.topk(log_probs.view(Bt, nb * V), k=keep)
         topk_beam = topk_i // V
         topk_ids = topk_i % V
         topk_run_bi = _gather_beams(run_beam_idx, topk_beam)

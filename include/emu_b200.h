@@ -164,6 +164,17 @@ int emu_op_rmsnorm(const void* x, const void* w, void* y, int rows, int cols, fl
 int emu_op_layernorm(const void* x, const void* w, const void* b, const void* residual, void* y, int rows, int cols,
                      float eps, emu_stream_t s);
 
+/* Device-side beam-search step.  Replaces, inside HF GenerationMixin._beam_search as driven by
+ * Emu2/emu/emu.py:213-229 (num_beams=5, length_penalty=-1), the vocabulary-wide work of one step:
+ *   log_softmax(logits) -> RepetitionPenaltyLogitsProcessor -> MinLength EOS ban -> + running beam score ->
+ *   topk(2*beams) over the flattened [beams*vocab] scores of every batch row.
+ * logits [batch*beams, vocab] fp32 is used as scratch (overwritten); running_scores [batch*beams] may be NULL;
+ * prev_tokens [batch*beams, prev_len] int64 (may be NULL); ban_id < 0 disables the ban.  Outputs out_lp / out_idx
+ * [batch, keep]: scores (largest first) and flat indices beam*vocab + token. */
+int emu_beam_topk(float* logits, const float* running_scores, int batch, int beams, int vocab, int keep, int ban_id,
+                  const long long* prev_tokens, int prev_len, float repetition_penalty, float* out_lp, int* out_idx,
+                  emu_stream_t s);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t emu_launch_count(void);
 const char* emu_version(void);

@@ -26,6 +26,9 @@ def _rand(shape, seed, scale=1.0):
     (128, 128, 64, 128), (1, 64, 64, 64), (75, 320, 192, 0), (1025, 5376, 1792, 0), (300, 1000, 584, 64),
     (257, 768, 1408, 128), (4096, 640, 640, 256), (64, 6656, 1792, 0), (513, 264, 72, 0),
     (2048, 1280, 1280, 0), (2048, 1280, 640, 160), (300, 1000, 584, 96), (700, 900, 320, 192), (257, 1344, 256, 224),
+    # 2048 = force the 2-CTA cluster (W tile TMA-multicast), 1024 = force it off; ragged / odd tile-row counts included
+    (2048, 1280, 1280, 2048 + 160), (2048, 1280, 1280, 1024 + 160), (385, 520, 448, 2048 + 128), (1025, 1792, 1792, 2048),
+    (100, 200, 136, 2048 + 64), (4096, 640, 640, 2048 + 256),
 ])
 def test_gemm_plain(cuda, M, N, K, bn):
     from emu_b200 import _lib
@@ -222,3 +225,32 @@ def test_gemv_rope_qkv(cuda):
     for b in range(B):
         assert O.rel_err(deinterleave(kc[b, :, int(pos[b])].cpu()), kr[b]) < TOL_BF16
         assert O.rel_err(vc[b, :, int(pos[b])].cpu(), v[b]) < TOL_BF16
+
+
+@pytest.mark.parametrize("Bt,nb,V,prev_len,ban", [(1, 5, 32272, 0, -1), (2, 3, 32272, 7, 2), (1, 1, 1000, 3, -1), (3, 4, 517, 0, 5)])
+def test_beam_topk(cuda, Bt, nb, V, prev_len, ban):
+    """emu_beam_topk vs the torch formulation of one HF _beam_search step (log_softmax -> repetition penalty -> EOS ban
+    -> + running score -> topk(2*beams) over beams*vocab)."""
+    from emu_b200 import _lib
+    g = torch.Generator().manual_seed(70)
+    logits = torch.randn(Bt * nb, V, generator=g) * 3
+    running = torch.randn(Bt, nb, generator=g)
+    running[:, -1] = -1e9 if nb > 1 else running[:, -1]
+    prev = torch.randint(0, V, (Bt * nb, prev_len), generator=g) if prev_len else None
+    if prev is not None:
+        prev[:, -1] = prev[:, 0]  # a duplicate: the penalty must apply once
+    keep, pen = 2 * nb, 1.3
+    lp = torch.log_softmax(logits, -1)
+    if prev is not None:
+        sc = torch.gather(lp, 1, prev)
+        sc = torch.where(sc < 0, sc * pen, sc / pen)
+        lp = lp.scatter(1, prev, sc)
+    if ban >= 0:
+        lp[:, ban] = float("-inf")
+    lp = lp.view(Bt, nb, V) + running[:, :, None]
+    ref_v, ref_i = torch.topk(lp.view(Bt, nb * V), k=keep)
+    out_v, out_i = _lib.op_beam_topk(logits.cuda(), running.cuda(), Bt, nb, keep, ban_id=ban,
+                                     prev_tokens=None if prev is None else prev.cuda(), repetition_penalty=pen)
+    real = ref_v > -1e8  # candidates of a dead (-1e9) beam tie at fp32 resolution: order is don't-care
+    assert torch.allclose(out_v.cpu()[real], ref_v[real], rtol=1e-5, atol=1e-4)
+    assert torch.equal(out_i.cpu()[real], ref_i[real])
