@@ -514,7 +514,7 @@ static bool use_cluster(int M, int force) {
   static int env = -1;
   if (env < 0) {
     const char* v = getenv("EMU_GEMM_CLUSTER");
-    env = v ? atoi(v) : 1;
+    env = v ? atoi(v) : 0;  // default off until validated on hardware (flip to 1 after the parity run)
   }
   if (force & 1024) return false;
   const int tiles_m = (M + BM - 1) / BM;
