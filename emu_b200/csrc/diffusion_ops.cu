@@ -12,7 +12,7 @@ namespace emu {
 // ----------------------------------------------------------------------------------------------
 // GroupNorm over NHWC: stage 1 — per (image, pixel-chunk) partial sums for every group (coalesced row reads)
 // ----------------------------------------------------------------------------------------------
-constexpr int kGnChunks = 64;  // partial-sum slots per image
+constexpr int kGnChunks = 128;  // partial-sum slots per image (x NB CTAs of 512 threads: ~2 CTAs per SM in flight)
 
 __global__ void __launch_bounds__(512) gn_partial_kernel(const bf16* __restrict__ x, float* __restrict__ part, int HW,
                                                          int C, int groups, int pdl) {
@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(const bf16* __restrict_
     float s[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = s2[j] = 0.f;
+#pragma unroll 4
     for (long idx = threadIdx.x; idx < total; idx += stride) {
       const long pix = idx / vecC;
       const uint4 v = *reinterpret_cast<const uint4*>(base + pix * C + cv * 8);
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(const bf16* __restrict_
 }
 
 // stage 2 — normalise (+ optional SiLU); mean/rstd are rebuilt from the partials by every CTA (fixed order)
-__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ part,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ part_,
                                                        const bf16* __restrict__ w, const bf16* __restrict__ bsh,
                                                        bf16* __restrict__ y, int HW, int C, int groups, float eps,
                                                        int do_silu, int pdl) {
@@ -81,17 +82,37 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   }
   const int b = blockIdx.y;
   const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+  // rebuild mean / rstd from the kGnChunks partial sums: (group, chunk-slice) pairs spread over the whole CTA so the
+  // dependent-load chain is kGnChunks / nparts long instead of kGnChunks; fixed summation order -> deterministic
+  __shared__ float ps[256 * 2];
+  const int nparts = groups <= 256 ? 256 / groups : 1;
+  for (int g0 = 0; g0 < groups; g0 += 256) {
+    const int g = g0 + (int)threadIdx.x % (groups < 256 ? groups : 256);
+    const int part = (int)threadIdx.x / (groups < 256 ? groups : 256);
     float s = 0.f, s2 = 0.f;
-    for (int c = 0; c < kGnChunks; ++c) {
-      s += part[(((long)b * kGnChunks + c) * groups + g) * 2];
-      s2 += part[(((long)b * kGnChunks + c) * groups + g) * 2 + 1];
+    if (g < groups && part < nparts) {
+      for (int c = part; c < kGnChunks; c += nparts) {
+        s += part_[(((long)b * kGnChunks + c) * groups + g) * 2];
+        s2 += part_[(((long)b * kGnChunks + c) * groups + g) * 2 + 1];
+      }
     }
-    const float n = (float)HW * cpg;
-    const float mean = s / n;
-    const float var = fmaxf(s2 / n - mean * mean, 0.f);
-    st[g * 2] = mean;
-    st[g * 2 + 1] = rsqrtf(var + eps);
+    ps[threadIdx.x * 2] = s;
+    ps[threadIdx.x * 2 + 1] = s2;
+    __syncthreads();
+    if (part == 0 && g < groups) {
+      const int gw = groups < 256 ? groups : 256;
+      float a = 0.f, a2 = 0.f;
+      for (int q = 0; q < nparts; ++q) {
+        a += ps[(q * gw + (int)threadIdx.x) * 2];
+        a2 += ps[(q * gw + (int)threadIdx.x) * 2 + 1];
+      }
+      const float n = (float)HW * cpg;
+      const float mean = a / n;
+      const float var = fmaxf(a2 / n - mean * mean, 0.f);
+      st[g * 2] = mean;
+      st[g * 2 + 1] = rsqrtf(var + eps);
+    }
+    __syncthreads();
   }
   __syncthreads();
   // every thread owns ONE 8-channel vector (its affine constants live in registers) and walks down the pixels
