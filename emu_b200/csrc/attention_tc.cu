@@ -16,6 +16,8 @@
 // O accumulates in TMEM across KV blocks.  The running max used for the exponent is only advanced when it grew by more
 // than 2^8 (exact: the final 1/l normalisation uses the same stale max), so the O rescale (TMEM ld/st) is rare.
 // While tile 0's softmax runs, the tensor core works on tile 1 and vice versa.
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -59,6 +61,7 @@ struct AtParams {
   int causal;
   float scale_log2;  // scale * log2(e)
   int pdl;
+  int poly_mask;  // bit pc set: the pc-th 8-key group of every 64-key chunk uses ex2_poly instead of MUFU.EX2
   int q_hf, k_hf, v_hf;  // tensor-map coordinate order: 1 = (d, head, token, batch), 0 = (d, token, head, batch)
 };
 
@@ -94,6 +97,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-4 polynomial for 2^f
+// (|rel err| < 5e-5, P is rounded to bf16 right after), exponent patched in with integer adds.  The softmax warps are
+// bound by the 16-op/clk XU pipe (ex2 + bf16 packing; ncu: profiles/r01_ncu_full_attn_tc_4096.txt), so a share of the
+// exponentials is moved here — the same trick FlashAttention-4 uses on Blackwell.
+__device__ __forceinline__ float ex2_poly(float x) {
+  const bool zero = x < -125.f;  // masked (-inf) and underflowing arguments give exactly 0, like ex2.approx.ftz
+  x = fmaxf(x, -125.f);
+  const float r = x + 12582912.f;              // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (r - 12582912.f);
+  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
+  p = fmaf(p, f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return zero ? 0.f : __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
 }
 
 template <int DT, int BN>
@@ -313,10 +331,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int pc = 0; pc < 8; ++pc) {
           float e[8];
+          if ((p.poly_mask >> pc) & 1) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            e[i] = ex2_approx(fmaf(s[kc * 64 + pc * 8 + i], c, -mu));
-            l += e[i];
+            for (int i = 0; i < 8; ++i) {
+              e[i] = ex2_poly(fmaf(s[kc * 64 + pc * 8 + i], c, -mu));
+              l += e[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              e[i] = ex2_approx(fmaf(s[kc * 64 + pc * 8 + i], c, -mu));
+              l += e[i];
+            }
           }
           uint4 w;
           w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]); w.z = pack_bf16(e[4], e[5]); w.w = pack_bf16(e[6], e[7]);
@@ -382,6 +408,12 @@ int launch_attn_tc(const AttnArgs& a, cudaStream_t st) {
   p.kv_start = a.kv_start; p.Nq = a.Nq; p.Nk = a.Nk; p.D = a.D; p.causal = a.causal;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.pdl = g_pdl_chain;
+  static int poly = -1;
+  if (poly < 0) {
+    const char* v = getenv("EMU_ATTN_POLY");
+    poly = v ? (int)strtol(v, nullptr, 0) & 0xff : 0x00;  // default off until measured; 0xAA = every second group
+  }
+  p.poly_mask = poly;
   dim3 grid((a.Nq + 255) / 256, a.H, a.B);
   return launch_kernel(attn_tc_kernel<DT, BN>, grid, dim3(kAtThreads), C::kSmem, st, p.pdl, tq, tk, tv, p);
 }

@@ -509,17 +509,20 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, tmA, tmB, p) == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
-// cluster (W multicast) whenever there are at least two tile rows; force: 1024 = off, 2048 = on (tests / A-B runs)
-static bool use_cluster(int M, int force) {
-  static int env = -1;
-  if (env < 0) {
+// Cluster mode (W tile TMA-multicast over a 2-CTA cluster).  Measured on B200 (profiles/r01_gemm_bench_cluster.txt):
+// +8..15 % on the K >= 5760 implicit-GEMM convolutions, -2..8 % on the one-wave linear layers (cluster start-up and
+// lock step cost more than the halved W traffic saves).  Default: convolutions only.  EMU_GEMM_CLUSTER = 0 (never),
+// 1 (always), unset (convs); force bits: 1024 = off, 2048 = on (tests / A-B runs).
+static bool use_cluster(int M, int force, bool is_conv) {
+  static int env = -2;
+  if (env == -2) {
     const char* v = getenv("EMU_GEMM_CLUSTER");
-    env = v ? atoi(v) : 0;  // default off until validated on hardware (flip to 1 after the parity run)
+    env = v ? atoi(v) : -1;
   }
   if (force & 1024) return false;
   const int tiles_m = (M + BM - 1) / BM;
   if (force & 2048) return tiles_m >= 1;
-  if (!env) return false;
+  if (env == 0 || (env < 0 && !is_conv)) return false;
   return tiles_m >= 2 && (tiles_m % 2 == 0 || tiles_m >= 7);
 }
 
@@ -572,7 +575,7 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
   p.bias2 = e.bias2; p.bias2_rows = e.bias2_rows > 0 ? e.bias2_rows : 1;
   p.epi = e.mode; p.out_fp32 = e.out_fp32; p.conv = 0; p.pdl = g_pdl_chain;
   const int bn = (e.force_bn & 1023) ? (e.force_bn & 1023) : pick_bn(M, N);
-  const bool cl = use_cluster(M, e.force_bn);
+  const bool cl = use_cluster(M, e.force_bn, false);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
@@ -599,7 +602,7 @@ int conv3x3_bf16(const bf16* X, int NB, int H, int W, int Cin, const bf16* Wk, i
   p.epi = e.mode; p.out_fp32 = e.out_fp32; p.pdl = g_pdl_chain;
   p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tw = tw; p.th = th;
   const int bn = (e.force_bn & 1023) ? (e.force_bn & 1023) : pick_bn(p.M, Cout);
-  const bool cl = use_cluster(p.M, e.force_bn);
+  const bool cl = use_cluster(p.M, e.force_bn, true);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_nhwc(&tmA, X, NB, H, W, Cin, tw, th);
   if (rc) return rc;
