@@ -61,7 +61,6 @@ struct AtParams {
   int causal;
   float scale_log2;  // scale * log2(e)
   int pdl;
-  int poly_mask;  // bit pc set: the pc-th 8-key group of every 64-key chunk uses ex2_poly instead of MUFU.EX2
   int q_hf, k_hf, v_hf;  // tensor-map coordinate order: 1 = (d, head, token, batch), 0 = (d, token, head, batch)
 };
 
@@ -98,21 +97,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-4 polynomial for 2^f
-// (|rel err| < 5e-5, P is rounded to bf16 right after), exponent patched in with integer adds.  The softmax warps are
-// bound by the 16-op/clk XU pipe (ex2 + bf16 packing; ncu: profiles/r01_ncu_full_attn_tc_4096.txt), so a share of the
-// exponentials is moved here — the same trick FlashAttention-4 uses on Blackwell.
-__device__ __forceinline__ float ex2_poly(float x) {
-  const bool zero = x < -125.f;  // masked (-inf) and underflowing arguments give exactly 0, like ex2.approx.ftz
-  x = fmaxf(x, -125.f);
-  const float r = x + 12582912.f;              // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float f = x - (r - 12582912.f);
-  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
-  p = fmaf(p, f, 0.2402265070f);
-  p = fmaf(p, f, 0.6931471806f);
-  p = fmaf(p, f, 1.0f);
-  return zero ? 0.f : __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
-}
+// (Tried and removed: FlashAttention-4's trick of evaluating a share of the exponentials with a polynomial on the FMA
+//  pipe.  ncu shows the XU pipe — ex2 + bf16 packing — as the busiest pipe of this kernel at 58 %, but the softmax warps
+//  are instruction-issue bound: every share of polynomial exp2 made the kernel slower, 457 -> 332/246/192 TFLOP/s at
+//  0/25/50 % on the 4096-token head-dim-64 shape, the 0 % figure being the cost of merely carrying the runtime switch.)
 
 template <int DT, int BN>
 __global__ void __launch_bounds__(kAtThreads, 1)
@@ -279,7 +267,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const float c = p.scale_log2;
     const int lo = p.kv_start ? p.kv_start[batch] : 0;
     const int hi = p.causal ? min(p.Nk - 1, qi + off) : p.Nk - 1;
-    float m_run = -INFINITY, m_used = -INFINITY, l = 0.f;
+    float m_run = -INFINITY, m_used = -INFINITY;
+    float l8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < n; ++j) {
       mbar_wait(&s_full[t], (uint32_t)j & 1u);
       tc_fence_after();
@@ -295,9 +284,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < BN; ++i) s[i] = (k0 + i < lo || k0 + i > hi) ? -INFINITY : s[i];
       }
-      float mx = s[0];
+      // 8 independent max chains (a single 128-long dependent chain is pure latency for a lone warp per sub-partition)
+      float mx8[8];
 #pragma unroll
-      for (int i = 1; i < BN; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 0; i < 8; ++i) mx8[i] = s[i];
+#pragma unroll
+      for (int i = 8; i < BN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], s[i]);
+      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       const float m_new = fmaxf(m_run, mx);
       m_run = m_new;
       if (j > 0) {
@@ -311,7 +304,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           f = (m_used == -INFINITY) ? 0.f : ex2_approx((m_used - m_new) * c);
           m_used = m_new;
         }
-        l *= f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) l8[i] *= f;
         if (j > 0) {
 #pragma unroll 1
           for (int cc = 0; cc < DT / 32; ++cc) {
@@ -331,18 +325,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int pc = 0; pc < 8; ++pc) {
           float e[8];
-          if ((p.poly_mask >> pc) & 1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              e[i] = ex2_poly(fmaf(s[kc * 64 + pc * 8 + i], c, -mu));
-              l += e[i];
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              e[i] = ex2_approx(fmaf(s[kc * 64 + pc * 8 + i], c, -mu));
-              l += e[i];
-            }
+          for (int i = 0; i < 8; ++i) {
+            e[i] = ex2_approx(fmaf(s[kc * 64 + pc * 8 + i], c, -mu));
+            l8[i] += e[i];  // 8 independent row-sum chains
           }
           uint4 w;
           w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]); w.z = pack_bf16(e[4], e[5]); w.w = pack_bf16(e[6], e[7]);
@@ -357,6 +343,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (n > 0) {
       mbar_wait(&o_done[t], (uint32_t)(n - 1) & 1u);
       tc_fence_after();
+      const float l = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
       const float inv = l > 0.f ? 1.f / l : 0.f;
       bf16* dst = p.out + (long)batch * p.o_bs + (long)qi * p.o_ts + (long)head * p.o_hs;
 #pragma unroll 1
@@ -408,12 +395,6 @@ int launch_attn_tc(const AttnArgs& a, cudaStream_t st) {
   p.kv_start = a.kv_start; p.Nq = a.Nq; p.Nk = a.Nk; p.D = a.D; p.causal = a.causal;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.pdl = g_pdl_chain;
-  static int poly = -1;
-  if (poly < 0) {
-    const char* v = getenv("EMU_ATTN_POLY");
-    poly = v ? (int)strtol(v, nullptr, 0) & 0xff : 0x00;  // default off until measured; 0xAA = every second group
-  }
-  p.poly_mask = poly;
   dim3 grid((a.Nq + 255) / 256, a.H, a.B);
   return launch_kernel(attn_tc_kernel<DT, BN>, grid, dim3(kAtThreads), C::kSmem, st, p.pdl, tq, tk, tv, p);
 }
