@@ -31,11 +31,16 @@ int make_tmap_bnhd(CUtensorMap* out, const void* base, int D, long N, int H, int
 
 namespace {
 
-constexpr int kAtThreads = 320;
 constexpr int kAtStages = 3;
 
-template <int DT, int BN>
+// SW = softmax warps per (query tile, TMEM lane quarter): 1 -> thread == whole row; 2 -> two warps split the row's key
+// columns (and O columns) and exchange max / sum through shared memory — twice the warps to hide latency with
+template <int DT, int BN, int SW>
 struct AtCfg {
+  static constexpr int kThreads = 64 + 2 * 4 * SW * 32;
+  static constexpr int kCW = BN / SW;              // S columns per softmax warp
+  static constexpr int kOW = DT / SW;              // O columns per softmax warp
+  static_assert(kCW % 32 == 0 && kOW % 32 == 0, "per-warp column slices are moved in 32-column TMEM chunks");
   static constexpr int kDC = DT / 64;              // 64-wide head-dim chunks (one 128 B swizzle row each)
   static constexpr int kKC = BN / 64;              // 64-wide key chunks of P
   static constexpr int kQBytes = 128 * DT * 2;     // one Q tile
@@ -45,7 +50,8 @@ struct AtCfg {
   static constexpr int kOffV = kOffK + kAtStages * kKVBytes;
   static constexpr int kOffP = kOffV + kAtStages * kKVBytes;
   static constexpr int kOffBar = kOffP + 2 * kPBytes;
-  static constexpr int kSmem = kOffBar + 32 * 8 + 1024;  // + barriers + 1024 B alignment slack
+  static constexpr int kOffX = kOffBar + 32 * 8;         // [2 parities][2 tiles][SW][128] fp32 max exchange, then sums
+  static constexpr int kSmem = kOffX + 2 * 2 * 2 * 128 * 4 + 1024;  // + 1024 B alignment slack
   static constexpr int kTmemS = 0;                 // S_t at t*BN
   static constexpr int kTmemO = 2 * BN;            // O_t at 2*BN + t*DT
   static constexpr int kTmemCols = 512;
@@ -102,11 +108,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 //  are instruction-issue bound: every share of polynomial exp2 made the kernel slower, 457 -> 332/246/192 TFLOP/s at
 //  0/25/50 % on the 4096-token head-dim-64 shape, the 0 % figure being the cost of merely carrying the runtime switch.)
 
-template <int DT, int BN>
-__global__ void __launch_bounds__(kAtThreads, 1)
+template <int DT, int BN, int SW>
+__global__ void __launch_bounds__(AtCfg<DT, BN, SW>::kThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AtParams p) {
-  using C = AtCfg<DT, BN>;
+  using C = AtCfg<DT, BN, SW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
@@ -156,8 +162,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&s_free[t], 4);
-      mbar_init(&p_ready[t], 4);
+      mbar_init(&s_free[t], 4 * SW);
+      mbar_init(&p_ready[t], 4 * SW);
       mbar_init(&o_done[t], 1);
     }
     mbar_fence_init();
@@ -255,14 +261,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else {
     // ===================== softmax / correction / epilogue warps =====================
-    const int t = (warp - 2) >> 2;
-    const int quad = warp & 3;  // TMEM lane quarter this warp may access
+    constexpr int CW = C::kCW, OW = C::kOW;
+    const int sw = warp - 2;
+    const int t = sw / (4 * SW);
+    const int half = (sw % (4 * SW)) >> 2;  // which column slice of the row this warp owns (0 when SW == 1)
+    const int quad = warp & 3;              // TMEM lane quarter this warp may access
     const int r = quad * 32 + lane;
     const int qi = q0 + t * 128 + r;
+    const int cbase = half * CW;            // first S column / key of this warp inside a KV block
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t tS = lane_base + C::kTmemS + t * BN;
-    const uint32_t tO = lane_base + C::kTmemO + t * DT;
+    const uint32_t tS = lane_base + C::kTmemS + t * BN + cbase;
+    const uint32_t tO = lane_base + C::kTmemO + t * DT + half * OW;
     uint8_t* Pt = smem + C::kOffP + t * C::kPBytes + (r >> 3) * 1024 + (r & 7) * 128;
+    float* xch = reinterpret_cast<float*>(smem + C::kOffX);  // [parity][tile][slice][row]
+    const int pair_bar = 1 + t * 4 + quad;                   // named barrier shared by the SW warps of this (tile, quarter)
     const int n = nb[t];
     const float c = p.scale_log2;
     const int lo = p.kv_start ? p.kv_start[batch] : 0;
@@ -272,25 +284,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int j = 0; j < n; ++j) {
       mbar_wait(&s_full[t], (uint32_t)j & 1u);
       tc_fence_after();
-      float s[BN];
+      float s[CW];
 #pragma unroll
-      for (int cc = 0; cc < BN / 32; ++cc) tmem_ld_32x32(tS + cc * 32, reinterpret_cast<uint32_t*>(s) + cc * 32);
+      for (int cc = 0; cc < CW / 32; ++cc) tmem_ld_32x32(tS + cc * 32, reinterpret_cast<uint32_t*>(s) + cc * 32);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[t]);
-      const int k0 = j * BN;
-      if (k0 < lo || k0 + BN - 1 > hi) {
+      const int k0 = j * BN + cbase;
+      if (k0 < lo || k0 + CW - 1 > hi) {
 #pragma unroll
-        for (int i = 0; i < BN; ++i) s[i] = (k0 + i < lo || k0 + i > hi) ? -INFINITY : s[i];
+        for (int i = 0; i < CW; ++i) s[i] = (k0 + i < lo || k0 + i > hi) ? -INFINITY : s[i];
       }
-      // 8 independent max chains (a single 128-long dependent chain is pure latency for a lone warp per sub-partition)
+      // 8 independent max chains (a single long dependent chain is pure latency for a lone warp per sub-partition)
       float mx8[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) mx8[i] = s[i];
 #pragma unroll
-      for (int i = 8; i < BN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], s[i]);
-      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+      for (int i = 8; i < CW; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], s[i]);
+      float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+      if (SW > 1) {
+        // combine the row maximum of the column slices (slots alternate with j so one barrier per block suffices)
+        float* slot = xch + (((j & 1) * 2 + t) * 2) * 128;
+        slot[half * 128 + r] = mx;
+        asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "r"(32 * SW) : "memory");
+        mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
+      }
       const float m_new = fmaxf(m_run, mx);
       m_run = m_new;
       if (j > 0) {
@@ -298,7 +317,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_after();
       }
       const bool need = (m_new - m_used) * c > 8.f;
-      if (__any_sync(0xffffffffu, need)) {
+      if (__any_sync(0xffffffffu, need)) {  // identical in every warp that shares these rows (same m_new, m_used)
         float f = 1.f;
         if (m_new != -INFINITY) {
           f = (m_used == -INFINITY) ? 0.f : ex2_approx((m_used - m_new) * c);
@@ -308,7 +327,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int i = 0; i < 8; ++i) l8[i] *= f;
         if (j > 0) {
 #pragma unroll 1
-          for (int cc = 0; cc < DT / 32; ++cc) {
+          for (int cc = 0; cc < OW / 32; ++cc) {
             uint32_t v[32];
             tmem_ld_32x32(tO + cc * 32, v);
             tmem_ld_wait();
@@ -321,19 +340,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       const float mu = (m_used == -INFINITY) ? 0.f : m_used * c;
 #pragma unroll
-      for (int kc = 0; kc < C::kKC; ++kc) {
+      for (int g = 0; g < CW / 8; ++g) {
+        const int kk = cbase + g * 8;          // key index inside the block
+        const int kc = kk >> 6, pc = (kk >> 3) & 7;
+        float e[8];
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc) {
-          float e[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            e[i] = ex2_approx(fmaf(s[kc * 64 + pc * 8 + i], c, -mu));
-            l8[i] += e[i];  // 8 independent row-sum chains
-          }
-          uint4 w;
-          w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]); w.z = pack_bf16(e[4], e[5]); w.w = pack_bf16(e[6], e[7]);
-          *reinterpret_cast<uint4*>(Pt + kc * (128 * 128) + ((pc ^ (r & 7)) << 4)) = w;
+        for (int i = 0; i < 8; ++i) {
+          e[i] = ex2_approx(fmaf(s[g * 8 + i], c, -mu));
+          l8[i] += e[i];  // 8 independent row-sum chains
         }
+        uint4 w;
+        w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]); w.z = pack_bf16(e[4], e[5]); w.w = pack_bf16(e[6], e[7]);
+        *reinterpret_cast<uint4*>(Pt + kc * (128 * 128) + ((pc ^ (r & 7)) << 4)) = w;
       }
       fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core's async-proxy reads
       tc_fence_before();
@@ -341,13 +359,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&p_ready[t]);
     }
     if (n > 0) {
+      float l = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
+      if (SW > 1) {
+        // row sum = sum over the column slices, added in slice order so both warps get the same bits
+        float* slot = xch + (((n & 1) * 2 + t) * 2) * 128;
+        slot[half * 128 + r] = l;
+        asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "r"(32 * SW) : "memory");
+        l = slot[r] + slot[128 + r];
+      }
       mbar_wait(&o_done[t], (uint32_t)(n - 1) & 1u);
       tc_fence_after();
-      const float l = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
       const float inv = l > 0.f ? 1.f / l : 0.f;
-      bf16* dst = p.out + (long)batch * p.o_bs + (long)qi * p.o_ts + (long)head * p.o_hs;
+      bf16* dst = p.out + (long)batch * p.o_bs + (long)qi * p.o_ts + (long)head * p.o_hs + half * OW;
 #pragma unroll 1
-      for (int cc = 0; cc < DT / 32; ++cc) {
+      for (int cc = 0; cc < OW / 32; ++cc) {
         uint32_t v[32];
         tmem_ld_32x32(tO + cc * 32, v);
         tmem_ld_wait();
@@ -355,7 +380,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = cc * 32 + g * 8;
-            if (col < p.D) {  // D % 8 == 0
+            if (half * OW + col < p.D) {  // D % 8 == 0
               uint4 w;
               w.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
               w.y = pack_bf16(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
@@ -377,12 +402,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-template <int DT, int BN>
+template <int DT, int BN, int SW>
 int launch_attn_tc(const AttnArgs& a, cudaStream_t st) {
-  using C = AtCfg<DT, BN>;
+  using C = AtCfg<DT, BN, SW>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_tc_kernel<DT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_tc_kernel<DT, BN, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) != cudaSuccess)
       return EMU_ERR_CUDA;
     attr_set = true;
   }
@@ -396,7 +421,7 @@ int launch_attn_tc(const AttnArgs& a, cudaStream_t st) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.pdl = g_pdl_chain;
   dim3 grid((a.Nq + 255) / 256, a.H, a.B);
-  return launch_kernel(attn_tc_kernel<DT, BN>, grid, dim3(kAtThreads), C::kSmem, st, p.pdl, tq, tk, tv, p);
+  return launch_kernel(attn_tc_kernel<DT, BN, SW>, grid, dim3(C::kThreads), C::kSmem, st, p.pdl, tq, tk, tv, p);
 }
 
 }  // namespace
@@ -410,8 +435,16 @@ int attn_prefill_tc(const AttnArgs& a, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(a.q) & 15) || (reinterpret_cast<uintptr_t>(a.k) & 15) || (reinterpret_cast<uintptr_t>(a.v) & 15))
     return EMU_ERR_UNSUPPORTED;
   if (a.H > 65535 || a.B > 65535) return EMU_ERR_UNSUPPORTED;
-  if (a.D <= 64) return a.Nk <= 64 ? launch_attn_tc<64, 64>(a, st) : launch_attn_tc<64, 128>(a, st);  // cross-attn: 64 keys
-  return launch_attn_tc<128, 64>(a, st);
+  static int sw = -1;
+  if (sw < 0) {
+    const char* v = getenv("EMU_ATTN_SW");
+    sw = (v && atoi(v) == 2) ? 2 : 1;  // 2 = split every row over two softmax warps (opt-in until measured)
+  }
+  if (a.D <= 64) {
+    if (a.Nk <= 64) return sw == 2 ? launch_attn_tc<64, 64, 2>(a, st) : launch_attn_tc<64, 64, 1>(a, st);  // cross-attn: 64 keys
+    return sw == 2 ? launch_attn_tc<64, 128, 2>(a, st) : launch_attn_tc<64, 128, 1>(a, st);
+  }
+  return sw == 2 ? launch_attn_tc<128, 64, 2>(a, st) : launch_attn_tc<128, 64, 1>(a, st);
 }
 
 }  // namespace emu
