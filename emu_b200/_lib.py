@@ -57,7 +57,7 @@ class EmuVAEConfig(C.Structure):
 
 # every symbol declared in include/emu_b200.h (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "emu_beam_topk", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
+    "emu_beam_topk", "emu_preprocess_image", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
     "emu_vit_forward", "emu_llm_reset", "emu_llm_embed", "emu_llm_prefill", "emu_llm_decode", "emu_llm_cur_len",
     "emu_project", "emu_cformer_forward", "emu_unet_configure", "emu_unet_forward", "emu_denoise_step",
     "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
@@ -331,6 +331,22 @@ def op_attn_prefill(q, k, v, scale, causal=False, kv_start=None, bias=None):
     rc = lib.emu_op_attn_prefill(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, H, Nq, Nk, D, st12, C.c_float(scale),
                                  1 if causal else 0, _ptr(kv_start), _ptr(bias), _stream())
     check(rc)
+    return out
+
+
+def op_preprocess_image(img_u8_hwc, out_h, out_w, mean, std, dtype=torch.float32):
+    """[H, W, 3] uint8 CUDA tensor -> [3, out_h, out_w] fp32/bf16: Resize(BICUBIC) + ToTensor + Normalize, bit-exact with the
+    reference's torchvision + Pillow transform."""
+    require_cuda()
+    lib = load()
+    assert img_u8_hwc.dtype == torch.uint8 and img_u8_hwc.dim() == 3 and img_u8_hwc.shape[2] == 3 and img_u8_hwc.is_cuda
+    img = img_u8_hwc.contiguous()
+    H, W, _ = img.shape
+    out = torch.empty(3, out_h, out_w, dtype=dtype, device=img.device)
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    code = {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16}[dtype]
+    check(lib.emu_preprocess_image(_ptr(img), H, W, out_h, out_w, m3, s3, _ptr(out), code, _stream()))
     return out
 
 

@@ -11,7 +11,7 @@ from .conf import CLIPVisionCfg, TextDecoderCfg
 from .constants import (ASSISTANT_TOKEN, DEFAULT_EOS_TOKEN, DEFAULT_IMG_PLACEHOLDER, DEFAULT_VID_PLACEHOLDER,
                         DEFAULT_VIDEO_TOKEN, EVA_IMAGE_SIZE, FAKE_VIDEO_END_TOKEN, GRD_SYMBOL, GROUND_SYSTEM_MESSAGE,
                         OPENAI_DATASET_MEAN, OPENAI_DATASET_STD, SYSTEM_MESSAGE, USER_TOKEN)
-from .diffusion import image_transform
+from .diffusion import image_transform, image_transform_cuda
 from .emu import EmuModel
 
 
@@ -21,7 +21,11 @@ class EmuChatGeneration:
         self.emu_model = emu_model
         self.eva_size, self.eva_mean, self.eva_std = eva_size, eva_mean, eva_std
 
-    def transform(self, img: Image.Image):
+    def transform(self, img: Image.Image, device=None):
+        """The reference's TF.Compose transform.  With a CUDA `device` the resize / ToTensor / Normalize run in the
+        library (emu_preprocess_image, bit-identical output) and only the raw uint8 pixels are copied to the GPU."""
+        if device is not None and torch.device(device).type == "cuda":
+            return image_transform_cuda(img, self.eva_size, self.eva_mean, self.eva_std, device=device)
         return image_transform(img, self.eva_size, self.eva_mean, self.eva_std)
 
     # ---- Emu2/emu/chat.py:41-119 ----
@@ -65,10 +69,10 @@ class EmuChatGeneration:
                 text_prompt += x
             elif is_video:
                 text_prompt += video_placeholder
-                video_prompt.append(self.transform(x))
+                video_prompt.append(self.transform(x, device))
             else:
                 text_prompt += image_placeholder
-                image_prompt.append(self.transform(x))
+                image_prompt.append(self.transform(x, device))
         image_prompt = torch.stack(image_prompt).to(device=device, dtype=dtype) if image_prompt else None
         video_prompt = torch.stack(video_prompt).to(device=device, dtype=dtype) if video_prompt else None
         return [text_prompt], image_prompt, video_prompt, image_placeholder, video_placeholder

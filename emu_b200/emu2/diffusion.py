@@ -37,6 +37,14 @@ def image_transform(img: Image.Image, size=EVA_IMAGE_SIZE, mean=OPENAI_DATASET_M
     return (x - torch.tensor(mean)[:, None, None]) / torch.tensor(std)[:, None, None]
 
 
+def image_transform_cuda(img: Image.Image, size=EVA_IMAGE_SIZE, mean=OPENAI_DATASET_MEAN, std=OPENAI_DATASET_STD,
+                         dtype=torch.float32, device="cuda"):
+    """Same transform on the GPU (emu_preprocess_image: Pillow-exact fixed-point bicubic + ToTensor + Normalize): only
+    the raw uint8 pixels cross PCIe; the result is bit-identical to image_transform()."""
+    raw = torch.from_numpy(np.asarray(img.convert("RGB"), dtype=np.uint8).copy())
+    return _lib.op_preprocess_image(raw.to(device, non_blocking=True), size, size, mean, std, dtype=dtype)
+
+
 def unet_config_from_json(cfg: dict) -> "_lib.EmuUNetConfig":
     u = _lib.EmuUNetConfig()
     u.in_channels, u.out_channels = cfg["in_channels"], cfg["out_channels"]
@@ -92,7 +100,9 @@ class EmuVisualGeneration:
         self.negative_prompt = {}
         self.device_ = multimodal_encoder.device_
 
-    def transform(self, img):
+    def transform(self, img, device=None):
+        if device is not None and torch.device(device).type == "cuda":
+            return image_transform_cuda(img, self.eva_size, self.eva_mean, self.eva_std, device=device)
         return image_transform(img, self.eva_size, self.eva_mean, self.eva_std)
 
     def eval(self):
@@ -166,7 +176,7 @@ class EmuVisualGeneration:
             else:
                 has_image = True
                 text_prompt += placeholder
-                image_prompt.append(self.transform(x))
+                image_prompt.append(self.transform(x, self.device_))
         image_prompt = torch.stack(image_prompt).to(self.device_, torch.bfloat16) if image_prompt else None
         enc = self.multimodal_encoder
         if has_image and not has_text:  # autoencoding mode: exactly one image

@@ -164,6 +164,13 @@ int emu_op_rmsnorm(const void* x, const void* w, void* y, int rows, int cols, fl
 int emu_op_layernorm(const void* x, const void* w, const void* b, const void* residual, void* y, int rows, int cols,
                      float eps, emu_stream_t s);
 
+/* Image pre-processing: TF.Resize((out_h, out_w), BICUBIC) -> ToTensor -> Normalize(mean, std) as in
+ * Emu2/emu/chat.py:35-39, Emu2/emu/diffusion.py:59-63, Emu1/models/pipeline.py:59-63, bit-exact with torchvision + Pillow
+ * (Pillow ImagingResample: two-pass fixed-point bicubic on uint8).  rgb_hwc: DEVICE pointer to [H, W, 3] uint8;
+ * mean3 / std3: HOST pointers to 3 floats; out_chw: device [3, out_h, out_w] of out_dtype (EMU_DTYPE_F32 / _BF16). */
+int emu_preprocess_image(const uint8_t* rgb_hwc, int H, int W, int out_h, int out_w, const float* mean3, const float* std3,
+                         void* out_chw, int out_dtype, emu_stream_t s);
+
 /* Device-side beam-search step.  Replaces, inside HF GenerationMixin._beam_search as driven by
  * Emu2/emu/emu.py:213-229 (num_beams=5, length_penalty=-1), the vocabulary-wide work of one step:
  *   log_softmax(logits) -> RepetitionPenaltyLogitsProcessor -> MinLength EOS ban -> + running beam score ->

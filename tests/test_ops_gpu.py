@@ -254,3 +254,21 @@ def test_beam_topk(cuda, Bt, nb, V, prev_len, ban):
     real = ref_v > -1e8  # candidates of a dead (-1e9) beam tie at fp32 resolution: order is don't-care
     assert torch.allclose(out_v.cpu()[real], ref_v[real], rtol=1e-5, atol=1e-4)
     assert torch.equal(out_i.cpu()[real], ref_i[real])
+
+
+@pytest.mark.parametrize("H,W,S", [(37, 53, 16), (500, 333, 448), (448, 448, 448), (1024, 768, 448), (31, 97, 224),
+                                   (448, 300, 448), (2160, 3840, 448)])
+def test_preprocess_image(cuda, H, W, S):
+    """emu_preprocess_image (Pillow-exact fixed-point bicubic + ToTensor + Normalize) is BIT-EXACT against the oracle,
+    which is pinned bit-exactly to torchvision + Pillow on the CPU side."""
+    import numpy as np
+    from emu_b200 import _lib
+    from oracle import preprocess_oracle as P
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    rng = np.random.default_rng(H * 1000 + W)
+    img = (rng.random((H, W, 3)) * 255).astype(np.uint8)
+    ref = torch.from_numpy(P.image_transform(img, S, mean, std))
+    out = _lib.op_preprocess_image(torch.from_numpy(img).cuda(), S, S, mean, std, dtype=torch.float32).cpu()
+    assert torch.equal(out, ref)
+    out16 = _lib.op_preprocess_image(torch.from_numpy(img).cuda(), S, S, mean, std, dtype=torch.bfloat16).cpu()
+    assert torch.equal(out16, ref.to(torch.bfloat16))

@@ -3,6 +3,7 @@
 reference imported live."""
 import os
 
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -81,3 +82,21 @@ def test_oracle_vs_live_reference(sd):
         return i.input_ids, i.attention_mask
     lit = O.generate_image_regress(sd, ids_fn, 4, layers=L, heads=NH, image_token_id=32003, boi_token_id=32001)
     assert O.rel_err(lit, gi) < 1e-5
+
+
+@pytest.mark.parametrize("H,W,S", [(37, 53, 16), (500, 333, 448), (448, 448, 448), (1024, 768, 448), (100, 100, 224),
+                                   (31, 97, 224), (224, 1000, 448)])
+def test_preprocess_oracle_vs_torchvision(H, W, S):
+    """oracle/preprocess_oracle.py must be BIT-EXACT with the reference's own transform (Emu2/emu/chat.py:35-39:
+    torchvision Resize(BICUBIC) on a PIL image -> ToTensor -> Normalize), up- and down-scaling, ragged sizes."""
+    tv = pytest.importorskip("torchvision.transforms")
+    from PIL import Image
+    from oracle import preprocess_oracle as P
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    rng = np.random.default_rng(H * 1000 + W)
+    img = (rng.random((H, W, 3)) * 255).astype(np.uint8)
+    pil = Image.fromarray(img)
+    assert np.array_equal(np.asarray(pil.resize((S, S), Image.BICUBIC)), P.resize_bicubic_u8(img, S, S))
+    t = tv.Compose([tv.Resize((S, S), interpolation=tv.InterpolationMode.BICUBIC), tv.ToTensor(),
+                    tv.Normalize(mean=mean, std=std)])
+    assert np.array_equal(t(pil).numpy(), P.image_transform(img, S, mean, std))
