@@ -57,7 +57,7 @@ class EmuVAEConfig(C.Structure):
 
 # every symbol declared in include/emu_b200.h (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "emu_beam_topk", "emu_preprocess_image", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
+    "emu_beam_topk", "emu_image_to_uint8", "emu_preprocess_image", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
     "emu_vit_forward", "emu_llm_reset", "emu_llm_embed", "emu_llm_prefill", "emu_llm_decode", "emu_llm_cur_len",
     "emu_project", "emu_cformer_forward", "emu_unet_configure", "emu_unet_forward", "emu_denoise_step",
     "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
@@ -347,6 +347,16 @@ def op_preprocess_image(img_u8_hwc, out_h, out_w, mean, std, dtype=torch.float32
     s3 = (C.c_float * 3)(*[float(v) for v in std])
     code = {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16}[dtype]
     check(lib.emu_preprocess_image(_ptr(img), H, W, out_h, out_w, m3, s3, _ptr(out), code, _stream()))
+    return out
+
+
+def op_image_to_uint8(image01):
+    """fp32 [0,1] CUDA tensor -> uint8 (x * 255, round half to even) — numpy_to_pil's conversion on the device."""
+    require_cuda()
+    x = image01.contiguous()
+    assert x.dtype == torch.float32 and x.is_cuda
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    check(load().emu_image_to_uint8(_ptr(x), _ptr(out), C.c_int64(x.numel()), _stream()))
     return out
 
 

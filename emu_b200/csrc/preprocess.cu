@@ -128,9 +128,27 @@ __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ in, void* out
   }
 }
 
+// image post-processing tail (Emu2/emu/diffusion.py:218-234): numpy_to_pil's (images * 255).round().astype("uint8") on the
+// [0, 1] fp32 image the VAE decode produced — round-half-to-even, like numpy
+__global__ void to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = rintf(__fmul_rn(x[i], 255.0f));
+    y[i] = (uint8_t)(v < 0.f ? 0.f : (v > 255.f ? 255.f : v));
+  }
+}
+
 }  // namespace emu
 
 using namespace emu;
+
+extern "C" int emu_image_to_uint8(const float* image01, uint8_t* out, int64_t n, emu_stream_t stream) {
+  if (!image01 || !out || n < 1) return EMU_ERR_INVALID;
+  const int grid = (int)((n + 255) / 256 < 8 * kNumSMs ? (n + 255) / 256 : 8 * kNumSMs);
+  to_uint8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image01, out, n);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+}
+
 
 extern "C" int emu_preprocess_image(const uint8_t* rgb_hwc, int H, int W, int out_h, int out_w, const float* mean3,
                                     const float* std3, void* out_chw, int out_dtype, emu_stream_t stream) {

@@ -171,6 +171,10 @@ int emu_op_layernorm(const void* x, const void* w, const void* b, const void* re
 int emu_preprocess_image(const uint8_t* rgb_hwc, int H, int W, int out_h, int out_w, const float* mean3, const float* std3,
                          void* out_chw, int out_dtype, emu_stream_t s);
 
+/* numpy_to_pil's `(images * 255).round().astype("uint8")` (Emu2/emu/diffusion.py:231-234) on the device: image01 = the fp32
+ * [0, 1] image emu_vae_decode wrote; round-half-to-even; n elements. */
+int emu_image_to_uint8(const float* image01, uint8_t* out, int64_t n, emu_stream_t s);
+
 /* Device-side beam-search step.  Replaces, inside HF GenerationMixin._beam_search as driven by
  * Emu2/emu/emu.py:213-229 (num_beams=5, length_penalty=-1), the vocabulary-wide work of one step:
  *   log_softmax(logits) -> RepetitionPenaltyLogitsProcessor -> MinLength EOS ban -> + running beam score ->

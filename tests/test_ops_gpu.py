@@ -272,3 +272,16 @@ def test_preprocess_image(cuda, H, W, S):
     assert torch.equal(out, ref)
     out16 = _lib.op_preprocess_image(torch.from_numpy(img).cuda(), S, S, mean, std, dtype=torch.bfloat16).cpu()
     assert torch.equal(out16, ref.to(torch.bfloat16))
+
+
+def test_image_to_uint8(cuda):
+    """device uint8 conversion == numpy_to_pil's (images * 255).round().astype("uint8") incl. exact .5 ties"""
+    import numpy as np
+    from emu_b200 import _lib
+    g = torch.Generator().manual_seed(80)
+    x = torch.rand(3, 64, 64, 3, generator=g)
+    x.view(-1)[:512] = (torch.arange(512) % 256 + 0.5) / 255.0   # products landing on (or next to) .5 ties
+    x = x.clamp(0, 1).to(torch.bfloat16).float()                 # the VAE path hands over bf16-rounded values
+    ref = (x.numpy() * 255).round().astype("uint8")
+    out = _lib.op_image_to_uint8(x.cuda()).cpu().numpy()
+    assert np.array_equal(out, ref)
