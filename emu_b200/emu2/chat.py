@@ -117,12 +117,10 @@ class EmuChatGeneration:
     def from_pretrained(cls, path: str, instruct: bool = False, dtype=torch.bfloat16, use_safetensors: bool = False,
                         **kwargs):
         ins = cls.from_config(instruct=instruct, **kwargs)
-        if use_safetensors:
-            from safetensors.torch import load_file
-            sd = load_file(path)
-        else:
-            sd = torch.load(path, map_location="cpu")
-        ins.emu_model.load_state_dict(sd, strict=True)
+        # stream tensor by tensor into the packed / tensor-parallel device buffers (emu_b200/checkpoint.py); the
+        # reference materialises the whole 74 GB state dict on the host first (Emu2/emu/chat.py:129-149)
+        from .. import checkpoint
+        checkpoint.load_into(ins.emu_model.engine, path)
         return ins
 
     def multito(self, device_list):

@@ -230,12 +230,16 @@ class EmuVisualGeneration:
         if config_path is None:
             config_path = model_path
         ins = cls.from_config(config_path, **kwargs)
-        if use_safetensors:
-            from safetensors.torch import load_file
-            sd = load_file(osp.join(model_path, "model.safetensors"))
-        else:
-            sd = torch.load(osp.join(model_path, "pytorch_model.bin"), map_location="cpu")
-        ins.load_state_dict(sd)
+        from .. import checkpoint
+
+        def keep(k):  # same filter as load_state_dict: no safety checker, only the decoder half of the VAE
+            if k.startswith("safety_checker."):
+                return None
+            if k.startswith("vae.") and (ins.vae_config is None or ".encoder." in k or k.startswith("vae.quant_conv")):
+                return None
+            return k
+        f = osp.join(model_path, "model.safetensors" if use_safetensors else "pytorch_model.bin")
+        checkpoint.load_into(ins.engine, f if osp.exists(f) else model_path, rename=keep)
         return ins
 
     def multito(self, device_list):
