@@ -57,7 +57,7 @@ class EmuVAEConfig(C.Structure):
 
 # every symbol declared in include/emu_b200.h (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "emu_beam_topk", "emu_image_to_uint8", "emu_preprocess_image", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
+    "emu_beam_topk", "emu_sample_tokens", "emu_image_to_uint8", "emu_preprocess_image", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
     "emu_vit_forward", "emu_llm_reset", "emu_llm_embed", "emu_llm_prefill", "emu_llm_decode", "emu_llm_cur_len",
     "emu_project", "emu_cformer_forward", "emu_unet_configure", "emu_unet_forward", "emu_denoise_step",
     "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
@@ -203,6 +203,9 @@ class Engine:
 
     def cur_len(self):
         return self.lib.emu_llm_cur_len(self.h)
+
+    def sample_tokens(self, logits, temperature=1.0, top_k=0, top_p=1.0, ban_id=-1, seed=0, offset=0):
+        return op_sample_tokens(logits, temperature, top_k, top_p, -1 if ban_id is None else ban_id, seed, offset)
 
     def beam_topk(self, logits, running_scores, batch, beams, keep, ban_id=-1, prev_tokens=None, repetition_penalty=1.0):
         if ban_id is None:
@@ -357,6 +360,17 @@ def op_image_to_uint8(image01):
     assert x.dtype == torch.float32 and x.is_cuda
     out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
     check(load().emu_image_to_uint8(_ptr(x), _ptr(out), C.c_int64(x.numel()), _stream()))
+    return out
+
+
+def op_sample_tokens(logits, temperature=1.0, top_k=0, top_p=1.0, ban_id=-1, seed=0, offset=0):
+    """logits [R, V] fp32 CUDA -> int32 [R]: temperature -> top-k -> top-p -> multinomial on the device."""
+    require_cuda()
+    lg = logits if (logits.dtype == torch.float32 and logits.is_contiguous()) else logits.float().contiguous()
+    out = torch.empty(lg.shape[0], dtype=torch.int32, device=lg.device)
+    check(load().emu_sample_tokens(_ptr(lg), lg.shape[0], lg.shape[1], C.c_float(temperature or 1.0), int(top_k or 0),
+                                   C.c_float(1.0 if top_p is None else top_p), int(ban_id), C.c_uint64(seed & (2 ** 64 - 1)),
+                                   C.c_uint64(offset), _ptr(out), _stream()))
     return out
 
 

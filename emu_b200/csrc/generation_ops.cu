@@ -100,9 +100,178 @@ __global__ void __launch_bounds__(1024) topk_group_kernel(float* x, long n, int 
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// sampling: HF warper order temperature -> top-k -> top-p, then one multinomial draw per row (Emu2/emu/chat.py:46-57 passes
+// do_sample / top_k / top_p / temperature through to GenerationMixin).  Sort-free: both filters are thresholds found by a
+// 32-step bitwise search over the order-preserving integer image of the scores, each step one pass over the L2-resident
+// row; the draw is an inverse-CDF lookup in index order.  One 1024-thread CTA per row, logits are not modified.
+//   top-k : keep x >= (k-th largest x)                         (ties with the k-th value are kept, as `scores < kth` does)
+//   top-p : keep x_i iff mass{x > x_i} < top_p                  (== sorted-ascending cumsum <= 1 - top_p removed)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t order_key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float block_sum_1024(float v, float* red) { return block_sum(v, red); }
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ logits, int V, float inv_temp, int top_k,
+                                                      float top_p, int ban_id, unsigned long long seed,
+                                                      unsigned long long offset, int* out_ids) {
+  __shared__ float red[33];
+  __shared__ float scan[32];
+  __shared__ int s_pick;
+  const float* row = logits + (long)blockIdx.x * V;
+  const int tid = threadIdx.x;
+  auto val = [&](int i) { return i == ban_id ? -INFINITY : row[i] * inv_temp; };
+  // row maximum (softmax shift)
+  float m = -INFINITY;
+  for (int i = tid; i < V; i += 1024) m = fmaxf(m, val(i));
+  m = warp_max(m);
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  if (tid < 32) {
+    float v = warp_max(red[tid]);
+    if (tid == 0) red[32] = v;
+  }
+  __syncthreads();
+  m = red[32];
+  __syncthreads();
+  // ---- top-k threshold: largest t with count{key >= t} >= k ----
+  uint32_t tk = 0;
+  if (top_k > 0 && top_k < V) {
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = tk | (1u << bit);
+      float cnt = 0.f;
+      for (int i = tid; i < V; i += 1024) cnt += order_key(val(i)) >= cand ? 1.f : 0.f;
+      cnt = block_sum_1024(cnt, red);
+      if (cnt >= (float)top_k) tk = cand;
+    }
+  }
+  // ---- top-p threshold on the top-k-filtered distribution: smallest t with mass{key > t} < top_p * Z ----
+  float z = 0.f;
+  for (int i = tid; i < V; i += 1024) {
+    const float x = val(i);
+    z += order_key(x) >= tk ? __expf(x - m) : 0.f;
+  }
+  z = block_sum_1024(z, red);
+  uint32_t tp = 0;
+  if (top_p < 1.0f) {
+    const float target = top_p * z;
+    tp = 0xFFFFFFFFu;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = tp & ~(1u << bit);
+      float mass = 0.f;
+      for (int i = tid; i < V; i += 1024) {
+        const float x = val(i);
+        const uint32_t k = order_key(x);
+        mass += (k > cand && k >= tk) ? __expf(x - m) : 0.f;
+      }
+      mass = block_sum_1024(mass, red);
+      if (mass < target) tp = cand;
+    }
+  }
+  const uint32_t thr = tk > tp ? tk : tp;
+  // ---- multinomial draw over the kept set, inverse CDF in index order (thread t owns a contiguous index chunk) ----
+  const int chunk = (V + 1023) / 1024;
+  const int i0 = tid * chunk, i1 = min(V, i0 + chunk);
+  float local = 0.f;
+  for (int i = i0; i < i1; ++i) {
+    const float x = val(i);
+    local += (order_key(x) >= thr && x > -INFINITY) ? __expf(x - m) : 0.f;
+  }
+  // block exclusive scan of `local`
+  float incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += n;
+  }
+  if ((tid & 31) == 31) scan[tid >> 5] = incl;
+  if (tid == 0) s_pick = -1;
+  __syncthreads();
+  if (tid < 32) {
+    float w = scan[tid], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float n = __shfl_up_sync(0xffffffffu, wi, o);
+      if (tid >= o) wi += n;
+    }
+    scan[tid] = wi - w;  // exclusive prefix of the warp totals
+    if (tid == 31) red[32] = wi;
+  }
+  __syncthreads();
+  const float total = red[32];
+  const float before = scan[tid >> 5] + incl - local;
+  const uint64_t h = mix64(seed ^ mix64(offset * 0x100000001B3ull + blockIdx.x));
+  const float u = (float)(h >> 40) * (1.0f / 16777216.0f) * total;  // 24 random bits -> [0, total)
+  if (local > 0.f && u >= before && u < before + local) {
+    float acc = before;
+    int pick = -1;
+    for (int i = i0; i < i1; ++i) {
+      const float x = val(i);
+      if (order_key(x) >= thr && x > -INFINITY) {
+        acc += __expf(x - m);
+        pick = i;
+        if (u < acc) break;
+      }
+    }
+    s_pick = pick;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int pick = s_pick;
+    if (pick < 0) {  // rounding at the very end of the CDF: fall back to the arg-max (always kept)
+      pick = 0;
+    }
+    out_ids[blockIdx.x] = pick;
+  }
+  // arg-max fallback needs the whole block: recompute only in the (rare) miss case
+  if (s_pick < 0) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < V; i += 1024) {
+      const float x = val(i);
+      if (x > best || (x == best && i < bi)) { best = x; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    if ((tid & 31) == 0) { sv[tid >> 5] = best; si[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 32; ++w)
+        if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+      out_ids[blockIdx.x] = bi;
+    }
+  }
+}
+
 }  // namespace emu
 
 using namespace emu;
+
+extern "C" int emu_sample_tokens(const float* logits, int rows, int vocab, float temperature, int top_k, float top_p,
+                                 int ban_id, uint64_t seed, uint64_t offset, int32_t* out_ids, emu_stream_t stream) {
+  if (!logits || !out_ids || rows < 1 || vocab < 1 || !(temperature > 0.f)) return EMU_ERR_INVALID;
+  if (!(top_p > 0.f)) return EMU_ERR_INVALID;
+  sample_kernel<<<rows, 1024, 0, (cudaStream_t)stream>>>(logits, vocab, 1.0f / temperature, top_k, top_p, ban_id,
+                                                         (unsigned long long)seed, (unsigned long long)offset, out_ids);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+}
+
 
 extern "C" int emu_beam_topk(float* logits, const float* running_scores, int batch, int beams, int vocab, int keep, int ban_id,
                              const long long* prev_tokens, int prev_len, float repetition_penalty, float* out_lp,

@@ -60,8 +60,22 @@ def sample_search(engine, inputs_embeds, attention_mask, max_new_tokens, eos_tok
     finished = torch.zeros(B, dtype=torch.bool, device=dev)
     nxt32 = torch.empty(B, dtype=torch.int32, device=dev)
     logits_buf = torch.empty_like(logits)
+    seed = generator.initial_seed() if generator is not None else torch.initial_seed()
     for step in range(max_new_tokens):
-        scores = logits.float().clone()
+        if hasattr(engine, "sample_tokens"):
+            # device-side step (emu_sample_tokens): warpers + multinomial draw in the library, no vocabulary-wide torch ops
+            nxt = engine.sample_tokens(logits, temperature or 1.0, top_k or 0, 1.0 if top_p is None else top_p,
+                                       eos_token_id if step < min_length else -1, seed, step).long()
+            nxt = torch.where(finished, torch.full_like(nxt, pad_token_id), nxt)
+            out.append(nxt)
+            finished |= nxt == eos_token_id
+            if bool(finished.all()) or step == max_new_tokens - 1:
+                break
+            nxt32.copy_(nxt)
+            engine.llm_decode(token_ids=nxt32, logits=logits_buf, B=B)
+            logits = logits_buf
+            continue
+        scores = logits.float().clone()  # engines without the op (the CPU oracle stub of tests/test_generation_cpu.py)
         if step < min_length:
             scores[:, eos_token_id] = float("-inf")
         if temperature is not None and temperature != 1.0:

@@ -186,6 +186,13 @@ int emu_beam_topk(float* logits, const float* running_scores, int batch, int bea
                   const long long* prev_tokens, int prev_len, float repetition_penalty, float* out_lp, int* out_idx,
                   emu_stream_t s);
 
+/* Device-side sampling step: HF warper order temperature -> top-k (0 = off) -> top-p (1 = off) and one
+ * multinomial draw per row, as GenerationMixin does for do_sample=True (Emu2/emu/chat.py:46-57 forwards the knobs).
+ * logits [rows, vocab] fp32 (not modified); ban_id < 0 disables the min-length EOS ban; the draw is a counter-based
+ * hash of (seed, offset, row) — statistically equivalent to torch.multinomial, not bit-identical to its Philox stream. */
+int emu_sample_tokens(const float* logits, int rows, int vocab, float temperature, int top_k, float top_p, int ban_id,
+                      uint64_t seed, uint64_t offset, int32_t* out_ids, emu_stream_t s);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t emu_launch_count(void);
 const char* emu_version(void);

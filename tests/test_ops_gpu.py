@@ -285,3 +285,52 @@ def test_image_to_uint8(cuda):
     ref = (x.numpy() * 255).round().astype("uint8")
     out = _lib.op_image_to_uint8(x.cuda()).cpu().numpy()
     assert np.array_equal(out, ref)
+
+
+def _hf_support(scores, top_k, top_p):
+    """kept-token mask of HF's TopK / TopP warpers (the torch formulation in emu_b200/generation.py)"""
+    s = scores.clone()
+    if top_k:
+        kth = torch.topk(s, min(top_k, s.shape[-1]))[0][..., -1, None]
+        s = s.masked_fill(s < kth, float("-inf"))
+    if top_p < 1.0:
+        ss, si = torch.sort(s, descending=False)
+        cum = ss.softmax(-1).cumsum(-1)
+        rem = cum <= (1 - top_p)
+        rem[..., -1:] = False
+        s = s.masked_fill(rem.scatter(1, si, rem), float("-inf"))
+    return s
+
+
+@pytest.mark.parametrize("V,top_k,top_p,temp", [(64, 0, 1.0, 1.0), (64, 8, 1.0, 0.7), (64, 0, 0.8, 1.0), (1000, 50, 0.9, 1.3),
+                                                 (32272, 50, 0.9, 1.0)])
+def test_sample_tokens(cuda, V, top_k, top_p, temp):
+    """emu_sample_tokens: every draw lies in HF's top-k/top-p support and the empirical distribution matches the filtered
+    softmax (total-variation distance within sampling noise)."""
+    from emu_b200 import _lib
+    g = torch.Generator().manual_seed(90)
+    R = 4096 if V <= 1000 else 2048
+    base = torch.randn(1, V, generator=g) * 2.0
+    logits = base.repeat(R, 1).contiguous()
+    kept = _hf_support(base / temp, top_k, top_p)
+    probs = kept.softmax(-1)[0]
+    ids = _lib.op_sample_tokens(logits.cuda(), temperature=temp, top_k=top_k, top_p=top_p, seed=1234, offset=7).cpu().long()
+    assert ids.min() >= 0 and ids.max() < V
+    # tokens whose cumulative mass sits within 1e-3 of the top-p cut may legitimately fall on either side (fp32 sums)
+    border = torch.zeros(V, dtype=torch.bool)
+    if top_p < 1.0:
+        sp, si = torch.sort((base / temp)[0].softmax(-1) if not top_k else _hf_support(base / temp, top_k, 1.0)[0].softmax(-1),
+                            descending=True)
+        before = sp.cumsum(0) - sp
+        border[si[(before - top_p).abs() < 1e-3]] = True
+    ok = (probs[ids] > 0) | border[ids]
+    assert bool(ok.all()), ids[~ok][:10]
+    emp = torch.bincount(ids, minlength=V).float() / R
+    tv = 0.5 * (emp - probs).abs().sum()
+    n_support = int((probs > 0).sum())
+    assert tv < 0.5 * (n_support / R) ** 0.5 + 0.02, (float(tv), n_support)
+    # different offsets give different draws, same (seed, offset) is reproducible
+    ids2 = _lib.op_sample_tokens(logits.cuda(), temperature=temp, top_k=top_k, top_p=top_p, seed=1234, offset=7).cpu().long()
+    assert torch.equal(ids, ids2)
+    ids3 = _lib.op_sample_tokens(logits.cuda(), temperature=temp, top_k=top_k, top_p=top_p, seed=1234, offset=8).cpu().long()
+    assert not torch.equal(ids, ids3) or n_support == 1
