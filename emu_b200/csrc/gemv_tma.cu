@@ -54,8 +54,9 @@ __global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_con
     return;
   }
   if (p.a.pdl) pdl_wait();
-  tma_stage_x(p, xs, s_ss, s_rstd);
-  tma_consume(&s_params, c0, c1, ring, full_bar, empty_bar, red, fin, xs, &s_last, stage, phase);
+  const int xsc = (p.xsc > 0 && p.xsc < p.cpt) ? p.xsc : p.cpt;
+  tma_stage_x(p, xs, s_ss, s_rstd, (int)(c0 % p.cpt) / xsc);
+  tma_consume(&s_params, c0, c1, ring, full_bar, empty_bar, red, fin, xs, &s_last, stage, phase, s_rstd);
 }
 
 static float* g_tws = nullptr;
@@ -90,6 +91,18 @@ int gemv_tma_bf16(const GemvArgs& a, cudaStream_t st) {
   p.kpad = (a.K + kTCols - 1) / kTCols * kTCols;
   p.ldxs = p.kpad + 8;  // row stride = 16 B (mod 128 B): the 8 batch rows hit distinct bank groups
   p.cpt = p.kpad / kTCols;
+  p.xsc = 0;
+  {
+    // batch x K too large to keep all of x in shared memory next to a deep ring (5 beams x 17920 = 179 KB): stage x in K
+    // segments of <= 88 KB instead, re-staged as the chunk stream crosses them
+    const size_t budget = 88 * 1024;
+    if ((size_t)a.B * p.ldxs * 2 > budget) {
+      int xsc = (int)((budget / ((size_t)a.B * 2) - 8) / kTCols);
+      if (xsc < 1) return EMU_ERR_UNSUPPORTED;
+      p.xsc = xsc;
+      p.ldxs = xsc * kTCols + 8;
+    }
+  }
   p.total = (long)groups * p.cpt;
   p.ws = g_tws;
   p.counters = g_tcounters;

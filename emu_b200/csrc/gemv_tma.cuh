@@ -25,6 +25,8 @@ struct GemvTmaParams {
   int ldxs;      // smem row stride of staged x (elements), = Kpad + 8
   int kpad;      // K rounded up to 256
   int cpt;       // chunks per row group
+  int xsc;       // chunks of x staged in shared memory at a time (0 or >= cpt: the whole row; smaller: K segments that
+                 //   are re-staged as the chunk stream crosses them — batch x K too large for shared memory, e.g. 5 x 17920)
   int nstages;   // ring depth actually used (<= kTStages)
   int geff;      // number of CTAs that share this matrix's chunks (<= gridDim.x); CTAs >= geff get none
   long total;    // total chunks
@@ -147,11 +149,49 @@ static __device__ __forceinline__ void tma_produce(const CUtensorMap* tm, int cp
 }
 
 // ---- consumers: stage x (optionally RMS-normalised, zero padded to kpad) into shared memory ----
-static __device__ __forceinline__ void tma_stage_x(const GemvTmaParams& p, bf16* xs, float (*s_ss)[8], float* s_rstd) {
+// columns [seg * xsc * 256, (seg + 1) * xsc * 256) of every batch row (the whole row when xsc covers it)
+static __device__ __forceinline__ void tma_stage_x_seg(const GemvTmaParams& p, bf16* xs, const float* s_rstd, int seg) {
+  const GemvArgs& a = p.a;
+  const int K = a.K, B = a.B;
+  const int vec_per_row = K >> 3;
+  const int xsc = (p.xsc > 0 && p.xsc < p.cpt) ? p.xsc : p.cpt;
+  const int v0 = seg * xsc * (kTCols >> 3);                       // first 16-byte vector of the segment
+  const int nv = min(xsc, p.cpt - seg * xsc) * (kTCols >> 3);     // vectors in this segment (zero padded past K)
+  for (int b = 0; b < B; ++b) {
+    const float rstd = a.norm_w ? s_rstd[b] : 1.f;
+    const uint4* src = reinterpret_cast<const uint4*>(a.x + (long)b * a.ldx);
+    const uint4* wsrc = reinterpret_cast<const uint4*>(a.norm_w);
+    uint4* dst = reinterpret_cast<uint4*>(xs + (long)b * p.ldxs);
+    for (int i = threadIdx.x; i < nv; i += 256) {
+      uint4 o = make_uint4(0, 0, 0, 0);
+      const int gi = v0 + i;
+      if (gi < vec_per_row) {
+        const uint4 v = __ldcg(src + gi);  // activations may have been produced by other CTAs of this very kernel
+        if (a.norm_w) {
+          const uint4 w = wsrc[gi];
+          const uint32_t v4[4] = {v.x, v.y, v.z, v.w}, w4[4] = {w.x, w.y, w.z, w.w};
+          uint32_t o4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
+            o4[j] = pack_bf16(round_bf16(bf16_lo(v4[j]) * rstd) * bf16_lo(w4[j]),
+                              round_bf16(bf16_hi(v4[j]) * rstd) * bf16_hi(w4[j]));
+          o = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        } else {
+          o = v;
+        }
+      }
+      dst[i] = o;
+    }
+  }
+  consumer_bar();
+}
+
+static __device__ __forceinline__ void tma_stage_x(const GemvTmaParams& p, bf16* xs, float (*s_ss)[8], float* s_rstd,
+                                                   int seg = 0) {
   const GemvArgs& a = p.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = a.K, B = a.B;
-  const int vec_per_row = K >> 3, vec_pad = p.kpad >> 3;
+  const int vec_per_row = K >> 3;
   if (a.norm_w != nullptr) {
     float ss[8];
 #pragma unroll
@@ -160,7 +200,7 @@ static __device__ __forceinline__ void tma_stage_x(const GemvTmaParams& p, bf16*
       const uint4* src = reinterpret_cast<const uint4*>(a.x + (long)b * a.ldx);
       float s = 0.f;
       for (int i = threadIdx.x; i < vec_per_row; i += 256) {
-        const uint4 v = __ldcg(src + i);  // activations may have been produced by other CTAs of this very kernel
+        const uint4 v = __ldcg(src + i);
         const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -183,38 +223,14 @@ static __device__ __forceinline__ void tma_stage_x(const GemvTmaParams& p, bf16*
     }
     consumer_bar();
   }
-  for (int b = 0; b < B; ++b) {
-    const float rstd = a.norm_w ? s_rstd[b] : 1.f;
-    const uint4* src = reinterpret_cast<const uint4*>(a.x + (long)b * a.ldx);
-    const uint4* wsrc = reinterpret_cast<const uint4*>(a.norm_w);
-    uint4* dst = reinterpret_cast<uint4*>(xs + (long)b * p.ldxs);
-    for (int i = threadIdx.x; i < vec_pad; i += 256) {
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (i < vec_per_row) {
-        const uint4 v = __ldcg(src + i);
-        if (a.norm_w) {
-          const uint4 w = wsrc[i];
-          const uint32_t v4[4] = {v.x, v.y, v.z, v.w}, w4[4] = {w.x, w.y, w.z, w.w};
-          uint32_t o4[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
-            o4[j] = pack_bf16(round_bf16(bf16_lo(v4[j]) * rstd) * bf16_lo(w4[j]),
-                              round_bf16(bf16_hi(v4[j]) * rstd) * bf16_hi(w4[j]));
-          o = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-        } else {
-          o = v;
-        }
-      }
-      dst[i] = o;
-    }
-  }
-  consumer_bar();
+  tma_stage_x_seg(p, xs, s_rstd, seg);
 }
 
 // ---- consumers: pull this CTA's chunks [c0, c1) out of the ring, mma them against xs, finish row groups ----
 static __device__ __forceinline__ void tma_consume(const GemvTmaParams* sp, long c0, long c1, uint8_t* ring,
                                                    uint64_t* full_bar, uint64_t* empty_bar, float* red, float* fin,
-                                                   const bf16* xs, int* s_last, int& stage, uint32_t& phase) {
+                                                   bf16* xs, int* s_last, int& stage, uint32_t& phase,
+                                                   const float* s_rstd = nullptr) {
   const GemvTmaParams& p = *sp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -233,10 +249,17 @@ static __device__ __forceinline__ void tma_consume(const GemvTmaParams* sp, long
   const bf16* xrow = xs + (long)g * p.ldxs + warp * 32 + 2 * t;
   int cp_grp = (int)(c0 / CPT), cp_kc = (int)(c0 % CPT);
   int seg_lo = cp_kc;
+  const int xsc = (p.xsc > 0 && p.xsc < CPT) ? p.xsc : CPT;  // chunks per staged x segment
+  int cur_seg = cp_kc / xsc;                                  // the caller staged this segment (tma_stage_x(.., seg))
   for (int i = 0; i < n; ++i) {
+    if (cp_kc / xsc != cur_seg) {  // the chunk stream left the staged K segment: all 8 consumer warps re-stage together
+      cur_seg = cp_kc / xsc;
+      consumer_bar();
+      tma_stage_x_seg(p, xs, s_rstd, cur_seg);
+    }
     mbar_wait(&full_bar[stage], phase);
     const uint32_t tbase = smem_u32(ring + stage * kTStageBytes + tile_j * (kTRows * 128));
-    const bf16* xk = xrow + cp_kc * kTCols;
+    const bf16* xk = xrow + (cp_kc - cur_seg * xsc) * kTCols;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       uint32_t bfr[2] = {0u, 0u};

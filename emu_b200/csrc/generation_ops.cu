@@ -112,7 +112,6 @@ __device__ __forceinline__ uint32_t order_key(float x) {
   const uint32_t u = __float_as_uint(x);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-__device__ __forceinline__ float block_sum_1024(float v, float* red) { return block_sum(v, red); }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
   z += 0x9E3779B97F4A7C15ull;
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
       const uint32_t cand = tk | (1u << bit);
       float cnt = 0.f;
       for (int i = tid; i < V; i += 1024) cnt += order_key(val(i)) >= cand ? 1.f : 0.f;
-      cnt = block_sum_1024(cnt, red);
+      cnt = block_sum(cnt, red);
       if (cnt >= (float)top_k) tk = cand;
     }
   }
@@ -160,7 +159,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     const float x = val(i);
     z += order_key(x) >= tk ? __expf(x - m) : 0.f;
   }
-  z = block_sum_1024(z, red);
+  z = block_sum(z, red);
   uint32_t tp = 0;
   if (top_p < 1.0f) {
     const float target = top_p * z;
@@ -173,7 +172,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
         const uint32_t k = order_key(x);
         mass += (k > cand && k >= tk) ? __expf(x - m) : 0.f;
       }
-      mass = block_sum_1024(mass, red);
+      mass = block_sum(mass, red);
       if (mass < target) tp = cand;
     }
   }

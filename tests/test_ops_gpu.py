@@ -75,13 +75,27 @@ def test_conv3x3(cuda, NB, H, W, Cin, Cout):
 
 
 @pytest.mark.parametrize("N,K,B", [(6656, 6656, 1), (1024, 256, 5), (32272, 512, 3), (2000, 1792, 8), (48, 64, 2),
-                                   (35840, 6656, 1), (6656, 17920, 5)])
+                                   (35840, 6656, 1), (6656, 17920, 5), (1024, 6656, 8), (512, 17920, 8), (640, 2304, 7)])
 def test_gemv_plain(cuda, N, K, B):
     from emu_b200 import _lib
     W, x = _rand((N, K), 10, 0.05), _rand((B, K), 11)
     ref = O.op_linear(x, W)
     assert O.rel_err(_lib.op_gemv(W.cuda(), x.cuda(), out_fp32=True).cpu(), ref) < TOL_F32
     assert O.rel_err(_lib.op_gemv(W.cuda(), x.cuda(), pdl=True).cpu(), ref) < TOL_BF16
+
+
+def test_gemv_segmented_x_with_norm(cuda):
+    """batch x K too large for shared memory: x is staged in K segments (fused RMSNorm statistics span all segments)"""
+    from emu_b200 import _lib
+    N, K, B = 2048, 6656, 8
+    W, x, nw = _rand((N, K), 16, 0.05), _rand((B, K), 17), (1 + 0.1 * _rand((K,), 18).float()).to(torch.bfloat16)
+    xn = O.rms_norm(x, nw, 1e-6)
+    ref = O.op_linear(xn, W)
+    assert O.rel_err(_lib.op_gemv(W.cuda(), x.cuda(), norm_w=nw.cuda(), out_fp32=True).cpu(), ref) < TOL_F32
+    g, u = O.op_linear(xn, W[0::2]), O.op_linear(xn, W[1::2])
+    bf = lambda t: t.to(torch.bfloat16)
+    assert O.rel_err(_lib.op_gemv(W.cuda(), x.cuda(), norm_w=nw.cuda(), mode=_lib.EPI_SWIGLU).cpu(),
+                     torch.nn.functional.silu(bf(g)) * bf(u)) < TOL_BF16
 
 
 def test_gemv_fused(cuda):
