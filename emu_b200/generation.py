@@ -62,34 +62,9 @@ def sample_search(engine, inputs_embeds, attention_mask, max_new_tokens, eos_tok
     logits_buf = torch.empty_like(logits)
     seed = generator.initial_seed() if generator is not None else torch.initial_seed()
     for step in range(max_new_tokens):
-        if hasattr(engine, "sample_tokens"):
-            # device-side step (emu_sample_tokens): warpers + multinomial draw in the library, no vocabulary-wide torch ops
-            nxt = engine.sample_tokens(logits, temperature or 1.0, top_k or 0, 1.0 if top_p is None else top_p,
-                                       eos_token_id if step < min_length else -1, seed, step).long()
-            nxt = torch.where(finished, torch.full_like(nxt, pad_token_id), nxt)
-            out.append(nxt)
-            finished |= nxt == eos_token_id
-            if bool(finished.all()) or step == max_new_tokens - 1:
-                break
-            nxt32.copy_(nxt)
-            engine.llm_decode(token_ids=nxt32, logits=logits_buf, B=B)
-            logits = logits_buf
-            continue
-        scores = logits.float().clone()  # engines without the op (the CPU oracle stub of tests/test_generation_cpu.py)
-        if step < min_length:
-            scores[:, eos_token_id] = float("-inf")
-        if temperature is not None and temperature != 1.0:
-            scores = scores / temperature
-        if top_k is not None and top_k > 0:
-            kth = torch.topk(scores, min(top_k, scores.shape[-1]))[0][..., -1, None]
-            scores = scores.masked_fill(scores < kth, float("-inf"))
-        if top_p is not None and top_p < 1.0:
-            s_sorted, s_idx = torch.sort(scores, descending=False)
-            cum = s_sorted.softmax(-1).cumsum(-1)
-            remove = cum <= (1 - top_p)
-            remove[..., -1:] = False
-            scores = scores.masked_fill(remove.scatter(1, s_idx, remove), float("-inf"))
-        nxt = torch.multinomial(scores.softmax(-1), 1, generator=generator).squeeze(1)
+        # device-side step (emu_sample_tokens): warpers + multinomial draw in the library
+        nxt = engine.sample_tokens(logits, temperature or 1.0, top_k or 0, 1.0 if top_p is None else top_p,
+                                   eos_token_id if step < min_length else -1, seed, step).long()
         nxt = torch.where(finished, torch.full_like(nxt, pad_token_id), nxt)
         out.append(nxt)
         finished |= nxt == eos_token_id
@@ -142,25 +117,14 @@ def beam_search(engine, inputs_embeds, attention_mask, num_beams, max_new_tokens
 
     cur_len = 0
     while True:
-        if hasattr(engine, "beam_topk"):
-            # device-side step (emu_beam_topk): log_softmax + processors + running score + top-2*beams in the library
-            prev = None
-            if repetition_penalty != 1.0 and cur_len > 0:
-                prev = running_seq[:, :, :cur_len].reshape(Bt * nb, cur_len)
-            topk_lp, topk_i = engine.beam_topk(logits, running_scores, Bt, nb, keep,
-                                               ban_id=eos_token_id if cur_len < min_length else -1, prev_tokens=prev,
-                                               repetition_penalty=repetition_penalty)
-        else:  # engines without the op (the CPU oracle stub used by tests/test_generation_cpu.py)
-            log_probs = torch.log_softmax(logits.float(), dim=-1)
-            if repetition_penalty != 1.0 and cur_len > 0:
-                prev = running_seq[:, :, :cur_len].reshape(Bt * nb, cur_len)
-                sc = torch.gather(log_probs, 1, prev)
-                sc = torch.where(sc < 0, sc * repetition_penalty, sc / repetition_penalty)
-                log_probs = log_probs.scatter(1, prev, sc)
-            if cur_len < min_length:
-                log_probs[:, eos_token_id] = float("-inf")
-            log_probs = log_probs.view(Bt, nb, V) + running_scores[:, :, None]
-            topk_lp, topk_i = torch.topk(log_probs.view(Bt, nb * V), k=keep)
+        # device-side step (emu_beam_topk): log_softmax + repetition penalty + EOS ban + running score + top-2*beams over
+        # beams x vocab all happen in the library; only the [batch, 2*beams] bookkeeping below runs here
+        prev = None
+        if repetition_penalty != 1.0 and cur_len > 0:
+            prev = running_seq[:, :, :cur_len].reshape(Bt * nb, cur_len)
+        topk_lp, topk_i = engine.beam_topk(logits, running_scores, Bt, nb, keep,
+                                           ban_id=eos_token_id if cur_len < min_length else -1, prev_tokens=prev,
+                                           repetition_penalty=repetition_penalty)
         topk_beam = topk_i // V
         topk_ids = topk_i % V
         topk_run_bi = _gather_beams(run_beam_idx, topk_beam)

@@ -56,6 +56,37 @@ class OracleEngine:
             next_ids.copy_(lg.argmax(-1).to(next_ids.dtype))
 
 
+    def beam_topk(self, logits, running_scores, batch, beams, keep, ban_id=-1, prev_tokens=None, repetition_penalty=1.0):
+        """torch formulation of the HF _beam_search step that emu_beam_topk implements on the device"""
+        V = logits.shape[-1]
+        lp = torch.log_softmax(logits.float(), dim=-1)
+        if prev_tokens is not None and repetition_penalty != 1.0:
+            sc = torch.gather(lp, 1, prev_tokens)
+            sc = torch.where(sc < 0, sc * repetition_penalty, sc / repetition_penalty)
+            lp = lp.scatter(1, prev_tokens, sc)
+        if ban_id is not None and ban_id >= 0:
+            lp[:, ban_id] = float("-inf")
+        lp = lp.view(batch, beams, V) + running_scores[:, :, None]
+        return torch.topk(lp.view(batch, beams * V), k=keep)
+
+    def sample_tokens(self, logits, temperature=1.0, top_k=0, top_p=1.0, ban_id=-1, seed=0, offset=0):
+        """HF warpers + torch.multinomial (what emu_sample_tokens implements on the device)"""
+        scores = logits.float().clone()
+        if ban_id is not None and ban_id >= 0:
+            scores[:, ban_id] = float("-inf")
+        scores = scores / temperature
+        if top_k:
+            kth = torch.topk(scores, min(top_k, scores.shape[-1]))[0][..., -1, None]
+            scores = scores.masked_fill(scores < kth, float("-inf"))
+        if top_p < 1.0:
+            s_sorted, s_idx = torch.sort(scores, descending=False)
+            remove = s_sorted.softmax(-1).cumsum(-1) <= (1 - top_p)
+            remove[..., -1:] = False
+            scores = scores.masked_fill(remove.scatter(1, s_idx, remove), float("-inf"))
+        g = torch.Generator().manual_seed((seed + offset) % (2 ** 63))
+        return torch.multinomial(scores.softmax(-1), 1, generator=g).squeeze(1).to(torch.int32)
+
+
 @pytest.fixture(scope="module")
 def setup():
     gold = torch.load(GOLD)
