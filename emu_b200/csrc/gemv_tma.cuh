@@ -251,15 +251,25 @@ static __device__ __forceinline__ void tma_consume(const GemvTmaParams* sp, long
   int seg_lo = cp_kc;
   const int xsc = (p.xsc > 0 && p.xsc < CPT) ? p.xsc : CPT;  // chunks per staged x segment
   int cur_seg = cp_kc / xsc;                                  // the caller staged this segment (tma_stage_x(.., seg))
+  int k_in_seg = cp_kc - cur_seg * xsc;                       // tracked incrementally: no division in the chunk loop
   for (int i = 0; i < n; ++i) {
-    if (cp_kc / xsc != cur_seg) {  // the chunk stream left the staged K segment: all 8 consumer warps re-stage together
-      cur_seg = cp_kc / xsc;
+    // leave the staged K segment?  (never when the whole row is staged: xsc == CPT)
+    bool restage = false;
+    if (cp_kc == 0) {  // a new row group starts at column 0
+      if (cur_seg != 0) { cur_seg = 0; restage = true; }
+      k_in_seg = 0;
+    } else if (k_in_seg == xsc) {  // ran off the end of the segment inside a row
+      ++cur_seg;
+      k_in_seg = 0;
+      restage = true;
+    }
+    if (restage) {  // all 8 consumer warps take this branch together (same chunk stream)
       consumer_bar();
       tma_stage_x_seg(p, xs, s_rstd, cur_seg);
     }
     mbar_wait(&full_bar[stage], phase);
     const uint32_t tbase = smem_u32(ring + stage * kTStageBytes + tile_j * (kTRows * 128));
-    const bf16* xk = xrow + (cp_kc - cur_seg * xsc) * kTCols;
+    const bf16* xk = xrow + k_in_seg * kTCols;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       uint32_t bfr[2] = {0u, 0u};
@@ -292,6 +302,7 @@ static __device__ __forceinline__ void tma_consume(const GemvTmaParams* sp, long
       }
       gemv_tma_flush(sp, red, fin, s_last, cp_grp, seg_lo, cp_kc);
     }
+    ++k_in_seg;
     if (++cp_kc == CPT) { cp_kc = 0; ++cp_grp; }
     if (grp_done) seg_lo = cp_kc;
   }
