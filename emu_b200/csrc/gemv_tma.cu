@@ -2,16 +2,17 @@
 // stream-K decomposition; this file is the production path whenever the shape allows, gemv.cu is the fallback).
 //
 // Why a second kernel: gemv.cu keeps its bytes-in-flight in registers (16 x 16 B per lane).  That needs two 256-thread
-// CTAs per SM to cover HBM latency, which fills the register file — so the NEXT kernel of the decode step cannot
-// become resident until this one exits and programmatic dependent launch has nothing to overlap: ~4 us of HBM idle per
-// launch x 300 launches per token (measured: 12.9 ms/token vs 11.5 ms of summed kernel time).  Here the bytes in flight
-// live in shared memory instead:
-//   * one producer thread issues cp.async.bulk.tensor (TMA) loads of [32 rows x 64 cols] 128B-swizzled tiles into a
-//     5-stage x 16 KB ring, signalled by mbarriers — 80 KB in flight per CTA with zero registers and zero address math;
+// CTAs per SM to cover HBM latency and fills the register file.  Here the bytes in flight live in shared memory instead:
+//   * one producer thread issues cp.async.bulk.tensor (TMA) loads of [32 rows x 64 cols] 128B-swizzled tiles into an
+//     8-stage x 16 KB ring signalled by mbarriers — 128 KB in flight per SM with zero registers and zero address math
+//     (measured: 8 stages 6.3 TB/s on the large projections, 5 stages 5.6; depth of prefetch beats letting the PDL
+//     successor co-reside — profiles/r01_kernel_bench_tma_stages.txt);
 //   * 8 consumer warps pull A fragments with ldmatrix (conflict-free through the swizzle) and run mma.sync with the
 //     staged x rows as the 8-wide N operand, then release the stage;
-//   * ONE CTA per SM (grid = 148, ~100 KB smem, 64 regs): the next kernel's CTA fits beside it, so with PDL its ring is
-//     already full when this kernel drains — HBM never idles across kernel boundaries.
+//   * ONE persistent CTA per SM (grid = 148), stream-K over (row group, k chunk) units, last-arriver fix-up in fixed
+//     order; with PDL the producer starts streaming weights before griddepcontrol.wait resolves.
+// x (batch <= 8 rows) is staged in shared memory once per CTA; when batch x K does not fit next to the ring (5 beams x
+// 17920) it is staged in K segments that are re-staged as the chunk stream crosses them (GemvTmaParams::xsc).
 // Ragged N and K tails cost nothing (TMA zero-fills out-of-bounds rows/columns).
 #include "gemv_tma.cuh"
 
