@@ -118,3 +118,78 @@ def build_emu2_model(vision_kwargs, llama_dir, instruct=False, seed=0, dtype=tor
     except Exception:
         pass
     return model.to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# Emu1 Causal-Former (Emu1/models/causal_former.py + the vendored Emu1/models/modeling_t5.py)
+# ------------------------------------------------------------------------------------------------
+def import_emu1_causal_former(t5_overrides=None):
+    """Import the UNMODIFIED reference CausalFormer under the installed transformers 5.x.  The vendored T5 was written
+    for transformers 4.31; what 5.x removed is put back as inert shims — none of them touches arithmetic:
+      * transformers.pytorch_utils.find_pruneable_heads_and_indices / prune_linear_layer (head pruning, never called)
+      * transformers.utils.model_parallel_utils (device-map helpers, never called)
+      * docstring decorators / DUMMY_* constants if missing
+      * PreTrainedModel.get_head_mask (returns [None] * n_layers for head_mask=None, as 4.31 did)
+      * PretrainedConfig.add_cross_attention = False (the 4.31 default the vendored T5Block reads)
+      * T5Config.from_pretrained("t5-base") needs the network: replaced by the published t5-base config values.
+    The module files are loaded by path into a synthetic package so Emu1/models/__init__.py (which pulls decord, peft,
+    xformers-configured ViT …) is not executed.  `t5_overrides` (dict of T5Config fields) shrinks the stack for golden
+    fixtures; None gives the real t5-base stack.  Returns the `CausalFormer` class."""
+    import importlib.util
+
+    import transformers  # noqa: F401
+    import transformers.pytorch_utils as pu
+    import transformers.utils as tu
+    from transformers.modeling_utils import PreTrainedModel
+    from transformers.models.t5.configuration_t5 import T5Config
+
+    def _never(*a, **k):
+        raise NotImplementedError("pruning / model-parallel helpers are not on the generate path")
+    for name in ("find_pruneable_heads_and_indices", "prune_linear_layer"):
+        if not hasattr(pu, name):
+            setattr(pu, name, _never)
+    for name in ("DUMMY_INPUTS", "DUMMY_MASK"):
+        if not hasattr(tu, name):
+            setattr(tu, name, [[0]])
+    for name in ("add_start_docstrings", "add_start_docstrings_to_model_forward", "replace_return_docstrings"):
+        if not hasattr(tu, name):
+            setattr(tu, name, lambda *a, **k: (lambda f: f))
+    if not hasattr(tu, "is_torch_fx_proxy"):
+        tu.is_torch_fx_proxy = lambda x: False
+    if "transformers.utils.model_parallel_utils" not in sys.modules:
+        m = types.ModuleType("transformers.utils.model_parallel_utils")
+        m.assert_device_map = lambda *a, **k: None
+        m.get_device_map = lambda *a, **k: None
+        sys.modules["transformers.utils.model_parallel_utils"] = m
+    if not hasattr(PreTrainedModel, "get_head_mask"):
+        def get_head_mask(self, head_mask, num_hidden_layers, is_attention_chunked=False):
+            if head_mask is not None:
+                raise NotImplementedError
+            return [None] * num_hidden_layers
+        PreTrainedModel.get_head_mask = get_head_mask
+
+    def t5_base_config(name, **kw):
+        fields = dict(vocab_size=32128, d_model=768, d_kv=64, d_ff=3072, num_layers=12, num_decoder_layers=12, num_heads=12,
+                      relative_attention_num_buckets=32, relative_attention_max_distance=128, dropout_rate=0.1,
+                      layer_norm_epsilon=1e-6, feed_forward_proj="relu", is_encoder_decoder=True)
+        fields.update(t5_overrides or {})
+        c = T5Config(**fields)
+        c.add_cross_attention = False
+        return c
+    T5Config.from_pretrained = staticmethod(t5_base_config)
+
+    pkg_name = "_emu1_ref_models"
+    if pkg_name not in sys.modules:
+        pkg = types.ModuleType(pkg_name)
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "Emu1", "models")]
+        sys.modules[pkg_name] = pkg
+    mods = {}
+    for name in ("modeling_t5", "causal_former"):
+        full = pkg_name + "." + name
+        if full not in sys.modules:
+            spec = importlib.util.spec_from_file_location(full, os.path.join(REFERENCE_ROOT, "Emu1", "models", name + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[full] = mod
+            spec.loader.exec_module(mod)
+        mods[name] = sys.modules[full]
+    return mods["causal_former"].CausalFormer

@@ -5,11 +5,14 @@ T5LayerNorm :318-331, T5Attention.forward :537-689 (no score scaling, relative p
 all blocks :455-536, fp32 softmax :666, cross-attention K/V from encoder_width :422-424), T5DenseActDense :352-365
 (ReLU), T5Block :787-905, T5Stack.forward :1100-1366 (decoder => causal self-attention mask, final_layer_norm).
 
-PINNING: the vendored modeling_t5.py does not import under the installed transformers 5.5.0 (removed helpers:
-find_pruneable_heads_and_indices, model_parallel_utils, get_head_mask; T5Config.from_pretrained("t5-base") needs the
-network — SURVEY.md §8c), so this oracle cannot be run against the reference module here: parity for this block is
-pinned by restatement only ("parity unpinned"), with t5-base constants: d_model 768, d_kv 64, 12 heads, d_ff 3072,
-12 layers, 32 buckets, max distance 128, eps 1e-6.
+PINNED (bit-exact): the vendored modeling_t5.py was written for transformers 4.31; oracle/ref_shim.py
+`import_emu1_causal_former()` puts back the inert helpers transformers 5.x removed (pruning / device-map utilities,
+`get_head_mask`, the `add_cross_attention` config default, a local t5-base config instead of the hub download) and
+imports the UNMODIFIED reference module.  tests/test_oracle_cpu.py::test_t5_oracle_vs_live_reference_t5_base checks this
+file bit for bit against it at the real t5-base dimensions (fp32 and bf16), and
+tests/golden/emu1_cformer_tiny.pt (tests/golden/gen_golden_cformer.py) carries reference outputs of a shrunk stack to the
+GPU box for `test_cformer_vs_reference_golden`.  t5-base constants: d_model 768, d_kv 64, 12 heads, d_ff 3072, 12 layers,
+32 buckets, max distance 128, eps 1e-6.
 """
 import math
 

@@ -100,3 +100,41 @@ def test_preprocess_oracle_vs_torchvision(H, W, S):
     t = tv.Compose([tv.Resize((S, S), interpolation=tv.InterpolationMode.BICUBIC), tv.ToTensor(),
                     tv.Normalize(mean=mean, std=std)])
     assert np.array_equal(t(pil).numpy(), P.image_transform(img, S, mean, std))
+
+
+def _cformer_golden():
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "emu1_cformer_tiny.pt"))
+    from oracle import diffusion_oracle as D, t5_oracle as T
+    sd = D.random_state_dict(T.param_shapes(g["cfg"], g["enc_w"], g["out_dim"], n_causal=g["n_causal"]), seed=g["seed"])
+    for k in sd:
+        if k.endswith("Attention.q.weight"):
+            sd[k] = sd[k] * 0.125
+    return g, sd
+
+
+def test_t5_oracle_vs_reference_golden():
+    """oracle/t5_oracle.py (Causal-Former restatement) reproduces the outputs the UNMODIFIED reference module produced
+    (tests/golden/gen_golden_cformer.py) bit for bit, fp32 and bf16."""
+    from oracle import t5_oracle as T
+    g, sd = _cformer_golden()
+    out = T.causal_former(sd, g["img_embeds"], g["cfg"])
+    assert torch.equal(out, g["out_fp32"])
+    sd16 = {k: v.to(torch.bfloat16) for k, v in sd.items()}
+    out16 = T.causal_former(sd16, g["img_embeds"].to(torch.bfloat16), g["cfg"]).float()
+    assert torch.equal(out16, g["out_bf16"])
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference only exists in the authoring container")
+def test_t5_oracle_vs_live_reference_t5_base():
+    """Same, against the live reference at the real t5-base dimensions (12 layers, d_model 768) with its own default
+    initialisation — bit-exact."""
+    from oracle import t5_oracle as T
+    CF = ref_shim.import_emu1_causal_former()
+    torch.manual_seed(0)
+    m = CF(None, n_causal=32, vision_width=1408, output_dim=512).eval()
+    x = torch.randn(1, 257, 1408)
+    for dt in (torch.float32, torch.bfloat16):  # the module is created half bf16 / half fp32: make it uniform first
+        m = m.to(dt)
+        sd = {"cformer." + k: v.detach().clone() for k, v in m.state_dict().items()}
+        with torch.no_grad():
+            assert torch.equal(m(x.to(dt)), T.causal_former(sd, x.to(dt)))
