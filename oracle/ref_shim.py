@@ -193,3 +193,40 @@ def import_emu1_causal_former(t5_overrides=None):
             spec.loader.exec_module(mod)
         mods[name] = sys.modules[full]
     return mods["causal_former"].CausalFormer
+
+
+def _load_emu1_module(name):
+    """Load Emu1/models/<name>.py by path into the synthetic package (Emu1/models/__init__.py is not executed)."""
+    import importlib.util
+    pkg_name = "_emu1_ref_models"
+    if pkg_name not in sys.modules:
+        pkg = types.ModuleType(pkg_name)
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "Emu1", "models")]
+        sys.modules[pkg_name] = pkg
+    full = pkg_name + "." + name
+    if full not in sys.modules:
+        spec = importlib.util.spec_from_file_location(full, os.path.join(REFERENCE_ROOT, "Emu1", "models", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[full] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules[full]
+
+
+def import_emu1_vit():
+    """The UNMODIFIED Emu1 `EVAVisionTransformer` (Emu1/models/eva_vit_model.py; pre-norm blocks, external ln_visual).
+    Needs only the timm shim; `xattn` must stay False (xformers is not installed — same math)."""
+    _install_timm_shim()
+    _load_emu1_module("transformer")
+    _load_emu1_module("rope")
+    return _load_emu1_module("eva_vit_model").EVAVisionTransformer
+
+
+def build_emu1_vit(vis, embed_dim=64):
+    """Construct it the way Emu1/models/model.py:_build_vision_tower does for Emu-14B.json (with xattn off)."""
+    from functools import partial
+    EVA = import_emu1_vit()
+    return EVA(img_size=vis["image_size"], patch_size=vis["patch_size"], num_classes=embed_dim, use_mean_pooling=False,
+               init_values=None, patch_dropout=0., embed_dim=vis["width"], depth=vis["layers"],
+               num_heads=vis["width"] // vis["head_width"], mlp_ratio=vis["mlp_ratio"], qkv_bias=True, drop_path_rate=0.,
+               norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), xattn=False, rope=False, postnorm=False, pt_hw_seq_len=16,
+               intp_freq=False, naiveswiglu=False, subln=False).eval()

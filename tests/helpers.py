@@ -72,3 +72,33 @@ class StubTokenizer:
 
     def batch_decode(self, ids, skip_special_tokens=True):
         return [" ".join(str(int(i)) for i in row if not (skip_special_tokens and int(i) in (0, 1, 2, 32000))) for row in ids]
+
+
+# ---- Emu1 fixtures (shared by tests/test_emu1_vae_gpu.py and tests/golden/gen_golden_emu1.py) ----
+EMU1_VIS = dict(image_size=56, patch_size=14, width=128, layers=2, head_width=32, mlp_ratio=4.0)  # head_dim 32
+EMU1_VIS88 = dict(image_size=56, patch_size=14, width=176, layers=2, head_width=88, mlp_ratio=4.0)  # head_dim 88 like EVA-g
+EMU1_LLAMA = dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512, rms_norm_eps=1e-6,
+                  max_position_embeddings=256, vocab_size=32000, rope_theta=10000.0)
+
+
+def emu1_t5_cfg():
+    from oracle import t5_oracle as T
+    return dict(T.T5_BASE, layers=2, d_model=128, heads=2, d_ff=256)
+
+
+def emu1_state_dict(vis, seed=0):
+    from oracle import diffusion_oracle as D
+    from oracle import t5_oracle as T
+    sd = make_emu2_state_dict(vision=dict(vis, n_query=4, v_query=4), llama=EMU1_LLAMA, vocab=32004, seed=seed)
+    sd.pop("project_up.weight"), sd.pop("project_down.weight")
+    g = torch.Generator().manual_seed(seed + 100)
+    W = vis["width"]
+    sd["ln_visual.weight"] = 1 + 0.1 * torch.randn(W, generator=g)
+    sd["ln_visual.bias"] = 0.05 * torch.randn(W, generator=g)
+    sd["decoder.lm.stu_regress_head.weight"] = torch.randn(256, 256, generator=g) / 16
+    cf = D.random_state_dict(T.param_shapes(emu1_t5_cfg(), W, 256, n_causal=8), seed=seed + 7)
+    for k in cf:  # T5 attention is unscaled: the Mesh-TF init keeps q small so that the softmax is not saturated
+        if k.endswith("Attention.q.weight"):
+            cf[k] = cf[k] * 0.125
+    sd.update(cf)
+    return sd

@@ -138,3 +138,30 @@ def test_t5_oracle_vs_live_reference_t5_base():
         sd = {"cformer." + k: v.detach().clone() for k, v in m.state_dict().items()}
         with torch.no_grad():
             assert torch.equal(m(x.to(dt)), T.causal_former(sd, x.to(dt)))
+
+
+def test_emu1_oracle_vs_reference_golden():
+    """Emu1 image path of the oracle (pre-norm EVA ViT -> ln_visual -> Causal-Former) == outputs of the UNMODIFIED
+    reference modules (tests/golden/gen_golden_emu1.py), bit for bit, head widths 32 and 88."""
+    from helpers import EMU1_VIS, EMU1_VIS88, emu1_state_dict, emu1_t5_cfg
+    from oracle import t5_oracle as T
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "emu1_tiny.pt"))
+    for vis in (EMU1_VIS, EMU1_VIS88):
+        g = gold["w%d" % vis["width"]]
+        sd = emu1_state_dict(vis)
+        feats = O.vit_forward_features(sd, g["image"], patch=14, num_heads=vis["width"] // vis["head_width"], layers=2,
+                                       postnorm=False)
+        feats = F.layer_norm(feats, (vis["width"],), sd["ln_visual.weight"], sd["ln_visual.bias"], 1e-6)
+        assert torch.equal(feats, g["ln_visual_features"])
+        assert torch.equal(T.causal_former(sd, feats, emu1_t5_cfg()), g["cformer_out"])
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference only exists in the authoring container")
+def test_emu1_vit_oracle_vs_live_reference():
+    from helpers import EMU1_VIS88
+    vit = ref_shim.build_emu1_vit(EMU1_VIS88)
+    sd = {"visual." + k: v.detach().clone() for k, v in vit.state_dict().items()}
+    img = torch.randn(2, 3, 56, 56, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ref = vit.forward_features(img)
+    assert torch.equal(ref, O.vit_forward_features(sd, img, patch=14, num_heads=2, layers=2, postnorm=False))
