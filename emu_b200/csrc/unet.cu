@@ -233,7 +233,14 @@ int load_by_spec(EmuEngine* e, const SpecMap& specs, const char* what, const std
 int unet_load_tensor(EmuEngine* e, const std::string& key, const bf16* src, const int64_t* shape, int ndim,
                      cudaStream_t st) {
   if (!e->unet) return e->fail(EMU_ERR_STATE, "emu_unet_configure must be called before loading unet.* tensors");
-  e->unet->kv_all_ready = false;  // re-stack the cross-attention weights on the next forward
+  UNetModel* m = e->unet;
+  m->kv_all_ready = false;  // re-stack the cross-attention weights on the next forward ...
+  if (!m->graphs.empty()) {  // ... which must run eagerly: captured steps read the (now stale) stacked copy
+    cudaDeviceSynchronize();
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+    m->graphs.clear();
+    m->warmed.clear();
+  }
   return load_by_spec(e, e->unet->specs, "unet", key, src, shape, ndim, st);
 }
 
