@@ -402,7 +402,8 @@ def run_cuda(args):
     n_query = vc.n_query
     prompt_len = 2 + n_query + 1 + N_TEXT
     model = EmuModel(vc, TextDecoderCfg(), tokenizer=synthetic.SyntheticTokenizer(vocab), llama_config=lc,
-                     max_batch=5, max_seq=prompt_len + NEW_TOKENS + 8, tp_rank=rank, tp_size=world, nccl_uid=uid)
+                     max_batch=5 if (world == 1 and not args.no_beam) else 1,  # 5 cache rows only for the 5-beam secondary
+                     max_seq=prompt_len + NEW_TOKENS + 8, tp_rank=rank, tp_size=world, nccl_uid=uid)
     synthetic.load_random_weights(model, vc, lc, vocab, seed=0)
 
     g = torch.Generator().manual_seed(1234)
