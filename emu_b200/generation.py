@@ -101,17 +101,21 @@ def beam_search(engine, inputs_embeds, attention_mask, num_beams, max_new_tokens
     logits_buf = torch.empty_like(logits)
 
     keep = 2 * nb
-    top_mask = torch.cat((torch.ones(nb, dtype=torch.bool), torch.zeros(keep - nb, dtype=torch.bool))).to(dev)
-    running_seq = torch.full((Bt, nb, max_length), pad_token_id, dtype=torch.int64, device=dev)
+    # The vocabulary-wide work of a step runs on the device (engine.beam_topk); what is left is bookkeeping on
+    # [batch, 2*beams] / [batch, beams, len] tensors, a few hundred bytes.  It lives on the HOST: one 80-byte D2H of the
+    # candidates (the step has to synchronise for the stopping test anyway) replaces ~40 tiny kernel launches per step.
+    bdev = torch.device("cpu")
+    top_mask = torch.cat((torch.ones(nb, dtype=torch.bool), torch.zeros(keep - nb, dtype=torch.bool))).to(bdev)
+    running_seq = torch.full((Bt, nb, max_length), pad_token_id, dtype=torch.int64, device=bdev)
     sequences = running_seq.clone()
-    running_scores = torch.zeros(Bt, nb, dtype=torch.float, device=dev)
+    running_scores = torch.zeros(Bt, nb, dtype=torch.float, device=bdev)
     running_scores[:, 1:] = -1e9
-    beam_scores = torch.full((Bt, nb), -1e9, dtype=torch.float, device=dev)
-    is_finished = torch.zeros(Bt, nb, dtype=torch.bool, device=dev)
-    unsat = torch.ones(Bt, 1, dtype=torch.bool, device=dev)
-    run_beam_idx = torch.full((Bt, nb, max_length), -1, dtype=torch.int32, device=dev)
+    beam_scores = torch.full((Bt, nb), -1e9, dtype=torch.float, device=bdev)
+    is_finished = torch.zeros(Bt, nb, dtype=torch.bool, device=bdev)
+    unsat = torch.ones(Bt, 1, dtype=torch.bool, device=bdev)
+    run_beam_idx = torch.full((Bt, nb, max_length), -1, dtype=torch.int32, device=bdev)
     beam_idx_fin = run_beam_idx.clone()
-    batch_off = (torch.arange(Bt, device=dev) * nb).view(-1, 1)
+    batch_off = (torch.arange(Bt, device=bdev) * nb).view(-1, 1)
     tok32 = torch.empty(Bt * nb, dtype=torch.int32, device=dev)
     src32 = torch.empty(Bt * nb, dtype=torch.int32, device=dev)
 
@@ -121,10 +125,11 @@ def beam_search(engine, inputs_embeds, attention_mask, num_beams, max_new_tokens
         # beams x vocab all happen in the library; only the [batch, 2*beams] bookkeeping below runs here
         prev = None
         if repetition_penalty != 1.0 and cur_len > 0:
-            prev = running_seq[:, :, :cur_len].reshape(Bt * nb, cur_len)
-        topk_lp, topk_i = engine.beam_topk(logits, running_scores, Bt, nb, keep,
+            prev = running_seq[:, :, :cur_len].reshape(Bt * nb, cur_len).to(dev)
+        topk_lp, topk_i = engine.beam_topk(logits, running_scores.to(dev), Bt, nb, keep,
                                            ban_id=eos_token_id if cur_len < min_length else -1, prev_tokens=prev,
                                            repetition_penalty=repetition_penalty)
+        topk_lp, topk_i = topk_lp.to(bdev), topk_i.to(bdev)  # [batch, 2*beams]: the only per-step device->host traffic
         topk_beam = topk_i // V
         topk_ids = topk_i % V
         topk_run_bi = _gather_beams(run_beam_idx, topk_beam)
@@ -179,4 +184,4 @@ def beam_search(engine, inputs_embeds, attention_mask, num_beams, max_new_tokens
     best = sequences[:, 0, :]
     bi = beam_idx_fin[:, 0, :]
     gen_len = int(((bi + 1).bool()).sum(dim=1).max())
-    return best[:, :gen_len]
+    return best[:, :gen_len].to(dev)
