@@ -230,3 +230,49 @@ def build_emu1_vit(vis, embed_dim=64):
                num_heads=vis["width"] // vis["head_width"], mlp_ratio=vis["mlp_ratio"], qkv_bias=True, drop_path_rate=0.,
                norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), xattn=False, rope=False, postnorm=False, pt_hw_seq_len=16,
                intp_freq=False, naiveswiglu=False, subln=False).eval()
+
+
+def build_emu1_model(vis, llama, n_causal=8, t5_overrides=None):
+    """Instantiate the UNMODIFIED reference `Emu` (Emu1/models/modeling_emu.py) on CPU with shrunk sub-models:
+    `vis` -> vision_cfg (xattn off), `llama` -> a temporary ./models/llama_config (the class reads that cwd-relative
+    path, Emu1/models/modeling_llama.py:5) holding the reference's own tokenizer files and a small config.json,
+    `t5_overrides` -> the Causal-Former's T5 stack.  decord / peft are stubbed (only imported, never used here)."""
+    import importlib
+    _install_timm_shim()
+    import_emu1_causal_former(t5_overrides)  # installs the transformers shims + the local T5 config
+    for stub in ("decord", "peft"):
+        if stub not in sys.modules:
+            sys.modules[stub] = types.ModuleType(stub)
+    if not hasattr(sys.modules["peft"], "PeftModel"):  # names prediction_mixin.py imports (LoRA eval helpers, unused here)
+        for name in ("PeftModel", "LoraConfig", "TaskType", "get_peft_model"):
+            setattr(sys.modules["peft"], name, type(name, (), {}))
+    root = os.path.join(REFERENCE_ROOT, "Emu1")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    work = tempfile.mkdtemp(prefix="emu1_ref_")
+    dst = os.path.join(work, "models", "llama_config")
+    os.makedirs(dst)
+    src = os.path.join(root, "models", "llama_config")
+    for f in os.listdir(src):
+        if f != "config.json":
+            shutil.copy(os.path.join(src, f), os.path.join(dst, f))
+    cfg = json.load(open(os.path.join(src, "config.json")))
+    cfg.update(hidden_size=llama["hidden_size"], num_hidden_layers=llama["num_hidden_layers"],
+               num_attention_heads=llama["num_attention_heads"], intermediate_size=llama["intermediate_size"],
+               max_position_embeddings=llama.get("max_position_embeddings", 256), rms_norm_eps=llama.get("rms_norm_eps", 1e-6),
+               torch_dtype="float32", attn_implementation="eager", _attn_implementation="eager")
+    cfg.pop("num_key_value_heads", None)
+    json.dump(cfg, open(os.path.join(dst, "config.json"), "w"))
+    cwd = os.getcwd()
+    os.chdir(work)
+    try:
+        me = importlib.import_module("models.modeling_emu")
+        args = types.SimpleNamespace(instruct=False)
+        vision_cfg = dict(image_size=vis["image_size"], layers=vis["layers"], width=vis["width"], head_width=vis["head_width"],
+                          mlp_ratio=vis["mlp_ratio"], patch_size=vis["patch_size"], eva_model_name="eva-clip-g-14-x",
+                          drop_path_rate=0, xattn=False, freeze=False)
+        model = me.Emu(embed_dim=64, multimodal_cfg=dict(name="llama-13B", xattn=False, n_causal=n_causal, freeze=False),
+                       vision_cfg=vision_cfg, vladapter_cfg=dict(name="cformer", n_causal=n_causal), args=args)
+    finally:
+        os.chdir(cwd)
+    return model.eval()

@@ -165,3 +165,36 @@ def test_emu1_vit_oracle_vs_live_reference():
     with torch.no_grad():
         ref = vit.forward_features(img)
     assert torch.equal(ref, O.vit_forward_features(sd, img, patch=14, num_heads=2, layers=2, postnorm=False))
+
+
+def _emu1_generate_image_oracle(sd, ids, image, vis):
+    """Emu1/models/modeling_emu.py:187-249 restated with the oracle pieces (cache-less literal loop: every iteration
+    re-runs the decoder over the grown sequence and appends stu_regress_head(h_last))."""
+    from helpers import emu1_t5_cfg
+    from oracle import t5_oracle as T
+    emb = F.embedding(ids, sd["decoder.lm.model.embed_tokens.weight"])
+    if image is not None:
+        feats = O.vit_forward_features(sd, image, patch=14, num_heads=vis["width"] // vis["head_width"], layers=2, postnorm=False)
+        feats = F.layer_norm(feats, (vis["width"],), sd["ln_visual.weight"], sd["ln_visual.bias"], 1e-6)
+        cf = T.causal_former(sd, feats, emu1_t5_cfg())
+        emb[ids == 32003] = cf.reshape(-1, cf.shape[-1])
+    outs = []
+    for _ in range(8):
+        h = O.llama_forward(sd, emb, torch.ones(1, emb.shape[1], dtype=torch.long), layers=2, heads=2)
+        reg = F.linear(h[:, -1], sd["decoder.lm.stu_regress_head.weight"])
+        outs.append(reg)
+        emb = torch.cat((emb, reg[:, None]), dim=1)
+    return torch.stack(outs, dim=1)
+
+
+def test_emu1_generate_image_oracle_vs_reference_golden():
+    """The oracle's Emu1 generate_image == the UNMODIFIED reference `Emu.generate_image` (tests/golden/
+    gen_golden_emu1_genimg.py; its own tokenizer, 8 full re-forwards), text-only and with a prompt image."""
+    from helpers import EMU1_VIS, emu1_state_dict
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "emu1_genimg_tiny.pt"))
+    sd = emu1_state_dict(EMU1_VIS)
+    for key in ("text_only", "with_image"):
+        g = gold[key]
+        out = _emu1_generate_image_oracle(sd, g["input_ids"], g.get("image"), EMU1_VIS)
+        assert out.shape == g["embeds"].shape
+        assert O.rel_err(out, g["embeds"]) < 1e-5, (key, O.rel_err(out, g["embeds"]))
