@@ -20,6 +20,11 @@ def test_euler_tables_match_oracle():
         assert abs(s.init_noise_sigma - init) < 1e-6
     s.set_timesteps(50)
     assert s.timesteps[0] == 981 and s.timesteps[-1] == 1 and s.sigmas[-1] == 0
+    # external anchor (diffusers is not installable here): the scaled-linear 0.00085 -> 0.012 / 1000-step noise
+    # schedule of Emu2/emu/conf/diffusion_config/scheduler/scheduler_config.json has the published Stable-Diffusion sigma
+    # range sigma_min = 0.0292, sigma_max = 14.6146 (k-diffusion / SD v1 sampling configs quote exactly these)
+    assert abs(float(s._sigmas_all[-1]) - 14.6146) < 1e-3
+    assert abs(float(s._sigmas_all[0]) - 0.0292) < 1e-4
 
 
 class _FakeModel:
