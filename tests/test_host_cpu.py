@@ -90,3 +90,42 @@ def test_unet_config_translation_and_param_count():
     assert abs(n / 1e9 - 2.526) < 2e-3   # 2.526 B parameters from the reference's config
     import bench
     assert sum(torch.Size(s).numel() for _, s in bench.unet_param_shapes(bench.emu2_unet_json())) == n
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_shim", fromlist=["x"]).available(),
+                    reason="/root/reference only exists in the authoring container")
+def test_chat_prompt_assembly_vs_live_reference():
+    """Prompt strings and image tensors of EmuChatGeneration._prepare_inputs / _prepare_chat_inputs are identical to the
+    UNMODIFIED reference's (Emu2/emu/chat.py:121-195), for plain, interleaved, video and multi-turn (grounding) inputs."""
+    from PIL import Image
+    from oracle import ref_shim
+    from emu_b200.emu2.chat import EmuChatGeneration
+    ref_shim.import_emu2()
+    import emu.chat as rchat
+    from emu.constants import DEFAULT_VIDEO_TOKEN, FAKE_VIDEO_END_TOKEN
+    mine = EmuChatGeneration(_FakeModel())
+    ref = rchat.EmuChatGeneration.__new__(rchat.EmuChatGeneration)   # no model needed for prompt assembly
+    ref.transform = rchat.TF.Compose([
+        rchat.TF.Resize((448, 448), interpolation=rchat.TF.InterpolationMode.BICUBIC), rchat.TF.ToTensor(),
+        rchat.TF.Normalize(mean=rchat.OPENAI_DATASET_MEAN, std=rchat.OPENAI_DATASET_STD)])
+    imgs = [Image.new("RGB", (64 + 10 * i, 48 + 7 * i), (10 * i, 200 - 20 * i, 30 + i)) for i in range(4)]
+    plain = [
+        [imgs[0], "describe"],
+        ["before", imgs[1], "between", imgs[2], "after"],
+        ["watch:", DEFAULT_VIDEO_TOKEN, imgs[0], imgs[1], FAKE_VIDEO_END_TOKEN, "what happens?", imgs[3]],
+        ["text only"],
+    ]
+    for inp in plain:
+        a, b = mine._prepare_inputs(inp), ref._prepare_inputs(inp)
+        assert a[0] == b[0] and a[3:] == b[3:]
+        for x, y in ((a[1], b[1]), (a[2], b[2])):
+            assert (x is None) == (y is None) and (x is None or torch.equal(x, y))
+    chats = [
+        ([[imgs[0], "what is this?"], ["a cat"], ["and this?", imgs[1]]], True),
+        ([["hello"]], False),
+        ([[imgs[2], imgs[3], "compare"], ["they differ"], ["how?"]], False),
+    ]
+    for inp, grounding in chats:
+        a, b = mine._prepare_chat_inputs(inp, is_grounding=grounding), ref._prepare_chat_inputs(inp, is_grounding=grounding)
+        assert a[0] == b[0]
+        assert (a[1] is None) == (b[1] is None) and (a[1] is None or torch.equal(a[1], b[1]))
