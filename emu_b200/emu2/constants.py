@@ -1,33 +1,32 @@
-"""Special-token strings and preprocessing constants of Emu2 (values as published in Emu2/emu/constants.py)."""
-EVA_IMAGE_SIZE = 448
-OPENAI_DATASET_MEAN = (0.48145466, 0.4578275, 0.40821073)
-OPENAI_DATASET_STD = (0.26862954, 0.26130258, 0.27577711)
+"""Special-token strings and preprocessing constants of Emu2.
 
-DEFAULT_PAD_TOKEN = "[PAD]"
-DEFAULT_BOS_TOKEN = "<s>"
-DEFAULT_EOS_TOKEN = "</s>"
-DEFAULT_UNK_TOKEN = "<unk>"
-DEFAULT_IMG_TOKEN = "[IMG]"
-DEFAULT_IMG_END_TOKEN = "[/IMG]"
-DEFAULT_IMAGE_TOKEN = "<image>"
-DEFAULT_gIMG_TOKEN = "[gIMG]"
-DEFAULT_gIMG_END_TOKEN = "[/gIMG]"
-DEFAULT_EOC_TOKEN = "[EOC]"
-DEFAULT_VIDEO_TOKEN = "[VIDEO]"
-GRD_SYMBOL = "<grounding>"
-BOP_SYMBOL = "<phrase>"
-EOP_SYMBOL = "</phrase>"
-BOO_SYMBOL = "<object>"
-EOO_SYMBOL = "</object>"
-DOM_SYMBOL = "</delimiter_of_multi_objects/>"
-REC_SYMBOL = "<REC>"
-USER_TOKEN = "[USER]"
-ASSISTANT_TOKEN = "[ASSISTANT]"
-DEFAULT_IMG_PLACEHOLDER = "[<IMG_PLH>]"
-DEFAULT_VID_PLACEHOLDER = "[<VID_PLH>]"
-FAKE_VIDEO_END_TOKEN = "[/VIDEO]"
-GROUND_SYSTEM_MESSAGE = "You are a helpful assistant, dedicated to provide concise and efficient answers."
-SYSTEM_MESSAGE = "You are a helpful assistant, dedicated to delivering comprehensive and meticulous responses."
+The VALUES are fixed by the published checkpoints and tokenizer (Emu2/emu/constants.py, Emu2/emu/lm.py:12-65): change one
+and token ids or pixel statistics no longer match the weights.  They are grouped here by what the engine does with them.
+"""
+# ---- image pre-processing (emu_preprocess_image): EVA-CLIP input side and the OpenAI CLIP pixel statistics ----
+EVA_IMAGE_SIZE = 448
+OPENAI_DATASET_MEAN, OPENAI_DATASET_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+
+# ---- tokenizer specials.  [PAD] is piece 32000; the rest get consecutive ids in the order of special_token_list() ----
+DEFAULT_PAD_TOKEN, DEFAULT_BOS_TOKEN, DEFAULT_EOS_TOKEN, DEFAULT_UNK_TOKEN = "[PAD]", "<s>", "</s>", "<unk>"
+# an image span in the prompt is  [IMG] <image> x n_query [/IMG]  (video frames use the [gIMG] pair), ids 32001..32005
+DEFAULT_IMG_TOKEN, DEFAULT_IMAGE_TOKEN, DEFAULT_IMG_END_TOKEN = "[IMG]", "<image>", "[/IMG]"
+DEFAULT_gIMG_TOKEN, DEFAULT_gIMG_END_TOKEN = "[gIMG]", "[/gIMG]"
+DEFAULT_EOC_TOKEN, DEFAULT_VIDEO_TOKEN, FAKE_VIDEO_END_TOKEN = "[EOC]", "[VIDEO]", "[/VIDEO]"
+# grounding vocabulary (phrase / object brackets, multi-object delimiter, referring-expression marker)
+GRD_SYMBOL, REC_SYMBOL = "<grounding>", "<REC>"
+BOP_SYMBOL, EOP_SYMBOL = "<phrase>", "</phrase>"
+BOO_SYMBOL, EOO_SYMBOL, DOM_SYMBOL = "<object>", "</object>", "</delimiter_of_multi_objects/>"
+# chat roles (only in the instruct tokenizer)
+USER_TOKEN, ASSISTANT_TOKEN = "[USER]", "[ASSISTANT]"
+
+# ---- what callers write in a prompt; EmuModel swaps them for the real spans before tokenising ----
+DEFAULT_IMG_PLACEHOLDER, DEFAULT_VID_PLACEHOLDER = "[<IMG_PLH>]", "[<VID_PLH>]"
+
+# ---- system prompts of the chat pipeline (plain / grounding) ----
+_ASSISTANT_PREFIX = "You are a helpful assistant, dedicated to "
+SYSTEM_MESSAGE = _ASSISTANT_PREFIX + "delivering comprehensive and meticulous responses."
+GROUND_SYSTEM_MESSAGE = _ASSISTANT_PREFIX + "provide concise and efficient answers."
 
 
 def special_token_list(instruct=False, quantized_size=256):
