@@ -55,55 +55,62 @@ class EmuChatGeneration:
 
     __call__ = forward
 
-    # ---- Emu2/emu/chat.py:121-157 ----
+    # ---- prompt assembly (behaviour of Emu2/emu/chat.py:121-195, pinned by tests/test_host_cpu.py against the live
+    #      reference).  A message is a flat list of strings and PIL images; "[VIDEO]" ... "[/VIDEO]" brackets frames. ----
+    @staticmethod
+    def _segments(items):
+        """Yield ("text", str) | ("image", img) | ("video", img).  The closing video marker is consumed silently, the
+        opening one is kept as text (that is what the tokenizer expects)."""
+        in_video = False
+        for it in items:
+            if isinstance(it, str):
+                if it == FAKE_VIDEO_END_TOKEN:
+                    in_video = False
+                    continue
+                in_video = in_video or it == DEFAULT_VIDEO_TOKEN
+                yield "text", it
+            else:
+                yield ("video" if in_video else "image"), it
+
+    def _stack(self, pictures, device, dtype):
+        if not pictures:
+            return None
+        return torch.stack([self.transform(p, device) for p in pictures]).to(device=device, dtype=dtype)
+
     def _prepare_inputs(self, inputs, device=torch.device("cpu"), dtype=torch.float32,
                         image_placeholder: str = DEFAULT_IMG_PLACEHOLDER, video_placeholder: str = DEFAULT_VID_PLACEHOLDER):
-        is_video = False
-        text_prompt, image_prompt, video_prompt = "", [], []
-        for x in inputs:
-            if isinstance(x, str) and x == FAKE_VIDEO_END_TOKEN:
-                is_video = False
-            elif isinstance(x, str):
-                if x == DEFAULT_VIDEO_TOKEN:
-                    is_video = True
-                text_prompt += x
-            elif is_video:
-                text_prompt += video_placeholder
-                video_prompt.append(self.transform(x, device))
+        pieces, pictures = [], {"image": [], "video": []}
+        slot = {"image": image_placeholder, "video": video_placeholder}
+        for kind, value in self._segments(inputs):
+            if kind == "text":
+                pieces.append(value)
             else:
-                text_prompt += image_placeholder
-                image_prompt.append(self.transform(x, device))
-        image_prompt = torch.stack(image_prompt).to(device=device, dtype=dtype) if image_prompt else None
-        video_prompt = torch.stack(video_prompt).to(device=device, dtype=dtype) if video_prompt else None
-        return [text_prompt], image_prompt, video_prompt, image_placeholder, video_placeholder
+                pieces.append(slot[kind])
+                pictures[kind].append(value)
+        return (["".join(pieces)], self._stack(pictures["image"], device, dtype),
+                self._stack(pictures["video"], device, dtype), image_placeholder, video_placeholder)
 
-    # ---- Emu2/emu/chat.py:159-195 ----
     def _prepare_chat_inputs(self, inputs, is_grounding: bool = False, device=torch.device("cpu"), dtype=torch.float32,
                              image_placeholder: str = DEFAULT_IMG_PLACEHOLDER,
                              video_placeholder: str = DEFAULT_VID_PLACEHOLDER):
-        text_prompt = GROUND_SYSTEM_MESSAGE if is_grounding else SYSTEM_MESSAGE
-        image_prompt, video_prompt = None, None
-        prev_r = None
-        for msg in inputs:
-            if prev_r == ASSISTANT_TOKEN:
-                text_prompt += f"{DEFAULT_EOS_TOKEN}{USER_TOKEN}: "
-                prev_r = USER_TOKEN
-            elif prev_r is None:
-                text_prompt += f" {USER_TOKEN}: "
-                prev_r = USER_TOKEN
+        """Turns alternate USER / ASSISTANT starting with USER; an assistant turn is closed with </s> before the next
+        user turn; the prompt ends with an open assistant turn (plus <grounding> when asked for)."""
+        parts = [GROUND_SYSTEM_MESSAGE if is_grounding else SYSTEM_MESSAGE]
+        images, videos = [], []
+        for turn, msg in enumerate(inputs):
+            if turn % 2 == 1:
+                parts.append(" %s: " % ASSISTANT_TOKEN)
             else:
-                text_prompt += f" {ASSISTANT_TOKEN}: "
-                prev_r = ASSISTANT_TOKEN
+                parts.append((" " if turn == 0 else DEFAULT_EOS_TOKEN) + "%s: " % USER_TOKEN)
             text, image, video, _, _ = self._prepare_inputs(msg, device, dtype, image_placeholder, video_placeholder)
-            text_prompt += text[0]
+            parts.append(text[0])
             if image is not None:
-                image_prompt = image if image_prompt is None else torch.cat([image_prompt, image])
+                images.append(image)
             if video is not None:
-                video_prompt = video if video_prompt is None else torch.cat([video_prompt, video])
-        text_prompt += f" {ASSISTANT_TOKEN}:"
-        if is_grounding:
-            text_prompt += GRD_SYMBOL
-        return [text_prompt], image_prompt, video_prompt, image_placeholder, video_placeholder
+                videos.append(video)
+        parts.append(" %s:" % ASSISTANT_TOKEN + (GRD_SYMBOL if is_grounding else ""))
+        return (["".join(parts)], torch.cat(images) if images else None, torch.cat(videos) if videos else None,
+                image_placeholder, video_placeholder)
 
     # ---- Emu2/emu/chat.py:197-232 ----
     @classmethod
