@@ -62,6 +62,7 @@ SYMBOLS = [
     "emu_project", "emu_cformer_forward", "emu_unet_configure", "emu_unet_forward", "emu_denoise_step",
     "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
     "emu_op_attn_prefill", "emu_op_attn_decode", "emu_op_rmsnorm", "emu_op_layernorm", "emu_launch_count",
+    "emu_debug_gemm_phases",
     "emu_version",
 ]
 
@@ -280,6 +281,21 @@ def op_gemm(A, W, bias=None, residual=None, epi=EPI_NONE, out_fp32=False, force_
                          1 if out_fp32 else 0, force_bn, _stream())
     check(rc)
     return Cm
+
+
+def debug_gemm_phases(A, W, bias=None, residual=None, epi=EPI_NONE, force_bn=0):
+    """emu_op_gemm + per-CTA phase stamps -> (C, stamps [148, 8] int64 on the host)"""
+    require_cuda()
+    lib = load()
+    M, K = A.shape
+    N = W.shape[0]
+    n_out = N // 2 if epi in (EPI_SWIGLU, EPI_GEGLU) else N
+    Cm = torch.empty(M, n_out, dtype=torch.bfloat16, device=A.device)
+    stamps = torch.zeros(148, 8, dtype=torch.int64, device=A.device)
+    check(lib.emu_debug_gemm_phases(_ptr(A), A.stride(0), _ptr(W), W.stride(0), M, N, K, _ptr(bias), _ptr(residual),
+                                    residual.stride(0) if residual is not None else 0, epi, _ptr(Cm), n_out, force_bn,
+                                    _ptr(stamps), _stream()))
+    return Cm, stamps.cpu()
 
 
 def op_conv3x3(x_nhwc, w_k, bias=None, residual=None):

@@ -6,13 +6,18 @@
 // the mma.sync kernel in attention.cu, which stays the path for additive-bias (T5) and tiny problems.
 //
 // One CTA = 256 query rows (two 128-row tiles) of one (batch, head); K/V blocks stream through a 3-stage TMA ring and
-// are shared by both tiles (halves L2->SMEM traffic per flop).  Warp roles (320 threads):
+// are shared by both tiles (halves L2->SMEM traffic per flop).  Warp roles (384 threads = 3 warpgroups):
 //   warp 0      TMA producer: Q once, then K_j / V_j tiles (4-D tensor maps over the strided [B, N, H, D] views, 128B
 //               swizzle, out-of-bounds rows / head-dim padding arrive as zeros)
 //   warp 1      single-thread tcgen05.mma issuer: S_t = Q_t K_j^T (both operands K-major) and O_t += P_t V_j (V is used
 //               in place as an MN-major B operand — no transpose pass), accumulators in TMEM
-//   warps 2-5   softmax for tile 0, warps 6-9 for tile 1: thread == query row (TMEM lane); S row -> registers, online
+//   warps 2-3   idle (they complete warpgroup 0 so that it can hand its registers over with setmaxnreg)
+//   warps 4-7   softmax for tile 0, warps 8-11 for tile 1: thread == query row (TMEM lane); S row -> registers, online
 //               max/sum, P (bf16) written to swizzled SMEM as the A operand of the second MMA.
+// Warpgroup 0 shrinks to 64 registers per thread and the two softmax warpgroups grow to 224 (setmaxnreg), so the 128
+// scores of a row live in registers without spills.  The softmax inner loop is written for issue slots, the scarce
+// resource of a lone warp per scheduler: packed f32x2 FMA / ADD (one instruction per two scores), 3-input max, one
+// 16-byte st.shared per 8 probabilities (conflict-free under the 128B swizzle).
 // O accumulates in TMEM across KV blocks.  The running max used for the exponent is only advanced when it grew by more
 // than 2^8 (exact: the final 1/l normalisation uses the same stale max), so the O rescale (TMEM ld/st) is rare.
 // While tile 0's softmax runs, the tensor core works on tile 1 and vice versa.
@@ -33,14 +38,9 @@ namespace {
 
 constexpr int kAtStages = 3;
 
-// SW = softmax warps per (query tile, TMEM lane quarter): 1 -> thread == whole row; 2 -> two warps split the row's key
-// columns (and O columns) and exchange max / sum through shared memory — twice the warps to hide latency with
-template <int DT, int BN, int SW>
+template <int DT, int BN>
 struct AtCfg {
-  static constexpr int kThreads = 64 + 2 * 4 * SW * 32;
-  static constexpr int kCW = BN / SW;              // S columns per softmax warp
-  static constexpr int kOW = DT / SW;              // O columns per softmax warp
-  static_assert(kCW % 32 == 0 && kOW % 32 == 0, "per-warp column slices are moved in 32-column TMEM chunks");
+  static constexpr int kThreads = 384;             // warpgroup 0 = {TMA, MMA, 2 idle}, warpgroups 1/2 = softmax of tile 0/1
   static constexpr int kDC = DT / 64;              // 64-wide head-dim chunks (one 128 B swizzle row each)
   static constexpr int kKC = BN / 64;              // 64-wide key chunks of P
   static constexpr int kQBytes = 128 * DT * 2;     // one Q tile
@@ -50,11 +50,11 @@ struct AtCfg {
   static constexpr int kOffV = kOffK + kAtStages * kKVBytes;
   static constexpr int kOffP = kOffV + kAtStages * kKVBytes;
   static constexpr int kOffBar = kOffP + 2 * kPBytes;
-  static constexpr int kOffX = kOffBar + 32 * 8;         // [2 parities][2 tiles][SW][128] fp32 max exchange, then sums
-  static constexpr int kSmem = kOffX + 2 * 2 * 2 * 128 * 4 + 1024;  // + 1024 B alignment slack
+  static constexpr int kSmem = kOffBar + 32 * 8 + 1024;  // + 1024 B alignment slack
   static constexpr int kTmemS = 0;                 // S_t at t*BN
   static constexpr int kTmemO = 2 * BN;            // O_t at 2*BN + t*DT
   static constexpr int kTmemCols = 512;
+  static_assert(BN % 32 == 0 && DT % 32 == 0, "rows are moved in 32-column TMEM chunks");
   static_assert(2 * BN + 2 * DT <= 512, "TMEM budget");
   static_assert(kSmem <= 227 * 1024, "SMEM budget");
 };
@@ -104,15 +104,55 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 // (Tried and removed: FlashAttention-4's trick of evaluating a share of the exponentials with a polynomial on the FMA
-//  pipe.  ncu shows the XU pipe — ex2 + bf16 packing — as the busiest pipe of this kernel at 58 %, but the softmax warps
-//  are instruction-issue bound: every share of polynomial exp2 made the kernel slower, 457 -> 332/246/192 TFLOP/s at
-//  0/25/50 % on the 4096-token head-dim-64 shape, the 0 % figure being the cost of merely carrying the runtime switch.)
+//  pipe — slower at every share in round 1, when the softmax warps were instruction-issue bound (729 issue slots per
+//  128-key block and row: 32-bit generic P stores, scalar FMA / ADD, spills under the 168-register cap).  Also removed:
+//  splitting each row over two softmax warps (330 vs 478 TFLOP/s).)
 
-template <int DT, int BN, int SW>
-__global__ void __launch_bounds__(AtCfg<DT, BN, SW>::kThreads, 1)
+// packed fp32 pairs: one issue slot for two scores (Blackwell FFMA2 / FADD2)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+template <int DT, int BN>
+__global__ void __launch_bounds__(AtCfg<DT, BN>::kThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AtParams p) {
-  using C = AtCfg<DT, BN, SW>;
+  using C = AtCfg<DT, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
@@ -132,22 +172,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int off = p.Nk - p.Nq;
 
   // KV blocks needed per 128-row tile (0 when the tile lies entirely past Nq)
-  int nb[2];
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int qlo = q0 + t * 128;
-    if (qlo >= p.Nq) {
-      nb[t] = 0;
-    } else {
-      int kmax = p.Nk - 1;
-      if (p.causal) {
-        const int qhi = min(qlo + 127, p.Nq - 1);
-        kmax = min(kmax, qhi + off);
-      }
-      nb[t] = kmax < 0 ? 0 : kmax / BN + 1;
-    }
-  }
-  const int nbmax = max(nb[0], nb[1]);
+  auto blocks_for = [&](int qlo) -> int {
+    if (qlo >= p.Nq) return 0;
+    int kmax = p.Nk - 1;
+    if (p.causal) kmax = min(kmax, min(qlo + 127, p.Nq - 1) + off);
+    return kmax < 0 ? 0 : kmax / BN + 1;
+  };
+  const int nb0 = blocks_for(q0), nb1 = blocks_for(q0 + 128);
+  const int nbmax = max(nb0, nb1);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -162,8 +194,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&s_free[t], 4 * SW);
-      mbar_init(&p_ready[t], 4 * SW);
+      mbar_init(&s_free[t], 4);
+      mbar_init(&p_ready[t], 4);
       mbar_init(&o_done[t], 1);
     }
     mbar_fence_init();
@@ -175,159 +207,166 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0 && nbmax > 0) {
-      if (p.pdl) pdl_wait();  // Q/K/V are the predecessor's output; all stores of this kernel happen after these loads
-      mbar_expect_tx(q_full, 2 * C::kQBytes);
-      for (int t = 0; t < 2; ++t)
-        for (int c = 0; c < C::kDC; ++c)
-          load_rows(smem + t * C::kQBytes + c * (128 * 128), &tmQ, q_full, c * 64, q0 + t * 128, head, batch, p.q_hf);
-      for (int j = 0; j < nbmax; ++j) {
-        const int s = j % kAtStages;
-        const uint32_t ph = (uint32_t)(j / kAtStages) & 1u;
-        mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_expect_tx(&k_full[s], C::kKVBytes);
-        for (int c = 0; c < C::kDC; ++c)
-          load_rows(smem + C::kOffK + s * C::kKVBytes + c * (BN * 128), &tmK, &k_full[s], c * 64, j * BN, head, batch, p.k_hf);
-        mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_expect_tx(&v_full[s], C::kKVBytes);
-        for (int c = 0; c < C::kDC; ++c)
-          load_rows(smem + C::kOffV + s * C::kKVBytes + c * (BN * 128), &tmV, &v_full[s], c * 64, j * BN, head, batch, p.v_hf);
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0 && nbmax > 0) {
+        if (p.pdl) pdl_wait();  // Q/K/V are the predecessor's output; all stores of this kernel happen after these loads
+        mbar_expect_tx(q_full, 2 * C::kQBytes);
+        for (int t = 0; t < 2; ++t)
+          for (int c = 0; c < C::kDC; ++c)
+            load_rows(smem + t * C::kQBytes + c * (128 * 128), &tmQ, q_full, c * 64, q0 + t * 128, head, batch, p.q_hf);
+        for (int j = 0; j < nbmax; ++j) {
+          const int s = j % kAtStages;
+          const uint32_t ph = (uint32_t)(j / kAtStages) & 1u;
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_expect_tx(&k_full[s], C::kKVBytes);
+          for (int c = 0; c < C::kDC; ++c)
+            load_rows(smem + C::kOffK + s * C::kKVBytes + c * (BN * 128), &tmK, &k_full[s], c * 64, j * BN, head, batch, p.k_hf);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_expect_tx(&v_full[s], C::kKVBytes);
+          for (int c = 0; c < C::kDC; ++c)
+            load_rows(smem + C::kOffV + s * C::kKVBytes + c * (BN * 128), &tmV, &v_full[s], c * 64, j * BN, head, batch, p.v_hf);
+        }
       }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && nbmax > 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, DT) | (1u << 16);  // B (= V) is MN-major
-      const uint32_t sQ = smem_u32(smem), sK = smem_u32(smem + C::kOffK), sV = smem_u32(smem + C::kOffV),
-                     sP = smem_u32(smem + C::kOffP);
-      auto issue_S = [&](int t, int stage) {
-        const uint32_t d = tmem_base + C::kTmemS + t * BN;
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0 && nbmax > 0) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, DT) | (1u << 16);  // B (= V) is MN-major
+        const uint32_t sQ = smem_u32(smem), sK = smem_u32(smem + C::kOffK), sV = smem_u32(smem + C::kOffV),
+                       sP = smem_u32(smem + C::kOffP);
+        auto issue_S = [&](int t, int stage) {
+          const uint32_t d = tmem_base + C::kTmemS + t * BN;
 #pragma unroll
-        for (int c = 0; c < C::kDC; ++c) {
-          const uint64_t da = umma_desc_sw128(sQ + t * C::kQBytes + c * (128 * 128));
-          const uint64_t db = umma_desc_sw128(sK + stage * C::kKVBytes + c * (BN * 128));
+          for (int c = 0; c < C::kDC; ++c) {
+            const uint64_t da = umma_desc_sw128(sQ + t * C::kQBytes + c * (128 * 128));
+            const uint64_t db = umma_desc_sw128(sK + stage * C::kKVBytes + c * (BN * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d, da + 2 * k, db + 2 * k, idesc_s, (c | k) != 0);
-        }
-      };
-      auto issue_PV = [&](int t, int stage, bool acc) {
-        const uint32_t d = tmem_base + C::kTmemO + t * DT;
+            for (int k = 0; k < 4; ++k) umma_bf16(d, da + 2 * k, db + 2 * k, idesc_s, (c | k) != 0);
+          }
+        };
+        auto issue_PV = [&](int t, int stage, bool acc) {
+          const uint32_t d = tmem_base + C::kTmemO + t * DT;
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {
-          const uint64_t da = umma_desc_sw128(sP + t * C::kPBytes + (kk >> 2) * (128 * 128)) + 2 * (kk & 3);
-          // V block in place: rows = keys (the MMA K dim), 64-wide d chunks BN*128 B apart (LBO), 8-key groups 1024 B (SBO)
-          const uint64_t db = umma_desc_sw128_ex(sV + stage * C::kKVBytes + kk * 2048, BN * 128, 1024);
-          umma_bf16(d, da, db, idesc_o, (acc || kk > 0) ? 1u : 0u);
-        }
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      for (int t = 0; t < 2; ++t)
-        if (nb[t] > 0) {
-          issue_S(t, 0);
-          umma_commit(&s_full[t]);
-        }
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < nbmax; ++j) {
-        const int sv = j % kAtStages;
-        const uint32_t phv = (uint32_t)(j / kAtStages) & 1u;
-        const bool has_next = j + 1 < nbmax;
-        const int sk = (j + 1) % kAtStages;
-        const uint32_t phk = (uint32_t)((j + 1) / kAtStages) & 1u;
-        if (has_next) mbar_wait(&k_full[sk], phk);
-        mbar_wait(&v_full[sv], phv);
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            const uint64_t da = umma_desc_sw128(sP + t * C::kPBytes + (kk >> 2) * (128 * 128)) + 2 * (kk & 3);
+            // V block in place: rows = keys (the MMA K dim), 64-wide d chunks BN*128 B apart (LBO), 8-key groups 1024 B (SBO)
+            const uint64_t db = umma_desc_sw128_ex(sV + stage * C::kKVBytes + kk * 2048, BN * 128, 1024);
+            umma_bf16(d, da, db, idesc_o, (acc || kk > 0) ? 1u : 0u);
+          }
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(&k_full[0], 0);
         tc_fence_after();
-        for (int t = 0; t < 2; ++t) {
-          if (j + 1 < nb[t]) {
-            mbar_wait(&s_free[t], (uint32_t)j & 1u);
-            tc_fence_after();
-            issue_S(t, sk);
-            umma_commit(&s_full[t]);
+        if (nb0 > 0) { issue_S(0, 0); umma_commit(&s_full[0]); }
+        if (nb1 > 0) { issue_S(1, 0); umma_commit(&s_full[1]); }
+        umma_commit(&k_empty[0]);
+        for (int j = 0; j < nbmax; ++j) {
+          const int sv = j % kAtStages;
+          const uint32_t phv = (uint32_t)(j / kAtStages) & 1u;
+          const bool has_next = j + 1 < nbmax;
+          const int sk = (j + 1) % kAtStages;
+          const uint32_t phk = (uint32_t)((j + 1) / kAtStages) & 1u;
+          if (has_next) mbar_wait(&k_full[sk], phk);
+          mbar_wait(&v_full[sv], phv);
+          tc_fence_after();
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int nbt = t ? nb1 : nb0;
+            if (j + 1 < nbt) {
+              mbar_wait(&s_free[t], (uint32_t)j & 1u);
+              tc_fence_after();
+              issue_S(t, sk);
+              umma_commit(&s_full[t]);
+            }
+            if (j < nbt) {
+              mbar_wait(&p_ready[t], (uint32_t)j & 1u);
+              tc_fence_after();
+              issue_PV(t, sv, j > 0);
+              umma_commit(&o_done[t]);
+            }
           }
-          if (j < nb[t]) {
-            mbar_wait(&p_ready[t], (uint32_t)j & 1u);
-            tc_fence_after();
-            issue_PV(t, sv, j > 0);
-            umma_commit(&o_done[t]);
-          }
+          if (has_next) umma_commit(&k_empty[sk]);
+          umma_commit(&v_empty[sv]);
         }
-        if (has_next) umma_commit(&k_empty[sk]);
-        umma_commit(&v_empty[sv]);
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue warps =====================
-    constexpr int CW = C::kCW, OW = C::kOW;
-    const int sw = warp - 2;
-    const int t = sw / (4 * SW);
-    const int half = (sw % (4 * SW)) >> 2;  // which column slice of the row this warp owns (0 when SW == 1)
-    const int quad = warp & 3;              // TMEM lane quarter this warp may access
+    // ===================== softmax / correction / epilogue warpgroups =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int t = (warp - 4) >> 2;  // query tile of this warpgroup
+    const int quad = warp & 3;      // TMEM lane quarter this warp may access
     const int r = quad * 32 + lane;
     const int qi = q0 + t * 128 + r;
-    const int cbase = half * CW;            // first S column / key of this warp inside a KV block
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t tS = lane_base + C::kTmemS + t * BN + cbase;
-    const uint32_t tO = lane_base + C::kTmemO + t * DT + half * OW;
-    uint8_t* Pt = smem + C::kOffP + t * C::kPBytes + (r >> 3) * 1024 + (r & 7) * 128;
-    float* xch = reinterpret_cast<float*>(smem + C::kOffX);  // [parity][tile][slice][row]
-    const int pair_bar = 1 + t * 4 + quad;                   // named barrier shared by the SW warps of this (tile, quarter)
-    const int n = nb[t];
+    const uint32_t tS = lane_base + C::kTmemS + t * BN;
+    const uint32_t tO = lane_base + C::kTmemO + t * DT;
+    // this row inside the swizzled P tile: 8-row groups 1024 B apart, 128 B per row, 16 B chunk index ^ (row & 7)
+    const uint32_t Pt = smem_u32(smem + C::kOffP) + t * C::kPBytes + (r >> 3) * 1024 + (r & 7) * 128;
+    const uint32_t swz = (uint32_t)(r & 7) << 4;
+    const uint32_t b_s_full = smem_u32(&s_full[t]), b_s_free = smem_u32(&s_free[t]), b_p_ready = smem_u32(&p_ready[t]),
+                   b_o_done = smem_u32(&o_done[t]);
+    const int n = t ? nb1 : nb0;
     const float c = p.scale_log2;
+    const uint64_t c2 = pack2(c, c);
     const int lo = p.kv_start ? p.kv_start[batch] : 0;
     const int hi = p.causal ? min(p.Nk - 1, qi + off) : p.Nk - 1;
     float m_run = -INFINITY, m_used = -INFINITY;
-    float l8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < n; ++j) {
-      mbar_wait(&s_full[t], (uint32_t)j & 1u);
-      tc_fence_after();
-      float s[CW];
+    uint64_t l2[4];  // 8 independent row-sum chains, packed in pairs
 #pragma unroll
-      for (int cc = 0; cc < CW / 32; ++cc) tmem_ld_32x32(tS + cc * 32, reinterpret_cast<uint32_t*>(s) + cc * 32);
+    for (int i = 0; i < 4; ++i) l2[i] = 0ull;
+    for (int j = 0; j < n; ++j) {
+      mbar_wait_s(b_s_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      float s[BN];
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) tmem_ld_32x32(tS + cc * 32, reinterpret_cast<uint32_t*>(s) + cc * 32);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[t]);
-      const int k0 = j * BN + cbase;
-      if (k0 < lo || k0 + CW - 1 > hi) {
+      if (lane == 0) mbar_arrive_s(b_s_free);
+      const int k0 = j * BN;
+      if (k0 < lo || k0 + BN - 1 > hi) {
 #pragma unroll
-        for (int i = 0; i < CW; ++i) s[i] = (k0 + i < lo || k0 + i > hi) ? -INFINITY : s[i];
+        for (int i = 0; i < BN; ++i) s[i] = (k0 + i < lo || k0 + i > hi) ? -INFINITY : s[i];
       }
-      // 8 independent max chains (a single long dependent chain is pure latency for a lone warp per sub-partition)
+      // 8 independent max chains (a single long dependent chain is pure latency for a lone warp per sub-partition);
+      // fmaxf(fmaxf(a, b), c) folds into one 3-input FMNMX3
       float mx8[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mx8[i] = s[i];
+      for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(s[i], s[i + 8]);
 #pragma unroll
-      for (int i = 8; i < CW; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], s[i]);
-      float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-      if (SW > 1) {
-        // combine the row maximum of the column slices (slots alternate with j so one barrier per block suffices)
-        float* slot = xch + (((j & 1) * 2 + t) * 2) * 128;
-        slot[half * 128 + r] = mx;
-        asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "r"(32 * SW) : "memory");
-        mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
+      for (int i = 16; i + 8 < BN; i += 16) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mx8[u] = fmaxf(fmaxf(mx8[u], s[i + u]), s[i + 8 + u]);
       }
+      if ((BN / 8) & 1) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mx8[u] = fmaxf(mx8[u], s[BN - 8 + u]);
+      }
+      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       const float m_new = fmaxf(m_run, mx);
       m_run = m_new;
       if (j > 0) {
-        mbar_wait(&o_done[t], (uint32_t)(j - 1) & 1u);  // PV_{j-1} retired: O is quiescent and P may be overwritten
+        mbar_wait_s(b_o_done, (uint32_t)(j - 1) & 1u);  // PV_{j-1} retired: O is quiescent and P may be overwritten
         tc_fence_after();
       }
       const bool need = (m_new - m_used) * c > 8.f;
-      if (__any_sync(0xffffffffu, need)) {  // identical in every warp that shares these rows (same m_new, m_used)
+      if (__any_sync(0xffffffffu, need)) {
         float f = 1.f;
         if (m_new != -INFINITY) {
           f = (m_used == -INFINITY) ? 0.f : ex2_approx((m_used - m_new) * c);
           m_used = m_new;
         }
+        const uint64_t f2 = pack2(f, f);
+        const uint64_t z2 = 0ull;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) l8[i] *= f;
+        for (int i = 0; i < 4; ++i) l2[i] = ffma2(l2[i], f2, z2);
         if (j > 0) {
 #pragma unroll 1
-          for (int cc = 0; cc < OW / 32; ++cc) {
+          for (int cc = 0; cc < DT / 32; ++cc) {
             uint32_t v[32];
             tmem_ld_32x32(tO + cc * 32, v);
             tmem_ld_wait();
@@ -339,40 +378,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
       const float mu = (m_used == -INFINITY) ? 0.f : m_used * c;
+      const uint64_t nmu2 = pack2(-mu, -mu);
 #pragma unroll
-      for (int g = 0; g < CW / 8; ++g) {
-        const int kk = cbase + g * 8;          // key index inside the block
-        const int kc = kk >> 6, pc = (kk >> 3) & 7;
+      for (int g = 0; g < BN / 8; ++g) {
         float e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          e[i] = ex2_approx(fmaf(s[g * 8 + i], c, -mu));
-          l8[i] += e[i];  // 8 independent row-sum chains
+        for (int i = 0; i < 4; ++i) {
+          float x0, x1;
+          unpack2(ffma2(pack2(s[g * 8 + 2 * i], s[g * 8 + 2 * i + 1]), c2, nmu2), x0, x1);
+          e[2 * i] = ex2_approx(x0);
+          e[2 * i + 1] = ex2_approx(x1);
+          l2[i] = fadd2(l2[i], pack2(e[2 * i], e[2 * i + 1]));
         }
-        uint4 w;
-        w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]); w.z = pack_bf16(e[4], e[5]); w.w = pack_bf16(e[6], e[7]);
-        *reinterpret_cast<uint4*>(Pt + kc * (128 * 128) + ((pc ^ (r & 7)) << 4)) = w;
+        // keys g*8 .. g*8+7 of this row: 64-key chunk g >> 3 (16 KB apart), 16-byte slot (g & 7) ^ (row & 7)
+        sts128(Pt + (g >> 3) * (128 * 128) + ((((uint32_t)g & 7u) << 4) ^ swz), pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]),
+               pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
       }
       fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core's async-proxy reads
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[t]);
+      if (lane == 0) mbar_arrive_s(b_p_ready);
     }
     if (n > 0) {
-      float l = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
-      if (SW > 1) {
-        // row sum = sum over the column slices, added in slice order so both warps get the same bits
-        float* slot = xch + (((n & 1) * 2 + t) * 2) * 128;
-        slot[half * 128 + r] = l;
-        asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "r"(32 * SW) : "memory");
-        l = slot[r] + slot[128 + r];
-      }
-      mbar_wait(&o_done[t], (uint32_t)(n - 1) & 1u);
+      float la[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) unpack2(l2[i], la[2 * i], la[2 * i + 1]);
+      const float l = ((la[0] + la[1]) + (la[2] + la[3])) + ((la[4] + la[5]) + (la[6] + la[7]));
+      mbar_wait_s(b_o_done, (uint32_t)(n - 1) & 1u);
       tc_fence_after();
       const float inv = l > 0.f ? 1.f / l : 0.f;
-      bf16* dst = p.out + (long)batch * p.o_bs + (long)qi * p.o_ts + (long)head * p.o_hs + half * OW;
+      bf16* dst = p.out + (long)batch * p.o_bs + (long)qi * p.o_ts + (long)head * p.o_hs;
 #pragma unroll 1
-      for (int cc = 0; cc < OW / 32; ++cc) {
+      for (int cc = 0; cc < DT / 32; ++cc) {
         uint32_t v[32];
         tmem_ld_32x32(tO + cc * 32, v);
         tmem_ld_wait();
@@ -380,7 +417,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = cc * 32 + g * 8;
-            if (half * OW + col < p.D) {  // D % 8 == 0
+            if (col < p.D) {  // D % 8 == 0
               uint4 w;
               w.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
               w.y = pack_bf16(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
@@ -402,12 +439,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-template <int DT, int BN, int SW>
+template <int DT, int BN>
 int launch_attn_tc(const AttnArgs& a, cudaStream_t st) {
-  using C = AtCfg<DT, BN, SW>;
+  using C = AtCfg<DT, BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_tc_kernel<DT, BN, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_tc_kernel<DT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) != cudaSuccess)
       return EMU_ERR_CUDA;
     attr_set = true;
   }
@@ -421,7 +458,7 @@ int launch_attn_tc(const AttnArgs& a, cudaStream_t st) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.pdl = g_pdl_chain;
   dim3 grid((a.Nq + 255) / 256, a.H, a.B);
-  return launch_kernel(attn_tc_kernel<DT, BN, SW>, grid, dim3(C::kThreads), C::kSmem, st, p.pdl, tq, tk, tv, p);
+  return launch_kernel(attn_tc_kernel<DT, BN>, grid, dim3(C::kThreads), C::kSmem, st, p.pdl, tq, tk, tv, p);
 }
 
 }  // namespace
@@ -435,16 +472,11 @@ int attn_prefill_tc(const AttnArgs& a, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(a.q) & 15) || (reinterpret_cast<uintptr_t>(a.k) & 15) || (reinterpret_cast<uintptr_t>(a.v) & 15))
     return EMU_ERR_UNSUPPORTED;
   if (a.H > 65535 || a.B > 65535) return EMU_ERR_UNSUPPORTED;
-  static int sw = -1;
-  if (sw < 0) {
-    const char* v = getenv("EMU_ATTN_SW");
-    sw = (v && atoi(v) == 2) ? 2 : 1;  // 2 = split every row over two softmax warps (opt-in until measured)
-  }
   if (a.D <= 64) {
-    if (a.Nk <= 64) return sw == 2 ? launch_attn_tc<64, 64, 2>(a, st) : launch_attn_tc<64, 64, 1>(a, st);  // cross-attn: 64 keys
-    return sw == 2 ? launch_attn_tc<64, 128, 2>(a, st) : launch_attn_tc<64, 128, 1>(a, st);
+    if (a.Nk <= 64) return launch_attn_tc<64, 64>(a, st);  // cross-attention: 64 keys
+    return launch_attn_tc<64, 128>(a, st);
   }
-  return sw == 2 ? launch_attn_tc<128, 64, 2>(a, st) : launch_attn_tc<128, 64, 1>(a, st);
+  return launch_attn_tc<128, 64>(a, st);
 }
 
 }  // namespace emu

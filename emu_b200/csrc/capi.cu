@@ -16,6 +16,17 @@ extern "C" int emu_op_gemm(const void* A, int lda, const void* W, int ldw, int M
   return gemm_bf16((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, e, (cudaStream_t)s);
 }
 
+extern "C" int emu_debug_gemm_phases(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const void* bias,
+                                     const void* residual, int ldr, int epi_mode, void* C, int ldc, int force_bn,
+                                     unsigned long long* stamps /*[148][8] device*/, emu_stream_t s) {
+  if (!A || !W || !C || !stamps) return EMU_ERR_INVALID;
+  GemmEpilogue e;
+  e.C = C; e.ldc = ldc; e.bias = (const bf16*)bias; e.residual = (const bf16*)residual; e.ldr = ldr;
+  e.mode = epi_mode; e.force_bn = force_bn; e.dbg = stamps;
+  count_launch();
+  return gemm_bf16((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, e, (cudaStream_t)s);
+}
+
 extern "C" int emu_op_conv3x3(const void* x, int NB, int H, int W, int Cin, const void* wk, int Cout, const void* bias,
                               const void* residual, void* y, emu_stream_t s) {
   if (!x || !wk || !y) return EMU_ERR_INVALID;

@@ -54,7 +54,21 @@ struct GemmParams {
   int conv;        // 0 = plain 2-D A, 1 = 3x3 conv (pad 1), 2 = 3x3 conv stride 2 is NOT handled here
   int H, W, Cin, tw, th;
   int pdl;  // launched with programmatic dependent launch: griddepcontrol.wait before touching activations
+  // diagnostics (emu_debug_gemm_phases): when non-null, every CTA writes 8 x u64 = {globaltimer at entry, clock64 at entry,
+  // after set-up, first TMA issued, first stage landed (MMA side), last MMA committed, epilogue released by the MMAs,
+  // epilogue done} for its FIRST tile
+  unsigned long long* dbg;
 };
+__device__ __forceinline__ unsigned long long clk64() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // CL = thread-block cluster size along M (1 or 2).  With CL == 2 the two CTAs of a cluster work on vertically adjacent
 // output tiles (same weight columns): each loads HALF of the W tile and TMA-multicasts it into both CTAs' shared memory,
@@ -88,6 +102,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kblocks_per_tap = p.conv ? (p.Cin + BK - 1) / BK : (p.K + BK - 1) / BK;
   const int num_kb = p.conv ? 9 * kblocks_per_tap : kblocks_per_tap;
 
+  unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) { dbg[0] = gtimer(); dbg[1] = clk64(); }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -108,11 +124,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (dbg && threadIdx.x == 0) dbg[2] = clk64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       if (p.pdl) pdl_wait();  // activations (A) come from the predecessor; everything above overlapped its tail
+      if (dbg) dbg[3] = clk64();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_step) {
@@ -166,6 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (dbg && kb == 0 && tile == unit0) dbg[4] = clk64();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint32_t sb = sa + BM * BK * 2;
           const uint64_t da = umma_desc_sw128(sa);
@@ -182,6 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        if (dbg && tile == unit0) dbg[5] = clk64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -234,6 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       prefetch(half);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (dbg && tile == unit0 && threadIdx.x == 64) dbg[6] = clk64();
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         uint32_t v[32];
@@ -365,6 +386,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (dbg && tile == unit0 && threadIdx.x == 64) dbg[7] = clk64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -573,7 +595,7 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
   p.M = M; p.N = N; p.K = K;
   p.C = e.C; p.ldc = e.ldc; p.bias = e.bias; p.residual = e.residual; p.ldr = e.ldr;
   p.bias2 = e.bias2; p.bias2_rows = e.bias2_rows > 0 ? e.bias2_rows : 1;
-  p.epi = e.mode; p.out_fp32 = e.out_fp32; p.conv = 0; p.pdl = g_pdl_chain;
+  p.epi = e.mode; p.out_fp32 = e.out_fp32; p.conv = 0; p.pdl = g_pdl_chain; p.dbg = e.dbg;
   const int bn = (e.force_bn & 1023) ? (e.force_bn & 1023) : pick_bn(M, N);
   const bool cl = use_cluster(M, e.force_bn, false);
   CUtensorMap tmA, tmB;
@@ -599,7 +621,7 @@ int conv3x3_bf16(const bf16* X, int NB, int H, int W, int Cin, const bf16* Wk, i
   p.M = NB * H * W; p.N = Cout; p.K = 9 * Cin;
   p.C = e.C; p.ldc = e.ldc; p.bias = e.bias; p.residual = e.residual; p.ldr = e.ldr;
   p.bias2 = e.bias2; p.bias2_rows = e.bias2_rows > 0 ? e.bias2_rows : 1;
-  p.epi = e.mode; p.out_fp32 = e.out_fp32; p.pdl = g_pdl_chain;
+  p.epi = e.mode; p.out_fp32 = e.out_fp32; p.pdl = g_pdl_chain; p.dbg = e.dbg;
   p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tw = tw; p.th = th;
   const int bn = (e.force_bn & 1023) ? (e.force_bn & 1023) : pick_bn(p.M, Cout);
   const bool cl = use_cluster(p.M, e.force_bn, true);

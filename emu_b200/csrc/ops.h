@@ -28,6 +28,7 @@ struct GemmEpilogue {
   int mode = EPI_NONE;
   int out_fp32 = 0;
   int force_bn = 0;  // tests only: force the N tile (64/128/256)
+  unsigned long long* dbg = nullptr;  // diagnostics: per-CTA phase time stamps (emu_debug_gemm_phases)
 };
 
 // ---- gemm_tc.cu : tcgen05 GEMM / implicit-GEMM conv ----

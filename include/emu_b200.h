@@ -193,6 +193,14 @@ int emu_beam_topk(float* logits, const float* running_scores, int batch, int bea
 int emu_sample_tokens(const float* logits, int rows, int vocab, float temperature, int top_k, float top_p, int ban_id,
                       uint64_t seed, uint64_t offset, int32_t* out_ids, emu_stream_t s);
 
+/* Diagnostics: emu_op_gemm (bf16 output) with per-CTA phase time stamps.  stamps: DEVICE [148][8] uint64, per CTA
+ * {globaltimer ns at entry, then SM clock64 at: entry, set-up done, first TMA issued, first stage landed, last MMA committed,
+ * epilogue released, epilogue done} of the CTA's first tile.  tools/gemm_phases.py turns them into the phase table under
+ * profiles/. */
+int emu_debug_gemm_phases(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const void* bias,
+                          const void* residual, int ldr, int epi_mode, void* C, int ldc, int force_bn,
+                          unsigned long long* stamps, emu_stream_t s);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t emu_launch_count(void);
 const char* emu_version(void);

@@ -15,6 +15,32 @@ SHAPES = [  # name, B, N, H, D, causal
     ("llama33b prefill 4k causal", 1, 4096, 52, 128, True),
     ("llama33b prefill 1k causal", 1, 1024, 52, 128, True),
 ]
+CROSS = [  # name, B, Nq, Nk, H, D   (UNet cross-attention over the 64 regressed visual tokens)
+    ("unet_64x64 cross-attn 64 keys", 2, 4096, 64, 10, 64),
+    ("unet_32x32 cross-attn 64 keys", 2, 1024, 64, 20, 64),
+]
+
+
+def graph_us(fn, reps=20):
+    """launch-to-launch time inside a CUDA graph (no host launch overhead; inputs stay in L2 like inside the model)"""
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (5 * reps) * 1000.0
 
 
 def main():
@@ -34,8 +60,16 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         flops = 4.0 * B * H * N * N * D * (0.5 if causal else 1.0)
-        print("%-34s %8.3f ms  %7.1f TFLOP/s  [%s]" % (name, ms, flops / ms / 1e9, os.environ.get("EMU_ATTN", "tcgen05")),
-              flush=True)
+        out = torch.empty(B, N, H, D, dtype=torch.bfloat16, device="cuda")
+        us = graph_us(lambda: _lib.op_attn_prefill(q, k, v, D ** -0.5, causal=causal))
+        print("%-34s %8.3f ms  %7.1f TFLOP/s | in-graph %8.1f us %7.1f TFLOP/s  [%s]"
+              % (name, ms, flops / ms / 1e9, us, flops / us / 1e6, os.environ.get("EMU_ATTN", "tcgen05")), flush=True)
+    for name, B, Nq, Nk, H, D in CROSS:
+        q = (torch.randn(B, Nq, H, D, generator=g) * 0.5).to(torch.bfloat16).cuda()
+        kv = (torch.randn(B, Nk, 2, H, D, generator=g) * 0.5).to(torch.bfloat16).cuda()
+        us = graph_us(lambda: _lib.op_attn_prefill(q, kv[:, :, 0], kv[:, :, 1], D ** -0.5))
+        flops = 4.0 * B * H * Nq * Nk * D
+        print("%-34s in-graph %8.1f us %7.1f TFLOP/s" % (name, us, flops / us / 1e6), flush=True)
 
 
 if __name__ == "__main__":
