@@ -122,7 +122,20 @@ _CPU_SD_CACHE = {}
 
 
 _CPU_BEST_THREADS = None
-NCU_TRAFFIC_RATIO = (477.327 + 6.566) / 477.102  # profiles/r01_ncu_full_gemv_tma_gateup.txt
+
+
+def ncu_traffic():
+    """dram bytes / algorithmic bytes of the dominant kernel, from the ncu --set full capture committed this round
+    (profiles/r02_ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep of the gate/up GEMV launch)."""
+    for name in ("r02_ncu_traffic.json",):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            try:
+                d = json.load(open(p))
+                return float(d["dram_bytes_per_launch"]) / float(d["algorithmic_bytes_per_launch"]), "profiles/" + name
+            except Exception:
+                pass
+    return None, None
 
 
 def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, ctx=75, threads=None, budget_s=25.0):
@@ -312,15 +325,13 @@ def unet_param_shapes(cfg):
     return out
 
 
-def run_denoise(steps=50, warm_loops=1, timed_loops=1, batch=1, hw=128, seed=0, profile=False):
-    """50 Euler steps of the Emu2-Gen denoise loop (CFG, guidance 3, 1024x1024 -> latent 128x128) on random-init weights
-    of the published UNet topology; returns (steps_per_s, ms_per_step, launches_per_step)."""
+def make_unet_engine(tp_rank=0, tp_size=1, uid=None, seed=0):
+    """Engine holding only the Emu2-Gen UNet (random-init weights of the published topology, same seed on every rank)."""
     from emu_b200 import _lib
     from emu_b200.emu2.diffusion import unet_config_from_json
-    from emu_b200.emu2.scheduler import EulerDiscreteScheduler
     cfg = emu2_unet_json()
-    eng = _lib.Engine(_lib.EmuConfig())
-    eng.unet_configure(unet_config_from_json(cfg))
+    eng = _lib.Engine(_lib.EmuConfig(), tp_rank=tp_rank, tp_size=tp_size, nccl_uid=uid)
+    eng.unet_configure(unet_config_from_json(cfg))   # collective over the pair when tp_size == 2 (CFG-parallel exchange)
     g = torch.Generator(device="cuda").manual_seed(seed)
     for k, shp in unet_param_shapes(cfg):
         if k.endswith(".bias"):
@@ -334,6 +345,23 @@ def run_denoise(steps=50, warm_loops=1, timed_loops=1, batch=1, hw=128, seed=0, 
             t = (torch.randn(shp, generator=g, device="cuda", dtype=torch.float32) * (fan ** -0.5)).to(torch.bfloat16)
         eng.load_tensor("unet." + k, t)
         del t
+    return eng, cfg
+
+
+def run_denoise(steps=50, warm_loops=1, timed_loops=1, batch=1, hw=128, seed=0, profile=False, eng=None, sync=None,
+                latent_seed=0):
+    """50 Euler steps of the Emu2-Gen denoise loop (CFG, guidance 3, 1024x1024 -> latent 128x128) on random-init weights
+    of the published UNet topology; returns dict(steps_per_s, ms_per_step, launches_per_step, finite, sha1 of the latents).
+    `eng`: a UNet engine (possibly one half of a CFG-parallel pair); `sync`: barrier used around the timed region."""
+    import hashlib
+    from emu_b200 import _lib
+    from emu_b200.emu2.scheduler import EulerDiscreteScheduler
+    own = eng is None
+    if own:
+        eng, cfg = make_unet_engine(seed=seed)
+    else:
+        cfg = emu2_unet_json()
+    g = torch.Generator(device="cuda").manual_seed(1000 + latent_seed)
     sched = EulerDiscreteScheduler()
     sched.set_timesteps(steps)
     ts, sig = sched.timesteps, sched.sigmas
@@ -352,21 +380,26 @@ def run_denoise(steps=50, warm_loops=1, timed_loops=1, batch=1, hw=128, seed=0, 
         loop()
     l0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    (sync or torch.cuda.synchronize)()
     if profile:  # ncu --profile-from-start off: capture only the timed loop (tools/ncu_unet.py)
         torch.cuda.profiler.start()
     ev0.record()
     for _ in range(timed_loops):
         loop()
     ev1.record()
-    torch.cuda.synchronize()
+    (sync or torch.cuda.synchronize)()
     if profile:
         torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1) / (timed_loops * steps)
     launches = (_lib.launch_count() - l0) / (timed_loops * steps)
-    finite = bool(torch.isfinite(lat).all())
-    eng.close()
-    return 1000.0 / ms, ms, launches, finite
+    out = {"steps_per_s": 1000.0 / ms, "ms_per_step": ms, "launches_per_step": launches,
+           "finite": bool(torch.isfinite(lat).all()),
+           # correctness handle: the same seeds must give the same latents on 1 GPU and on a CFG-parallel pair (bitwise)
+           "latents_sha1": hashlib.sha1(lat.cpu().numpy().tobytes()).hexdigest()[:16],
+           "latents_abs_mean": float(lat.abs().mean())}
+    if own:
+        eng.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -464,11 +497,41 @@ def run_cuda(args):
     ms_e2e, _ = timed(False, args.steps)
     e2e = args.steps * NEW_TOKENS / (ms_e2e / 1000.0)
 
-    # decode-step timing for the roofline: events around each CUDA-graphed decode step of one more generate
+    # correctness handle of the timed run: the 128 greedy ids, hashed, so that the N = 1/2/4/8 lines of a scaling
+    # run can be compared; every tensor-parallel rank must hold the same ids (fixed-order reductions)
+    import hashlib
+    tok_cpu = toks.to(torch.int64).cpu().contiguous()
+    tokens_sha1 = hashlib.sha1(tok_cpu.numpy().tobytes()).hexdigest()[:16]
+    ranks_agree = True
+    if world > 1:
+        mine = torch.tensor([int(tokens_sha1, 16) >> 1], dtype=torch.int64, device="cuda")
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        ranks_agree = all(int(h.item()) == int(mine.item()) for h in allh)
+
+    # ViT and prefill times of the same request (reported separately from decode tok/s)
     eng = model.engine
+
+    def ev_ms(fn, reps=3):
+        fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, out
+    vit_ms, e = ev_ms(lambda: model.encode_image(image_dev))
     emb = eng.llm_embed(ids_dev)
-    e = model.encode_image(image_dev)
     emb[ids_dev == 32003] = model._project_up(e.reshape(-1, e.shape[-1]))
+
+    def prefill():
+        eng.llm_reset()
+        return eng.llm_prefill(emb, mask_dev, hf_positions=True, want_logits=True)
+    prefill_ms, _ = ev_ms(prefill)
+
+    # decode-step timing for the roofline: events around each CUDA-graphed decode step of one more generate
     eng.llm_reset()
     _, logits = eng.llm_prefill(emb, mask_dev, hf_positions=True, want_logits=True)
     ping = [logits.argmax(-1).to(torch.int32), torch.empty(1, dtype=torch.int32, device="cuda")]
@@ -493,8 +556,9 @@ def run_cuda(args):
             ms_b, tb = timed_fn(beam_gen, 1)
             beam5 = {"metric": "emu2_img2text_beam5_tok_per_s", "value": tb.shape[1] / (ms_b / 1000.0), "unit": "tok/s",
                      "new_tokens": int(tb.shape[1]), "ms": ms_b,
+                     "tokens_sha1": hashlib.sha1(tb.to(torch.int64).cpu().numpy().tobytes()).hexdigest()[:16],
                      "config": "num_beams=5, length_penalty=-1 (reference default), batch 1 -> 5 cache rows, "
-                               "device-side emu_beam_topk per step, host beam bookkeeping on [1,10] tensors"}
+                               "device-side emu_beam_topk + emu_beam_step per step (no host synchronisation in the loop)"}
         except Exception as ex:
             beam5 = {"metric": "emu2_img2text_beam5_tok_per_s", "value": None, "error": repr(ex)}
     ctx_avg = prompt_len + NEW_TOKENS / 2.0
@@ -502,31 +566,67 @@ def run_cuda(args):
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (step_ms_avg / 1000.0) / 1e9
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
+    # ---- second half of the headline metric: Emu2-Gen denoise steps/s at this GPU count ----
+    # N = 1: batch 1 + CFG on one GPU.  N = 2: CFG-parallel pair (cond on rank 0, uncond on rank 1, noise predictions swapped
+    # over NVLink inside the CFG+Euler kernel).  N = 4 / 8: N/2 such pairs, each denoising its own image (UNet tensor
+    # parallelism at batch 1 does not pay: SURVEY.md §8e) — value = images x steps / s over the whole job.
     denoise = None
-    if world == 1 and not args.small and not args.no_denoise:
+    if not args.small and not args.no_denoise:
         try:
+            del model
             torch.cuda.empty_cache()
-            sps, ms_d, lpl, finite = run_denoise()
             bf16_peak = 1739.4
             try:
                 bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
             except Exception:
                 pass
-            ach = 2 * UNET_FLOP_PER_SAMPLE_STEP / (ms_d / 1000.0) / 1e12
-            denoise = {"metric": "emu2gen_denoise_steps_per_s", "value": sps, "unit": "steps/s", "ms_per_step": ms_d,
-                       "config": "SDXL-topology UNet 2.53B, 1024x1024 (latent 128x128), batch 1 + CFG (UNet batch 2), "
-                                 "50 Euler steps, guidance 3, ctx [2,64,1792], bf16, CUDA-graphed fused step",
-                       "gpu_launches_per_step": lpl, "finite": finite,
-                       "roofline": {"bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s",
-                                    "frac": ach / bf16_peak, "flops_per_step": 2 * UNET_FLOP_PER_SAMPLE_STEP,
-                                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"}}
+            if world == 1:
+                r = run_denoise()
+                images, layout = 1, "1 GPU: UNet batch 2 (cond + uncond)"
+            else:
+                import ctypes
+                pair, prank = rank // 2, rank % 2
+                mine = torch.zeros(128, dtype=torch.uint8, device="cuda")
+                if prank == 0:
+                    raw = ctypes.create_string_buffer(128)
+                    _lib.check(_lib.load().emu_nccl_unique_id(raw))
+                    mine.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+                alls = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(alls, mine)
+                puid = bytes(alls[pair * 2].cpu().numpy().tobytes())   # the id made by the even rank of my pair
+                ueng, _ = make_unet_engine(tp_rank=prank, tp_size=2, uid=puid)
+                r = run_denoise(eng=ueng, sync=barrier, latent_seed=pair)
+                t = torch.tensor([r["ms_per_step"]], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                r["ms_per_step"] = float(t.item())
+                # both ranks of a pair must hold bitwise identical latents
+                hv = torch.tensor([int(r["latents_sha1"], 16) >> 1], dtype=torch.int64, device="cuda")
+                hs = [torch.zeros_like(hv) for _ in range(world)]
+                dist.all_gather(hs, hv)
+                r["pair_latents_identical"] = all(int(hs[2 * q].item()) == int(hs[2 * q + 1].item()) for q in range(world // 2))
+                r["latents_sha1_per_pair"] = ["%016x" % (int(hs[2 * q].item()) << 1) for q in range(world // 2)]
+                images, layout = world // 2, "%d CFG-parallel pair(s): cond on even ranks, uncond on odd ranks, one image per pair" % (world // 2)
+                ueng.close()
+            sps = images * 1000.0 / r["ms_per_step"]
+            ach = images * 2 * UNET_FLOP_PER_SAMPLE_STEP / (r["ms_per_step"] / 1000.0) / 1e12
+            denoise = {"metric": "emu2gen_denoise_steps_per_s", "value": sps, "unit": "steps/s", "ms_per_step": r["ms_per_step"],
+                       "images_in_flight": images, "scaling": "strong 1->2 (one image), weak beyond (one image per pair)",
+                       "config": "SDXL-topology UNet 2.53B, 1024x1024 (latent 128x128), batch 1 + CFG per image, 50 Euler "
+                                 "steps, guidance 3, ctx [2,64,1792], bf16, CUDA-graphed fused step; " + layout,
+                       "gpu_launches_per_step": r["launches_per_step"], "finite": r["finite"],
+                       "latents_sha1": r["latents_sha1"], "latents_abs_mean": r["latents_abs_mean"],
+                       "pair_latents_identical": r.get("pair_latents_identical"),
+                       "latents_sha1_per_pair": r.get("latents_sha1_per_pair"),
+                       "roofline": {"bound": "tensor", "achieved": ach, "peak": bf16_peak * world, "unit": "TFLOP/s",
+                                    "frac": ach / (bf16_peak * world), "flops_per_step": images * 2 * UNET_FLOP_PER_SAMPLE_STEP,
+                                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained x n_gpus"}}
         except Exception as ex:
             denoise = {"metric": "emu2gen_denoise_steps_per_s", "value": None, "error": repr(ex)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -536,6 +636,7 @@ def run_cuda(args):
         except Exception as ex:  # the CPU baseline must never take the GPU result down with it
             cpu = {"value": None, "unit": "tok/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % ex}
 
+    traffic_ratio, traffic_src = ncu_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -549,11 +650,14 @@ def run_cuda(args):
                      "frac": achieved / peak, "peak_source": peak_src,
                      # ncu --set full on the gate/up launch (profiles/r01_ncu_full_gemv_tma_gateup.txt): dram read
                      # 477.3 MB + write 6.5 MB for 477.1 MB of weights -> x1.014 of the algorithmic bytes, per step here
-                     "traffic": alg_bytes * NCU_TRAFFIC_RATIO, "traffic_source": "ncu dram bytes / algorithmic bytes of "
-                     "the gate_up launch (x%.3f), scaled to the step" % NCU_TRAFFIC_RATIO,
+                     "traffic": (alg_bytes * traffic_ratio) if traffic_ratio else None,
+                     "traffic_source": ("ncu dram__bytes_read+write / algorithmic bytes of the gate_up launch (x%.3f, %s), "
+                                        "scaled to the step" % (traffic_ratio, traffic_src)) if traffic_ratio else None,
                      "decode_step_ms": step_ms_avg, "decode_step_ms_p50": step_ms[len(step_ms) // 2],
                      "algorithmic_bytes_per_step": alg_bytes},
         "cpu_baseline": cpu,
+        "tokens_sha1": tokens_sha1, "tokens_head": [int(v) for v in tok_cpu[0, :8]], "tokens_identical_across_ranks": ranks_agree,
+        "vit_ms": vit_ms, "prefill_ms": prefill_ms,
         "denoise": denoise,
         "beam5": beam5,
     }

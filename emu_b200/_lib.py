@@ -57,7 +57,7 @@ class EmuVAEConfig(C.Structure):
 
 # every symbol declared in include/emu_b200.h (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "emu_beam_topk", "emu_sample_tokens", "emu_image_to_uint8", "emu_preprocess_image", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
+    "emu_beam_topk", "emu_beam_step", "emu_sample_tokens", "emu_image_to_uint8", "emu_preprocess_image", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
     "emu_vit_forward", "emu_llm_reset", "emu_llm_embed", "emu_llm_prefill", "emu_llm_decode", "emu_llm_cur_len",
     "emu_project", "emu_cformer_forward", "emu_unet_configure", "emu_unet_forward", "emu_denoise_step",
     "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
@@ -208,12 +208,28 @@ class Engine:
     def sample_tokens(self, logits, temperature=1.0, top_k=0, top_p=1.0, ban_id=-1, seed=0, offset=0):
         return op_sample_tokens(logits, temperature, top_k, top_p, -1 if ban_id is None else ban_id, seed, offset)
 
-    def beam_topk(self, logits, running_scores, batch, beams, keep, ban_id=-1, prev_tokens=None, repetition_penalty=1.0):
+    def beam_topk(self, logits, running_scores, batch, beams, keep, ban_id=-1, prev_tokens=None, prev_len=0,
+                  repetition_penalty=1.0, penalty_on_logits=False, no_repeat_ngram=0, allowed=None):
         if ban_id is None:
             ban_id = -1
         lg = logits if (logits.dtype == torch.float32 and logits.is_contiguous()) else logits.float().contiguous()
         return op_beam_topk(lg, running_scores, batch, beams, keep, ban_id=int(ban_id), prev_tokens=prev_tokens,
-                            repetition_penalty=float(repetition_penalty))
+                            prev_len=prev_len, repetition_penalty=float(repetition_penalty),
+                            penalty_on_logits=penalty_on_logits, no_repeat_ngram=int(no_repeat_ngram or 0), allowed=allowed)
+
+    def beam_state(self, batch, beams, max_length, pad_token_id, device):
+        return BeamState(batch, beams, max_length, pad_token_id, device)
+
+    def beam_step(self, st, topk_lp, topk_idx, cur_len, eos_token_id, length_penalty, early_stopping):
+        """emu_beam_step: hypothesis bookkeeping of one HF beam-search step on the device (no host synchronisation)."""
+        best_len = st.max_length if (early_stopping == "never" and length_penalty > 0.0) else cur_len + 1
+        es = 1 if early_stopping is True else (2 if early_stopping == "never" else 0)
+        check(self.lib.emu_beam_step(_ptr(topk_lp), _ptr(topk_idx), st.batch, st.beams, self.cfg.llm_vocab, cur_len,
+                                     st.max_length, int(eos_token_id), C.c_float(float((cur_len + 1) ** length_penalty)),
+                                     C.c_float(float(best_len ** length_penalty)), es, _ptr(st.running_seq),
+                                     _ptr(st.running_scores), _ptr(st.sequences), _ptr(st.beam_scores), _ptr(st.is_finished),
+                                     _ptr(st.fin_len), _ptr(st.unsat), _ptr(st.done), _ptr(st.next_tokens), _ptr(st.beam_src),
+                                     _stream()), self.h)
 
     # ---- Emu1 Causal-Former ----
     def cformer_forward(self, vit_tokens, n_queries, out_dim):
@@ -390,21 +406,62 @@ def op_sample_tokens(logits, temperature=1.0, top_k=0, top_p=1.0, ban_id=-1, see
     return out
 
 
-def op_beam_topk(logits, running_scores, batch, beams, keep, ban_id=-1, prev_tokens=None, repetition_penalty=1.0):
+class BeamState:
+    """Device-resident state of one beam search (layout documented at emu_beam_step in include/emu_b200.h)."""
+
+    def __init__(self, batch, beams, max_length, pad_token_id, device):
+        self.batch, self.beams, self.max_length = batch, beams, max_length
+        i32 = dict(dtype=torch.int32, device=device)
+        self.running_seq = torch.full((2, batch, beams, max_length), pad_token_id, **i32)
+        self.sequences = torch.full((2, batch, beams, max_length), pad_token_id, **i32)
+        self.running_scores = torch.zeros(batch, beams, dtype=torch.float32, device=device)
+        self.running_scores[:, 1:] = -1e9
+        self.beam_scores = torch.full((batch, beams), -1e9, dtype=torch.float32, device=device)
+        self.is_finished = torch.zeros(batch, beams, **i32)
+        self.fin_len = torch.zeros(batch, beams, **i32)
+        self.unsat = torch.ones(batch, **i32)
+        self.done = torch.zeros(1, **i32)
+        self.next_tokens = torch.zeros(batch * beams, **i32)
+        self.beam_src = torch.zeros(batch * beams, **i32)
+
+    def live(self, cur_len):
+        """the plane holding the sequences after `cur_len` tokens"""
+        return cur_len & 1
+
+    def is_done(self):
+        return bool(self.done.item())   # the only device->host synchronisation of the loop
+
+    def result(self, cur_len):
+        best = self.sequences[self.live(cur_len), :, 0, :]
+        gen_len = int(self.fin_len[:, 0].max())
+        return best[:, :gen_len].to(torch.int64)
+
+
+def op_beam_topk(logits, running_scores, batch, beams, keep, ban_id=-1, prev_tokens=None, prev_len=0, repetition_penalty=1.0,
+                 penalty_on_logits=False, no_repeat_ngram=0, allowed=None):
     """logits [batch*beams, V] fp32 (overwritten), running_scores [batch, beams] fp32 -> (scores [batch, keep] fp32,
-    flat indices [batch, keep] int64 = beam*V + token), HF _beam_search step semantics."""
+    flat indices [batch, keep] int32 = beam*V + token), HF _beam_search step semantics.  prev_tokens: int32 [batch*beams, L]
+    (any row stride), prev_len valid tokens per row."""
     require_cuda()
     lib = load()
     V = logits.shape[-1]
     assert logits.dtype == torch.float32 and logits.is_contiguous()
     rs = running_scores.to(torch.float32).contiguous().view(-1) if running_scores is not None else None
-    prev = prev_tokens.to(torch.int64).contiguous() if prev_tokens is not None and prev_tokens.numel() else None
+    stride = 0
+    if prev_tokens is not None and prev_len > 0:
+        assert prev_tokens.dtype == torch.int32 and prev_tokens.stride(-1) == 1
+        prev_tokens = prev_tokens.reshape(batch * beams, -1) if prev_tokens.dim() != 2 else prev_tokens
+        stride = prev_tokens.stride(0)
+    else:
+        prev_tokens, prev_len = None, 0
+    if allowed is not None:
+        allowed = allowed.to(torch.uint8).contiguous()
     out_lp = torch.empty(batch, keep, dtype=torch.float32, device=logits.device)
     out_idx = torch.empty(batch, keep, dtype=torch.int32, device=logits.device)
-    check(lib.emu_beam_topk(_ptr(logits), _ptr(rs), batch, beams, V, keep, ban_id, _ptr(prev),
-                            prev.shape[1] if prev is not None else 0, C.c_float(repetition_penalty), _ptr(out_lp),
-                            _ptr(out_idx), _stream()))
-    return out_lp, out_idx.to(torch.int64)
+    check(lib.emu_beam_topk(_ptr(logits), _ptr(rs), batch, beams, V, keep, ban_id, _ptr(prev_tokens), int(prev_len), int(stride),
+                            C.c_float(repetition_penalty), 1 if penalty_on_logits else 0, int(no_repeat_ngram), _ptr(allowed),
+                            _ptr(out_lp), _ptr(out_idx), _stream()))
+    return out_lp, out_idx
 
 
 def op_attn_decode(q, k_cache, v_cache, pos, start, scale, max_len):

@@ -28,44 +28,81 @@ def _iter_safetensors(path: str) -> Iterator[Tuple[str, torch.Tensor]]:
             yield k, f.get_tensor(k)  # one tensor resident at a time (the file is memory-mapped)
 
 
-def _iter_torch_bin(path: str) -> Iterator[Tuple[str, torch.Tensor]]:
+def _load_torch_bin(path: str, allow_pickle: bool = False):
+    """torch.load restricted to tensors (weights_only=True).  Legacy (non-zip) pickles cannot be memory-mapped, so the
+    retry drops mmap — it never widens the unpickler.  A checkpoint that needs arbitrary pickled objects loads only
+    when the caller opts in with allow_pickle=True (the reference's plain torch.load, Emu1/inference.py:44, trusts
+    the file; a drop-in must not do that silently)."""
     try:
         sd = torch.load(path, map_location="cpu", mmap=True, weights_only=True)
-    except Exception:  # legacy (non-zip) pickles cannot be memory-mapped
-        sd = torch.load(path, map_location="cpu", weights_only=False)
+    except Exception:
+        try:
+            sd = torch.load(path, map_location="cpu", mmap=False, weights_only=True)
+        except Exception:
+            if not allow_pickle:
+                raise
+            sd = torch.load(path, map_location="cpu", weights_only=False)
     if isinstance(sd, dict) and "module" in sd and isinstance(sd["module"], dict):
         sd = sd["module"]  # Emu1: torch.load(ckpt)['module']  (Emu1/inference.py:44-45)
+    return sd
+
+
+def _iter_torch_bin(path: str, allow_pickle: bool = False) -> Iterator[Tuple[str, torch.Tensor]]:
+    sd = _load_torch_bin(path, allow_pickle)
     for k in list(sd.keys()):
         yield k, sd.pop(k)
 
 
-def iter_checkpoint(path: str) -> Iterator[Tuple[str, torch.Tensor]]:
+def _files_of(path: str):
+    if not osp.isdir(path):
+        return [path]
+    for index in ("model.safetensors.index.json", "pytorch_model.bin.index.json"):
+        ip = osp.join(path, index)
+        if osp.exists(ip):
+            shards = sorted(set(json.load(open(ip))["weight_map"].values()))
+            missing = [s for s in shards if not osp.exists(osp.join(path, s))]
+            if missing:  # the reference loads with strict=True (Emu2/emu/chat.py:212): an absent shard is an error
+                raise FileNotFoundError("checkpoint shards listed in %s are missing: %s" % (index, missing[:3]))
+            return [osp.join(path, s) for s in shards]
+    files = sorted(f for f in os.listdir(path) if f.endswith((".safetensors", ".bin", ".pt", ".pth")))
+    if not files:
+        raise FileNotFoundError("no checkpoint files under %s" % path)
+    return [osp.join(path, f) for f in files]
+
+
+def iter_checkpoint(path: str, allow_pickle: bool = False) -> Iterator[Tuple[str, torch.Tensor]]:
     """Yield (key, cpu tensor) pairs of a file, a sharded directory (index.json) or a directory of weight files."""
-    if osp.isdir(path):
-        for index in ("model.safetensors.index.json", "pytorch_model.bin.index.json"):
-            ip = osp.join(path, index)
-            if osp.exists(ip):
-                shards = sorted(set(json.load(open(ip))["weight_map"].values()))
-                for s in shards:
-                    yield from iter_checkpoint(osp.join(path, s))
-                return
-        files = sorted(f for f in os.listdir(path) if f.endswith((".safetensors", ".bin", ".pt", ".pth")))
-        if not files:
-            raise FileNotFoundError("no checkpoint files under %s" % path)
-        for f in files:
-            yield from iter_checkpoint(osp.join(path, f))
-        return
-    if path.endswith(".safetensors"):
-        yield from _iter_safetensors(path)
-    else:
-        yield from _iter_torch_bin(path)
+    for f in _files_of(path):
+        if f.endswith(".safetensors"):
+            yield from _iter_safetensors(f)
+        else:
+            yield from _iter_torch_bin(f, allow_pickle)
 
 
-def merge_lora(pairs: Iterator[Tuple[str, torch.Tensor]], scaling: Optional[float] = None, lora_alpha: float = 16.0
-               ) -> Iterator[Tuple[str, torch.Tensor]]:
-    """peft-style adapters (`…base_layer.weight` / `…lora_A.default.weight` / `…lora_B.default.weight`, as produced for the
-    Emu1 instruct checkpoint, Emu1/inference.py:47-57) are folded into the base weight: W + (alpha / r) * B @ A.  Keys
-    are renamed to the plain module path.  Adapter tensors are small, so they are buffered; base weights stream through."""
+def iter_keys(path: str, allow_pickle: bool = False) -> Iterator[str]:
+    """Key names only (safetensors: header read; torch files: memory-mapped load, no tensor data touched)."""
+    for f in _files_of(path):
+        if f.endswith(".safetensors"):
+            from safetensors import safe_open
+            with safe_open(f, framework="pt", device="cpu") as h:
+                yield from h.keys()
+        else:
+            yield from _load_torch_bin(f, allow_pickle).keys()
+
+
+def lora_stems(keys) -> set:
+    """Module paths that carry an adapter: `<stem>.lora_A.<name>.weight` / `<stem>.lora_B.<name>.weight`."""
+    return {k.split(".lora_")[0] for k in keys if ".lora_A." in k or ".lora_B." in k}
+
+
+def merge_lora(pairs: Iterator[Tuple[str, torch.Tensor]], scaling: Optional[float] = None, lora_alpha: float = 16.0,
+               stems: Optional[set] = None) -> Iterator[Tuple[str, torch.Tensor]]:
+    """peft adapters are folded into the base weight: W + (alpha / r) * B @ A.  Both key layouts are handled:
+      * peft >= 0.7   `<stem>.base_layer.weight` + `<stem>.lora_A.default.weight` / `lora_B.default.weight`
+      * 2023-era peft (the Emu1 instruct checkpoint, Emu1/inference.py:40-57)   `<stem>.weight` next to the adapters.
+    `stems` = the module paths that carry an adapter (lora_stems(iter_keys(path))); with it only those base weights are
+    held back until their A / B arrive and everything else streams through.  Without it (single pass over an
+    in-memory dict) every 2-D `.weight` is held until the end.  Adapter tensors left without a base weight raise."""
     A: Dict[str, torch.Tensor] = {}
     B: Dict[str, torch.Tensor] = {}
     held: Dict[str, torch.Tensor] = {}
@@ -85,22 +122,30 @@ def merge_lora(pairs: Iterator[Tuple[str, torch.Tensor]], scaling: Optional[floa
             (A if ".lora_A." in k else B)[stem] = t
         elif k.endswith(".base_layer.weight"):
             held[k[: -len(".base_layer.weight")]] = t
+        elif k.endswith(".weight") and t.dim() == 2 and (stems is None or k[: -len(".weight")] in stems):
+            held[k[: -len(".weight")]] = t  # legacy layout: the adapter of this module may still arrive
         else:
             yield clean(k), t
             continue
         for stem in [s for s in list(held) if s in A and s in B]:
             yield emit(stem)
     for stem in list(held):  # base layers without an adapter
+        if stem in A or stem in B:
+            raise KeyError("incomplete LoRA adapter for %s (lora_A and lora_B are both required)" % stem)
         yield clean(stem) + ".weight", held.pop(stem)
+    left = sorted(set(A) | set(B))
+    if left:
+        raise KeyError("LoRA adapters without a base weight: %s" % left[:3])
 
 
 def load_into(sink, path: str, prefix: str = "", rename: Optional[Callable[[str], Optional[str]]] = None,
-              lora: bool = False, strict_keys: Optional[set] = None) -> int:
+              lora: bool = False, strict_keys: Optional[set] = None, allow_pickle: bool = False) -> int:
     """Stream every tensor under `path` into sink.load_tensor(prefix + key, tensor).  `rename(key)` may map or drop
-    (return None) keys.  Returns the number of tensors loaded."""
-    pairs = iter_checkpoint(path)
+    (return None) keys.  `strict_keys`: names that must all arrive (the reference loads with strict=True).  Returns the
+    number of tensors loaded."""
+    pairs = iter_checkpoint(path, allow_pickle)
     if lora:
-        pairs = merge_lora(pairs)
+        pairs = merge_lora(pairs, stems=lora_stems(iter_keys(path, allow_pickle)))
     n = 0
     seen = set()
     for k, t in pairs:

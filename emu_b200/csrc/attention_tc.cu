@@ -14,7 +14,7 @@
 //   warps 2-3   idle (they complete warpgroup 0 so that it can hand its registers over with setmaxnreg)
 //   warps 4-7   softmax for tile 0, warps 8-11 for tile 1: thread == query row (TMEM lane); S row -> registers, online
 //               max/sum, P (bf16) written to swizzled SMEM as the A operand of the second MMA.
-// Warpgroup 0 shrinks to 64 registers per thread and the two softmax warpgroups grow to 224 (setmaxnreg), so the 128
+// Warpgroup 0 shrinks to 72 registers per thread and the two softmax warpgroups grow to 216 (setmaxnreg; 128 x 72 + 256 x 216 = the 384 x 168 registers the CTA was launched with — asking for more would block forever), so the 128
 // scores of a row live in registers without spills.  The softmax inner loop is written for issue slots, the scarce
 // resource of a lone warp per scheduler: packed f32x2 FMA / ADD (one instruction per two scores), 3-input max, one
 // 16-byte st.shared per 8 probabilities (conflict-free under the 128B swizzle).
@@ -208,7 +208,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0) {
       // ===================== TMA producer =====================
       if (lane == 0 && nbmax > 0) {
@@ -295,7 +295,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else {
     // ===================== softmax / correction / epilogue warpgroups =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int t = (warp - 4) >> 2;  // query tile of this warpgroup
     const int quad = warp & 3;      // TMEM lane quarter this warp may access
     const int r = quad * 32 + lane;

@@ -199,21 +199,24 @@ static int nccl_allreduce_min_int(EmuEngine* e, int* v) {
   return rc;
 }
 int tp_setup(EmuEngine* e) { return tp_exchange_setup(e, nccl_allgather_bytes, nccl_allreduce_min_int); }
+int engine_allgather_bytes(EmuEngine* e, const void* src, void* dst, size_t bytes) { return nccl_allgather_bytes(e, src, dst, bytes); }
+int engine_allreduce_min_int(EmuEngine* e, int* v) { return nccl_allreduce_min_int(e, v); }
 
 // vocab-sharded logits: local [B, Vl] fp32 -> all ranks' shards [tp][B][Vl] -> logits [B, V]
-__global__ void logits_unshard_kernel(const float* __restrict__ g, float* out, int tp, int B, int Vl) {
+__global__ void logits_unshard_kernel(const float* __restrict__ g, float* out, int tp, int B, int Vl, int V) {
   const long total = (long)tp * B * Vl;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int v = i % Vl;
     const int b = (i / Vl) % B;
     const int r = i / ((long)Vl * B);
-    out[(long)b * tp * Vl + (long)r * Vl + v] = g[i];
+    const long col = (long)r * Vl + v;
+    if (col < V) out[(long)b * V + col] = g[i];  // rows past V are the zero padding of the last shard
   }
 }
 int gather_logits(EmuEngine* e, const float* local, float* gathered, float* out, int B, cudaStream_t st) {
   // ncclFloat32 = 7
   if (g_nccl.AllGather(local, gathered, (size_t)B * e->Vl, 7, e->nccl_comm, st) != 0) return e->fail(EMU_ERR_NCCL, "ncclAllGather failed");
-  logits_unshard_kernel<<<2 * kNumSMs, 256, 0, st>>>(gathered, out, e->tp_size, B, e->Vl);
+  logits_unshard_kernel<<<2 * kNumSMs, 256, 0, st>>>(gathered, out, e->tp_size, B, e->Vl, e->cfg.llm_vocab);
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
@@ -270,7 +273,7 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
   e->tp_size = tp_size;
   const EmuConfig& c = e->cfg;
   if (c.llm_layers > 0) {
-    if (c.llm_ffn % tp_size || c.llm_vocab % tp_size || c.llm_max_batch < 1 ||
+    if (c.llm_ffn % tp_size || c.llm_max_batch < 1 ||
         c.llm_max_batch > 8 || c.llm_hidden % 32 || c.llm_ffn % (32 * tp_size) || (c.llm_head_dim != 64 && c.llm_head_dim != 128)) {
       delete e;
       return EMU_ERR_UNSUPPORTED;
@@ -280,7 +283,9 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
     e->Hl = (c.llm_heads + tp_size - 1) / tp_size;
     emu_tp_head_range(c.llm_heads, tp_size, tp_rank, &e->head_start, &e->head_count);
     e->Fl = c.llm_ffn / tp_size;
-    e->Vl = c.llm_vocab / tp_size;
+    // the vocabulary need not divide the TP degree either (Emu2-Chat: 32274, Emu1: 32004): every rank holds ceil(V/tp)
+    // lm_head rows, rows past V are zero and are dropped when the shards are gathered
+    e->Vl = (c.llm_vocab + tp_size - 1) / tp_size;
     e->layers.resize(c.llm_layers);
     const int half = c.llm_head_dim / 2;
     const int max_pos = c.llm_max_seq + 8;
@@ -302,7 +307,7 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
     e->dec_logits_local = (float*)e->dmalloc((size_t)Bm * c.llm_vocab * sizeof(float));
     e->dec_logits_shard = (float*)e->dmalloc(((size_t)Bm * e->Vl + 4) * sizeof(float));
     e->dec_part = (float*)e->dmalloc((size_t)Bm * c.llm_hidden * sizeof(float));
-    e->dec_logits_gather = (float*)e->dmalloc((size_t)Bm * c.llm_vocab * sizeof(float));
+    e->dec_logits_gather = (float*)e->dmalloc((size_t)Bm * e->Vl * tp_size * sizeof(float));
     if (!e->rope_cos || !e->rope_sin || !e->kv || !e->d_pos || !e->dec_h || !e->dec_q || !e->dec_attn || !e->dec_act ||
         !e->dec_tmp || !e->dec_attn_ws || !e->dec_counters || !e->dec_logits_local) {
       emu_engine_destroy(e);
@@ -349,7 +354,6 @@ extern "C" void emu_engine_destroy(EmuEngine* e) {
   cudaDeviceSynchronize();
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
-  if (e->mega) mega_destroy(e->mega);
   if (e->unet) unet_destroy(e->unet);
   if (e->vae) vae_destroy(e->vae);
   if (e->cformer) cformer_destroy(e->cformer);
@@ -401,14 +405,20 @@ static int load_llm(EmuEngine* e, const std::string& key, const bf16* src, const
     if (n != (long)c.llm_vocab * Hd) return e->fail(EMU_ERR_INVALID, "embed_tokens shape");
     return alloc_copy(e, &e->embed, src, n, st);
   }
-  if (key == "decoder.lm.model.norm.weight") return alloc_copy(e, &e->final_norm, src, Hd, st);
+  if (key == "decoder.lm.model.norm.weight") {
+    if (n != Hd) return e->fail(EMU_ERR_INVALID, "final norm shape");
+    return alloc_copy(e, &e->final_norm, src, Hd, st);
+  }
   if (key == "decoder.lm.lm_head.weight") {
     if (n != (long)c.llm_vocab * Hd) return e->fail(EMU_ERR_INVALID, "lm_head shape");
-    if (!e->lm_head) e->lm_head = (bf16*)e->dmalloc((size_t)e->Vl * Hd * 2);
-    if (!e->lm_head) return e->fail(EMU_ERR_NOMEM, "lm_head alloc");
-    return pack_rows(e->lm_head, src, e->Vl, Hd, Hd, Hd, (long)e->tp_rank * e->Vl, 0, 0, D, 0, 1, st);
+    EMU_TRY(alloc_zero(e, &e->lm_head, (size_t)e->Vl * Hd, st));
+    const long row0 = (long)e->tp_rank * e->Vl;
+    const long rows = row0 >= c.llm_vocab ? 0 : (row0 + e->Vl <= c.llm_vocab ? e->Vl : c.llm_vocab - row0);
+    if (rows == 0) return EMU_OK;
+    return pack_rows(e->lm_head, src, rows, Hd, Hd, Hd, row0, 0, 0, D, 0, 1, st);
   }
   if (key == "decoder.lm.stu_regress_head.weight") {
+    if (ndim != 2) return e->fail(EMU_ERR_INVALID, "stu_regress_head shape");
     e->stu_out = (int)shape[0];
     e->stu_in = (int)shape[1];
     return alloc_copy(e, &e->stu_head, src, n, st);
@@ -421,17 +431,24 @@ static int load_llm(EmuEngine* e, const std::string& key, const bf16* src, const
   if (li < 0 || li >= c.llm_layers) return e->fail(EMU_ERR_INVALID, "layer index out of range: " + key);
   const std::string sub = key.substr(p1 + 1);
   LlmLayer& L = e->layers[li];
-  if (sub == "input_layernorm.weight") return alloc_copy(e, &L.ln1, src, Hd, st);
-  if (sub == "post_attention_layernorm.weight") return alloc_copy(e, &L.ln2, src, Hd, st);
+  if (sub == "input_layernorm.weight" || sub == "post_attention_layernorm.weight") {
+    if (n != Hd) return e->fail(EMU_ERR_INVALID, "norm shape " + key);
+    const bool first = sub[0] == 'i';
+    L.loaded |= first ? 128u : 256u;
+    return alloc_copy(e, first ? &L.ln1 : &L.ln2, src, Hd, st);
+  }
   if (sub == "self_attn.q_proj.weight" || sub == "self_attn.k_proj.weight" || sub == "self_attn.v_proj.weight") {
     if (n != (long)c.llm_heads * D * Hd) return e->fail(EMU_ERR_INVALID, "qkv shape " + key);
     EMU_TRY(alloc_zero(e, &L.wqkv, (size_t)3 * Hl * D * Hd, st));
     const int which = sub[10] == 'q' ? 0 : (sub[10] == 'k' ? 1 : 2);
+    L.loaded |= 1u << which;
     // q,k rows are pair-interleaved per head so a RoPE rotation pair is adjacent (see gemv.cu / elementwise.cu)
     return pack_rows(L.wqkv, src, (long)e->head_count * D, Hd, Hd, Hd, (long)e->head_start * D, 0, which < 2 ? 1 : 0, D,
                      (long)which * Hl * D, 1, st);
   }
   if (sub == "self_attn.o_proj.weight") {
+    if (n != (long)c.llm_heads * D * Hd) return e->fail(EMU_ERR_INVALID, "o_proj shape " + key);
+    L.loaded |= 8u;
     EMU_TRY(alloc_zero(e, &L.wo, (size_t)Hd * Hl * D, st));
     return pack_rows(L.wo, src, Hd, e->head_count * D, (long)c.llm_heads * D, (long)Hl * D, 0, e->head_start * D, 0, D, 0, 1, st);
   }
@@ -440,9 +457,12 @@ static int load_llm(EmuEngine* e, const std::string& key, const bf16* src, const
     if (!L.wgu) L.wgu = (bf16*)e->dmalloc((size_t)2 * Fl * Hd * 2);
     if (!L.wgu) return e->fail(EMU_ERR_NOMEM, "wgu alloc");
     const int which = sub[4] == 'g' ? 0 : 1;
+    L.loaded |= 16u << which;
     return pack_rows(L.wgu, src, Fl, Hd, Hd, Hd, (long)e->tp_rank * Fl, 0, 0, D, which, 2, st);
   }
   if (sub == "mlp.down_proj.weight") {
+    if (n != (long)c.llm_ffn * Hd) return e->fail(EMU_ERR_INVALID, "mlp shape " + key);
+    L.loaded |= 64u;
     if (!L.wdown) L.wdown = (bf16*)e->dmalloc((size_t)Hd * Fl * 2);
     if (!L.wdown) return e->fail(EMU_ERR_NOMEM, "wdown alloc");
     return pack_rows(L.wdown, src, Hd, Fl, c.llm_ffn, Fl, 0, e->tp_rank * Fl, 0, D, 0, 1, st);
@@ -457,7 +477,11 @@ static int load_vit(EmuEngine* e, const std::string& key, const bf16* src, const
   const int W = c.vit_width;
   const long n = numel(shape, ndim);
   const int G = c.vit_image / c.vit_patch;
-  if (key == "visual.cls_token") return alloc_copy(e, &e->vit_cls, src, W, st);
+  auto sized = [&](long want, bf16** dst) -> int {
+    if (n != want) return e->fail(EMU_ERR_INVALID, "shape mismatch for " + key);
+    return alloc_copy(e, dst, src, (size_t)want, st);
+  };
+  if (key == "visual.cls_token") return sized(W, &e->vit_cls);
   if (key == "visual.pos_embed") {
     if (n != (long)(G * G + 1) * W) return e->fail(EMU_ERR_INVALID, "pos_embed shape");
     return alloc_copy(e, &e->vit_pos, src, n, st);
@@ -468,9 +492,9 @@ static int load_vit(EmuEngine* e, const std::string& key, const bf16* src, const
     EMU_TRY(alloc_zero(e, &e->vit_wpatch, (size_t)W * e->vit_kpad, st));
     return pack_rows(e->vit_wpatch, src, W, kin, kin, e->vit_kpad, 0, 0, 0, 1, 0, 1, st);
   }
-  if (key == "visual.patch_embed.proj.bias") return alloc_copy(e, &e->vit_bpatch, src, W, st);
-  if (key == "ln_visual.weight") return alloc_copy(e, &e->vit_lnf_w, src, W, st);
-  if (key == "ln_visual.bias") return alloc_copy(e, &e->vit_lnf_b, src, W, st);
+  if (key == "visual.patch_embed.proj.bias") return sized(W, &e->vit_bpatch);
+  if (key == "ln_visual.weight") return sized(W, &e->vit_lnf_w);
+  if (key == "ln_visual.bias") return sized(W, &e->vit_lnf_b);
   // unused-by-forward_features members of the Emu1 EVA tower (Emu1/models/eva_vit_model.py: head / norm / fc_norm / rope)
   if (starts_with(key, "visual.head.") || starts_with(key, "visual.norm.") || starts_with(key, "visual.fc_norm.") ||
       starts_with(key, "visual.rope."))
@@ -483,25 +507,27 @@ static int load_vit(EmuEngine* e, const std::string& key, const bf16* src, const
   if (li < 0 || li >= c.vit_layers) return e->fail(EMU_ERR_INVALID, "vit block index out of range");
   const std::string sub = key.substr(p1 + 1);
   VitBlock& B = e->vit[li];
-  if (sub == "norm1.weight") return alloc_copy(e, &B.ln1w, src, W, st);
-  if (sub == "norm1.bias") return alloc_copy(e, &B.ln1b, src, W, st);
-  if (sub == "norm2.weight") return alloc_copy(e, &B.ln2w, src, W, st);
-  if (sub == "norm2.bias") return alloc_copy(e, &B.ln2b, src, W, st);
-  if (sub == "attn.qkv.weight") return alloc_copy(e, &B.wqkv, src, (size_t)3 * W * W, st);
+  if (sub == "norm1.weight") return sized(W, &B.ln1w);
+  if (sub == "norm1.bias") return sized(W, &B.ln1b);
+  if (sub == "norm2.weight") return sized(W, &B.ln2w);
+  if (sub == "norm2.bias") return sized(W, &B.ln2b);
+  if (sub == "attn.qkv.weight") return sized((long)3 * W * W, &B.wqkv);
   if (sub == "attn.q_bias" || sub == "attn.v_bias") {
     // qkv bias = cat(q_bias, zeros, v_bias): K has no bias (Emu2/emu/eva_vit.py:194-196)
+    if (n != W) return e->fail(EMU_ERR_INVALID, "shape mismatch for " + key);
     EMU_TRY(alloc_zero(e, &B.bqkv, (size_t)3 * W, st));
+    B.bias_loaded |= sub == "attn.q_bias" ? 1u : 2u;
     const size_t off = sub == "attn.q_bias" ? 0 : (size_t)2 * W;
     return cudaMemcpyAsync(B.bqkv + off, src, (size_t)W * 2, cudaMemcpyDeviceToDevice, st) == cudaSuccess
                ? EMU_OK
                : e->fail(EMU_ERR_CUDA, "bias copy");
   }
-  if (sub == "attn.proj.weight") return alloc_copy(e, &B.wproj, src, (size_t)W * W, st);
-  if (sub == "attn.proj.bias") return alloc_copy(e, &B.bproj, src, W, st);
-  if (sub == "mlp.fc1.weight") return alloc_copy(e, &B.wfc1, src, (size_t)c.vit_mlp * W, st);
-  if (sub == "mlp.fc1.bias") return alloc_copy(e, &B.bfc1, src, c.vit_mlp, st);
-  if (sub == "mlp.fc2.weight") return alloc_copy(e, &B.wfc2, src, (size_t)c.vit_mlp * W, st);
-  if (sub == "mlp.fc2.bias") return alloc_copy(e, &B.bfc2, src, W, st);
+  if (sub == "attn.proj.weight") return sized((long)W * W, &B.wproj);
+  if (sub == "attn.proj.bias") return sized(W, &B.bproj);
+  if (sub == "mlp.fc1.weight") return sized((long)c.vit_mlp * W, &B.wfc1);
+  if (sub == "mlp.fc1.bias") return sized(c.vit_mlp, &B.bfc1);
+  if (sub == "mlp.fc2.weight") return sized((long)c.vit_mlp * W, &B.wfc2);
+  if (sub == "mlp.fc2.bias") return sized(W, &B.bfc2);
   if (starts_with(sub, "attn.rope.") || starts_with(sub, "attn.inner_attn_ln.")) return EMU_OK;
   return e->fail(EMU_ERR_INVALID, "unknown vit key " + key);
 }
@@ -519,6 +545,8 @@ extern "C" int emu_engine_load_tensor(EmuEngine* e, const char* state_dict_key, 
   int rc;
   if (starts_with(key, "visual.") || starts_with(key, "ln_visual.")) rc = load_vit(e, key, dsrc, shape, ndim, st);
   else if (starts_with(key, "decoder.")) rc = load_llm(e, key, dsrc, shape, ndim, st);
+  else if ((key == "project_up.weight" || key == "project_down.weight") && ndim != 2)
+    rc = e->fail(EMU_ERR_INVALID, "projection shape " + key);
   else if (key == "project_up.weight") {
     e->proj_up_out = (int)shape[0];
     e->proj_up_in = (int)shape[1];
@@ -552,8 +580,8 @@ extern "C" int emu_vit_forward(EmuEngine* e, const void* image, int B, void* out
   const long M = (long)B * N;
   if (!e->vit_wpatch || !e->vit_bpatch || !e->vit_cls || !e->vit_pos) return e->fail(EMU_ERR_STATE, "ViT stem weights missing");
   for (auto& b : e->vit)
-    if (!b.wqkv || !b.bqkv || !b.wproj || !b.bproj || !b.wfc1 || !b.bfc1 || !b.wfc2 || !b.bfc2 || !b.ln1w || !b.ln1b ||
-        !b.ln2w || !b.ln2b)
+    if (!b.wqkv || !b.bqkv || b.bias_loaded != 3u || !b.wproj || !b.bproj || !b.wfc1 || !b.bfc1 || !b.wfc2 || !b.bfc2 ||
+        !b.ln1w || !b.ln1b || !b.ln2w || !b.ln2b)
       return e->fail(EMU_ERR_STATE, "ViT block weights missing");
   EMU_TRY(e->ensure(e->vit_patches, (size_t)B * Np * (e->vit_kpad > W ? e->vit_kpad : W) * 2 * 2));
   EMU_TRY(e->ensure(e->vit_x, (size_t)M * W * 2));
@@ -655,8 +683,17 @@ static inline bf16* kv_layer(EmuEngine* e, int layer, int kv) {
 static int llm_ready(EmuEngine* e) {
   if (e->cfg.llm_layers < 1) return e->fail(EMU_ERR_STATE, "engine has no LLM");
   if (!e->embed || !e->final_norm || !e->lm_head) return e->fail(EMU_ERR_STATE, "LLM embed/norm/lm_head missing");
-  for (auto& L : e->layers)
-    if (!L.wqkv || !L.wo || !L.wgu || !L.wdown || !L.ln1 || !L.ln2) return e->fail(EMU_ERR_STATE, "LLM layer weights missing");
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    const LlmLayer& L = e->layers[l];
+    if (!L.wqkv || !L.wo || !L.wgu || !L.wdown || !L.ln1 || !L.ln2 || L.loaded != LlmLayer::kAll) {
+      static const char* names[9] = {"q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj",
+                                     "input_layernorm", "post_attention_layernorm"};
+      std::string miss;
+      for (int b = 0; b < 9; ++b)
+        if (!(L.loaded & (1u << b))) miss += std::string(miss.empty() ? "" : ", ") + names[b];
+      return e->fail(EMU_ERR_STATE, "LLM layer " + std::to_string(l) + " is missing " + miss);
+    }
+  }
   return EMU_OK;
 }
 
@@ -939,15 +976,6 @@ extern "C" int emu_llm_decode(EmuEngine* e, const int32_t* token_ids, const void
     EMU_TRY(kv_reorder(e->kv, c.llm_max_batch, beam_src_idx, B, (long)c.llm_layers * 2, e->cur_len, e->Hl, c.llm_head_dim,
                        c.llm_max_seq, st));
     count_launch();
-  }
-  // preferred path: the whole step in one persistent cooperative kernel (decode_mega.cu)
-  {
-    const int rc = decode_mega_step(e, token_ids, embeds, B, logits, hidden, next_ids, ban_id, st);
-    if (rc == EMU_OK) {
-      e->cur_len += 1;
-      return EMU_OK;
-    }
-    if (rc != EMU_ERR_UNSUPPORTED) return rc;
   }
   int nl = 0;
   const char* no_graph = getenv("EMU_NO_GRAPH");  // debugging / parity switch: launch the step eagerly

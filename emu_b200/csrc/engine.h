@@ -18,11 +18,16 @@ inline void count_launch(int n = 1) { g_launches += n; }
 
 struct LlmLayer {
   bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr, *ln1 = nullptr, *ln2 = nullptr;
+  // which reference tensors have arrived: q k v o gate up down ln1 ln2 (fused buffers are allocated by the first of their
+  // parts, so a pointer check alone cannot tell a complete layer from one that is missing k_proj or up_proj)
+  unsigned loaded = 0;
+  static constexpr unsigned kAll = 0x1ff;
 };
 struct VitBlock {
   bf16 *wqkv = nullptr, *bqkv = nullptr, *wproj = nullptr, *bproj = nullptr;
   bf16 *wfc1 = nullptr, *bfc1 = nullptr, *wfc2 = nullptr, *bfc2 = nullptr;
   bf16 *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
+  unsigned bias_loaded = 0;  // bit 0 q_bias, bit 1 v_bias (they share the fused qkv bias buffer)
 };
 
 struct DevBuf {
@@ -75,7 +80,6 @@ struct EmuEngine {
   std::map<GraphKey, int> graph_nodes;
   bool use_graphs = true;
   cudaStream_t cap_stream = nullptr;
-  void* mega = nullptr;  // persistent decode-step kernel state (decode_mega.cu)
 
   // ---- ViT ----
   std::vector<emu::VitBlock> vit;
@@ -110,9 +114,6 @@ int tp_gather_logits(EmuEngine* e, const float* shard, float* logits, int B, int
 int tp_ll_prepare(EmuEngine* e, GemvArgs& g, int idx);
 int tp_ll_reduce(EmuEngine* e, bf16* h, long n_elem, int idx, int pdl, cudaStream_t st);
 unsigned* tp_step_counter(EmuEngine* e);
-int decode_mega_step(EmuEngine* e, const int32_t* token_ids, const void* embeds, int B, float* logits, void* hidden,
-                     int32_t* next_ids, int ban_id, cudaStream_t st);
-void mega_destroy(void* p);
 
 // sub-model entry points
 int unet_load_tensor(EmuEngine* e, const std::string& key, const bf16* src, const int64_t* shape, int ndim, cudaStream_t st);

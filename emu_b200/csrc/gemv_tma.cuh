@@ -1,5 +1,4 @@
-// emu_b200 — device-side building blocks of the TMA-fed skinny GEMM, shared by the one-GEMV kernel (gemv_tma.cu) and
-// the persistent decode-step kernel (decode_mega.cu).  See gemv_tma.cu for the design notes.
+// emu_b200 — device-side building blocks of the TMA-fed skinny GEMM (gemv_tma.cu has the design notes).
 #pragma once
 #include <stdlib.h>
 

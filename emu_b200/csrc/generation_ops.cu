@@ -1,8 +1,10 @@
 // emu_b200 — device-side generation control for beam search: the vocabulary-wide part of one HF
 // `_beam_search` step (transformers GenerationMixin, driven from Emu2/emu/emu.py:213-229 with num_beams=5,
 // length_penalty=-1) — log_softmax, repetition penalty, min-length EOS ban, "+ running beam score" and the top-2·beams
-// selection over beams x vocab — as three small kernels instead of full-vocabulary torch ops.  Only the [batch, 2·beams]
-// bookkeeping that follows stays on the host side (emu_b200/generation.py).
+// selection over beams x vocab — as three small kernels instead of full-vocabulary torch ops, and the [batch, 2·beams]
+// hypothesis bookkeeping that follows (emu_beam_step) as one more, so that a beam-search step never leaves the device:
+// the next tokens and the KV-cache reorder indices are chained device-to-device into the CUDA-graphed decode step and
+// the host only reads the "finished" flag every few steps.
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -37,12 +39,12 @@ __global__ void __launch_bounds__(1024) logsoftmax_add_kernel(float* __restrict_
 
 // HF RepetitionPenaltyLogitsProcessor on scores that already carry `add[r]`: s < 0 ? s * p : s / p at every previously
 // generated token (each distinct token once, like gather -> where -> scatter)
-__global__ void rep_penalty_kernel(float* x, const float* __restrict__ add, const long long* __restrict__ prev, int prev_len,
-                                   int V, float penalty) {
+__global__ void rep_penalty_kernel(float* x, const float* __restrict__ add, const int* __restrict__ prev, int prev_len,
+                                   int prev_stride, int V, float penalty) {
   const int r = blockIdx.x;
-  const long long* p = prev + (long)r * prev_len;
+  const int* p = prev + (long)r * prev_stride;
   for (int j = threadIdx.x; j < prev_len; j += blockDim.x) {
-    const long long t = p[j];
+    const int t = p[j];
     if (t < 0 || t >= V) continue;
     bool first = true;
     for (int k = 0; k < j; ++k) first = first && (p[k] != t);
@@ -56,6 +58,180 @@ __global__ void rep_penalty_kernel(float* x, const float* __restrict__ add, cons
 
 __global__ void ban_token_kernel(float* x, int V, int ban) {
   if (ban >= 0 && ban < V) x[(long)blockIdx.x * V + ban] = -INFINITY;
+}
+
+// HF NoRepeatNGramLogitsProcessor: ban every token that would complete an n-gram already present in the row's generated
+// tokens (Emu1/models/modeling_emu.py:110-115 forwards no_repeat_ngram_size to generate)
+__global__ void no_repeat_ngram_kernel(float* x, const int* __restrict__ prev, int prev_len, int prev_stride, int V, int n) {
+  const int r = blockIdx.x;
+  const int* p = prev + (long)r * prev_stride;
+  if (prev_len + 1 < n) return;
+  const int* tail = p + prev_len - (n - 1);  // the n-1 most recent tokens
+  for (int i = threadIdx.x; i + n - 1 < prev_len; i += blockDim.x) {
+    bool same = true;
+    for (int k = 0; k < n - 1; ++k) same = same && (p[i + k] == tail[k]);
+    const int t = p[i + n - 1];
+    if (same && t >= 0 && t < V) x[(long)r * V + t] = -INFINITY;
+  }
+}
+
+// HF PrefixConstrainedLogitsProcessor (Emu1/mm_eval/models/emu.py:97-109): allowed [rows, V] bytes, 0 = banned
+__global__ void allowed_mask_kernel(float* x, const unsigned char* __restrict__ allowed, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    if (!allowed[i]) x[i] = -INFINITY;
+}
+
+// ----------------------------------------------------------------------------------------------
+// One step of the hypothesis bookkeeping of HF's vectorised `_beam_search` (transformers >= 4.50: running beams, finished
+// beams, early-stopping heuristic), for all batch rows, in ONE small CTA.  Every array is tiny ([batch, beams] or
+// [batch, beams, max_length]); thread 0 of each row's warp makes the decisions in the exact order and fp32 arithmetic of
+// the torch formulation (tests/test_generation_cpu.py pins that formulation against the reference's lm.generate), the
+// whole CTA then moves the token rows.  Sequences are ping-ponged between two planes (parity of cur_len) so that the
+// gathers never read what they write.  When *done is already set the step is a no-op (the host polls `done` only every
+// few steps; the decode steps it launched in between are harmless).
+// ----------------------------------------------------------------------------------------------
+struct BeamStepArgs {
+  const float* topk_lp;   // [batch, 2*beams]
+  const int* topk_idx;    // [batch, 2*beams] flat beam*V + token
+  int batch, beams, vocab, cur_len, max_length, eos_id;
+  float fin_div;          // (cur_len + 1) ** length_penalty
+  float best_div;         // best_len ** length_penalty
+  int early_stopping;     // 0 = False, 1 = True, 2 = "never"
+  int* running_seq;       // [2][batch, beams, max_length]
+  float* running_scores;  // [batch, beams]
+  int* sequences;         // [2][batch, beams, max_length]
+  float* beam_scores;     // [batch, beams]
+  int* is_finished;       // [batch, beams]
+  int* fin_len;           // [batch, beams] length of each finished hypothesis
+  int* unsat;             // [batch]  "next_token_hits_criteria / improvement still possible" flag of each row
+  int* done;              // [1]
+  int* next_tokens;       // [batch * beams] -> emu_llm_decode token_ids
+  int* beam_src;          // [batch * beams] -> emu_llm_decode beam_src_idx
+};
+constexpr int kBeamMaxRows = 8;    // batch rows per call
+constexpr int kBeamMaxBeams = 16;
+
+__global__ void __launch_bounds__(256) beam_step_kernel(BeamStepArgs a) {
+  __shared__ int s_run_src[kBeamMaxRows][kBeamMaxBeams];   // candidate index feeding each new running beam
+  __shared__ int s_fin_src[kBeamMaxRows][kBeamMaxBeams];   // < nb: old finished slot, >= nb: candidate (index - nb)
+  __shared__ int s_all_hits[kBeamMaxRows], s_all_fin[kBeamMaxRows], s_unsat[kBeamMaxRows];
+  if (*a.done) return;
+  const int nb = a.beams, keep = 2 * nb, L = a.max_length, V = a.vocab;
+  const int b = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pin = a.cur_len & 1, pout = pin ^ 1;
+  const long plane = (long)a.batch * nb * L;
+  if (b < a.batch && lane == 0) {
+    const float* lp = a.topk_lp + (long)b * keep;
+    const int* ix = a.topk_idx + (long)b * keep;
+    bool hits[2 * kBeamMaxBeams];
+    float run_lp[2 * kBeamMaxBeams];
+    bool all_hits = true;
+    for (int c = 0; c < keep; ++c) {
+      hits[c] = (ix[c] % V == a.eos_id) || (a.cur_len + 1 >= L);
+      all_hits = all_hits && hits[c];
+      run_lp[c] = lp[c] + (hits[c] ? 1.0f : 0.0f) * -1.0e9f;
+    }
+    // running beams of the next iteration: top-nb of run_lp (largest first, ties to the lower index)
+    float new_run_sc[kBeamMaxBeams];
+    {
+      bool used[2 * kBeamMaxBeams];
+      for (int c = 0; c < keep; ++c) used[c] = false;
+      for (int k = 0; k < nb; ++k) {
+        int best = -1;
+        for (int c = 0; c < keep; ++c)
+          if (!used[c] && (best < 0 || run_lp[c] > run_lp[best])) best = c;
+        used[best] = true;
+        s_run_src[b][k] = best;
+        new_run_sc[k] = run_lp[best];
+      }
+    }
+    // finished beams: merge the old ones with the candidates that just finished, keep the best nb
+    bool full = true;
+    for (int k = 0; k < nb; ++k) full = full && (a.is_finished[b * nb + k] != 0);
+    const bool uns = a.unsat[b] != 0;
+    float m_sc[3 * kBeamMaxBeams];
+    int m_fin[3 * kBeamMaxBeams];
+    for (int k = 0; k < nb; ++k) { m_sc[k] = a.beam_scores[b * nb + k]; m_fin[k] = a.is_finished[b * nb + k]; }
+    for (int c = 0; c < keep; ++c) {
+      const bool just = hits[c] && c < nb;
+      float f = lp[c] / a.fin_div;
+      f = f + ((full && a.early_stopping == 1) ? 1.0f : 0.0f) * -1.0e9f;
+      f = f + (uns ? 0.0f : 1.0f) * -1.0e9f;
+      f = f + (just ? 0.0f : 1.0f) * -1.0e9f;
+      m_sc[nb + c] = f;
+      m_fin[nb + c] = just ? 1 : 0;
+    }
+    float new_sc[kBeamMaxBeams];
+    int new_fin[kBeamMaxBeams], new_len[kBeamMaxBeams];
+    {
+      bool used[3 * kBeamMaxBeams];
+      for (int c = 0; c < 3 * nb; ++c) used[c] = false;
+      for (int k = 0; k < nb; ++k) {
+        int best = -1;
+        for (int c = 0; c < 3 * nb; ++c)
+          if (!used[c] && (best < 0 || m_sc[c] > m_sc[best])) best = c;
+        used[best] = true;
+        s_fin_src[b][k] = best;
+        new_sc[k] = m_sc[best];
+        new_fin[k] = m_fin[best];
+        new_len[k] = best < nb ? a.fin_len[b * nb + best] : a.cur_len + 1;
+      }
+    }
+    bool all_fin = true;
+    float worst = 0.f;
+    for (int k = 0; k < nb; ++k) {
+      all_fin = all_fin && new_fin[k];
+      worst = k == 0 ? new_sc[k] : fminf(worst, new_sc[k]);
+    }
+    const float best_running = new_run_sc[0] / a.best_div;
+    bool any_better = false;
+    for (int k = 0; k < nb; ++k) any_better = any_better || (best_running > (new_fin[k] ? worst : -1.0e9f));
+    for (int k = 0; k < nb; ++k) {
+      a.running_scores[b * nb + k] = new_run_sc[k];
+      a.beam_scores[b * nb + k] = new_sc[k];
+      a.is_finished[b * nb + k] = new_fin[k];
+      a.fin_len[b * nb + k] = new_len[k];
+      const int c = s_run_src[b][k];
+      a.next_tokens[b * nb + k] = ix[c] % V;
+      a.beam_src[b * nb + k] = ix[c] / V + b * nb;
+    }
+    a.unsat[b] = (uns && any_better) ? 1 : 0;
+    s_unsat[b] = (uns && any_better) ? 1 : 0;
+    s_all_hits[b] = all_hits ? 1 : 0;
+    s_all_fin[b] = all_fin ? 1 : 0;
+  }
+  __syncthreads();
+  // move the token rows (whole CTA): plane pin -> plane pout
+  const int rows = a.batch * nb;
+  for (int i = threadIdx.x; i < rows * L; i += blockDim.x) {
+    const int t = i % L, k = (i / L) % nb, bb = i / (L * nb);
+    const int* ix = a.topk_idx + (long)bb * keep;
+    {  // running sequences
+      const int c = s_run_src[bb][k];
+      const int src_beam = ix[c] / V;
+      a.running_seq[pout * plane + i] = t == a.cur_len ? ix[c] % V : a.running_seq[pin * plane + ((long)bb * nb + src_beam) * L + t];
+    }
+    {  // finished sequences
+      const int m = s_fin_src[bb][k];
+      int v;
+      if (m < nb) v = a.sequences[pin * plane + ((long)bb * nb + m) * L + t];
+      else {
+        const int c = m - nb;
+        v = t == a.cur_len ? ix[c] % V : a.running_seq[pin * plane + ((long)bb * nb + ix[c] / V) * L + t];
+      }
+      a.sequences[pout * plane + i] = v;
+    }
+  }
+  if (threadIdx.x == 0) {
+    bool improvement = false, all_fin = true, all_hits = true;
+    for (int r = 0; r < a.batch; ++r) {
+      improvement = improvement || s_unsat[r];
+      all_fin = all_fin && s_all_fin[r];
+      all_hits = all_hits && s_all_hits[r];
+    }
+    const bool open_beam = !(all_fin && a.early_stopping == 1);
+    if (!(improvement && open_beam && !all_hits)) *a.done = 1;
+  }
 }
 
 // top-`keep` of each group of n contiguous values (n = beams * V), largest first, ties to the lower index.
@@ -273,17 +449,59 @@ extern "C" int emu_sample_tokens(const float* logits, int rows, int vocab, float
 
 
 extern "C" int emu_beam_topk(float* logits, const float* running_scores, int batch, int beams, int vocab, int keep, int ban_id,
-                             const long long* prev_tokens, int prev_len, float repetition_penalty, float* out_lp,
+                             const int32_t* prev_tokens, int prev_len, int prev_stride, float repetition_penalty,
+                             int penalty_on_logits, int no_repeat_ngram, const uint8_t* allowed, float* out_lp,
                              int* out_idx, emu_stream_t stream) {
   if (!logits || !out_lp || !out_idx || batch < 1 || beams < 1 || vocab < 1 || keep < 1 || (long)keep > (long)beams * vocab)
     return EMU_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = batch * beams;
+  int nl = 2;
+  const bool rep = prev_tokens && prev_len > 0 && repetition_penalty != 1.0f;
+  // greedy / sampling apply the processors to the raw logits, beam search to the log-probabilities (HF _sample vs _beam_search)
+  if (rep && penalty_on_logits) {
+    rep_penalty_kernel<<<rows, 128, 0, st>>>(logits, nullptr, prev_tokens, prev_len, prev_stride, vocab, repetition_penalty);
+    ++nl;
+  }
   logsoftmax_add_kernel<<<rows, 1024, 0, st>>>(logits, running_scores, vocab);
-  if (prev_tokens && prev_len > 0 && repetition_penalty != 1.0f)
-    rep_penalty_kernel<<<rows, 128, 0, st>>>(logits, running_scores, prev_tokens, prev_len, vocab, repetition_penalty);
-  if (ban_id >= 0) ban_token_kernel<<<rows, 1, 0, st>>>(logits, vocab, ban_id);
+  if (rep && !penalty_on_logits) {
+    rep_penalty_kernel<<<rows, 128, 0, st>>>(logits, running_scores, prev_tokens, prev_len, prev_stride, vocab, repetition_penalty);
+    ++nl;
+  }
+  if (prev_tokens && prev_len > 0 && no_repeat_ngram > 0) {
+    no_repeat_ngram_kernel<<<rows, 128, 0, st>>>(logits, prev_tokens, prev_len, prev_stride, vocab, no_repeat_ngram);
+    ++nl;
+  }
+  if (ban_id >= 0) {
+    ban_token_kernel<<<rows, 1, 0, st>>>(logits, vocab, ban_id);
+    ++nl;
+  }
+  if (allowed) {
+    allowed_mask_kernel<<<2 * kNumSMs, 256, 0, st>>>(logits, allowed, (long)rows * vocab);
+    ++nl;
+  }
   topk_group_kernel<<<batch, 1024, 0, st>>>(logits, (long)beams * vocab, keep, out_lp, out_idx);
-  count_launch(2 + (ban_id >= 0 ? 1 : 0));
+  count_launch(nl);
+  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+}
+
+extern "C" int emu_beam_step(const float* topk_lp, const int32_t* topk_idx, int batch, int beams, int vocab, int cur_len,
+                             int max_length, int eos_id, float fin_div, float best_div, int early_stopping,
+                             int32_t* running_seq, float* running_scores, int32_t* sequences, float* beam_scores,
+                             int32_t* is_finished, int32_t* fin_len, int32_t* unsat, int32_t* done, int32_t* next_tokens,
+                             int32_t* beam_src, emu_stream_t stream) {
+  if (!topk_lp || !topk_idx || !running_seq || !running_scores || !sequences || !beam_scores || !is_finished || !fin_len ||
+      !unsat || !done || !next_tokens || !beam_src)
+    return EMU_ERR_INVALID;
+  if (batch < 1 || batch > kBeamMaxRows || beams < 1 || beams > kBeamMaxBeams || cur_len < 0 || cur_len >= max_length)
+    return EMU_ERR_INVALID;
+  BeamStepArgs a;
+  a.topk_lp = topk_lp; a.topk_idx = topk_idx; a.batch = batch; a.beams = beams; a.vocab = vocab; a.cur_len = cur_len;
+  a.max_length = max_length; a.eos_id = eos_id; a.fin_div = fin_div; a.best_div = best_div; a.early_stopping = early_stopping;
+  a.running_seq = running_seq; a.running_scores = running_scores; a.sequences = sequences; a.beam_scores = beam_scores;
+  a.is_finished = is_finished; a.fin_len = fin_len; a.unsat = unsat; a.done = done; a.next_tokens = next_tokens;
+  a.beam_src = beam_src;
+  beam_step_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }

@@ -134,10 +134,10 @@ __global__ void __launch_bounds__(kTpThreads) tp_reduce_add_kernel(TpPeers peers
   }
 }
 
-// logits[b, r*Vl + v] = shard_r[b, v]
+// logits[b, r*Vl + v] = shard_r[b, v]   (Vl = ceil(V / n))
 __global__ void __launch_bounds__(kTpThreads) tp_gather_logits_kernel(TpPeers peers, int rank, int n,
                                                                       const float* __restrict__ shard, float* logits,
-                                                                      int B, int Vl, long n_pad, size_t data_off,
+                                                                      int B, int Vl, int V, long n_pad, size_t data_off,
                                                                       size_t slot_elems, size_t flag_off, size_t seq_off,
                                                                       int pdl) {
   if (pdl) {
@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(kTpThreads) tp_gather_logits_kernel(TpPeers pe
     const long j = i - (long)r * per;
     const int b = (int)(j / Vl), v = (int)(j - (long)b * Vl);
     const float x = (r == rank) ? __ldcg(shard + j) : __ldcg(local + data_off + ((size_t)parity * n + r) * slot_elems + j);
-    logits[(long)b * n * Vl + (long)r * Vl + v] = x;
+    const long col = (long)r * Vl + v;
+    if (col < V) logits[(long)b * V + col] = x;  // rows past V are the zero padding of the last shard
   }
 }
 
@@ -256,9 +257,9 @@ int tp_gather_logits(EmuEngine* e, const float* shard, float* logits, int B, int
   long n_pad = ((long)B * e->Vl + 3) / 4 * 4;  // the shard buffer is allocated with this padding
   TpPeers peers;
   for (int r = 0; r < 8; ++r) peers.base[r] = e->tp_peer[r];
-  int rank = e->tp_rank, n = e->tp_size, Vl = e->Vl;
+  int rank = e->tp_rank, n = e->tp_size, Vl = e->Vl, V = e->cfg.llm_vocab;
   size_t data_off = L.gat_off, slot = L.gat_slot, flag_off = L.flag_gat_off, seq_off = L.seq_off;
-  void* args[] = {&peers, &rank, &n, &shard, &logits, &B, &Vl, &n_pad, &data_off, &slot, &flag_off, &seq_off, &pdl};
+  void* args[] = {&peers, &rank, &n, &shard, &logits, &B, &Vl, &V, &n_pad, &data_off, &slot, &flag_off, &seq_off, &pdl};
   return launch_pdl((const void*)tp_gather_logits_kernel, dim3(tp_grid(n_pad)), args, pdl, st);
 }
 

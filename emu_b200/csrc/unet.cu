@@ -11,6 +11,8 @@
 // GEMM epilogues; attention is the flash kernel (head_dim 64).  The whole denoise step (≈1.5 k launches) is
 // captured once into a CUDA graph; per-step scalars (sigma, timestep, guidance) are read from device memory.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "diffusion_common.h"
@@ -42,11 +44,23 @@ struct UNetModel {
   bf16* kv_all_w = nullptr;
   long kv_all_n = 0;
   bool kv_all_ready = false;
+  // CFG-parallel denoising on a pair of GPUs (engine created with tp_size == 2): rank 0 runs the conditional half of the
+  // UNet batch, rank 1 the unconditional half, and the two noise predictions are swapped through NVLink peer memory
+  // inside the CFG + Euler kernel (cfg_exchange_euler_kernel below)
+  unsigned char* xch = nullptr;       // this rank's exchange buffer (cudaMalloc: IPC-exportable)
+  unsigned char* xch_peer = nullptr;  // the other rank's, mapped through CUDA IPC
 };
+
+// exchange buffer layout (bytes): [2 parities][kXchSlot] noise predictions | [kXchCtas] flags | [kXchCtas] sequence counters
+constexpr size_t kXchSlot = (size_t)4 << 20;  // 4 MiB per slot: batch * h * w <= 262144 latent pixels (16 samples of 128x128)
+constexpr int kXchCtas = 64;
+constexpr size_t kXchBytes = 2 * kXchSlot + 2 * kXchCtas * sizeof(unsigned);
 
 // ----------------------------------------------------------------------------------------------
 // configuration: builds the module tree and the key -> destination table
 // ----------------------------------------------------------------------------------------------
+static int unet_exchange_setup(EmuEngine* e, UNetModel* m);
+
 void reg_lin(SpecMap& specs, const std::string& p, Lin& l, int out, int in, bool bias) {
   l.out = out; l.in = in;
   specs[p + ".weight"] = {&l.w, LK_COPY, (long)out * in, out, in, 0, 0};
@@ -163,6 +177,9 @@ extern "C" int emu_unet_configure(EmuEngine* e, const EmuUNetConfig* cfg) {
   reg_conv(m->specs, "conv_out", m->conv_out, cfg->out_channels, boc[0], 3);
   m->step_params = (float*)e->dmalloc(8 * sizeof(float));
   if (!m->step_params) { delete m; return e->fail(EMU_ERR_NOMEM, "unet params alloc"); }
+  // engines created as a pair (tp_size == 2) set up the CFG-parallel exchange here: COLLECTIVE over both ranks
+  const int xrc = unet_exchange_setup(e, m);
+  if (xrc != EMU_OK) { unet_destroy(m); return xrc; }
   e->unet = m;
   return EMU_OK;
 }
@@ -193,6 +210,9 @@ __global__ void geglu_interleave_kernel(const bf16* __restrict__ src, bf16* dst,
 void unet_destroy(UNetModel* m) {
   if (!m) return;
   for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+  if (m->xch_peer) cudaIpcCloseMemHandle(m->xch_peer);
+  if (m->xch) cudaFree(m->xch);
+  cudaGetLastError();
   delete m;
 }
 
@@ -242,6 +262,109 @@ int unet_load_tensor(EmuEngine* e, const std::string& key, const bf16* src, cons
     m->warmed.clear();
   }
   return load_by_spec(e, e->unet->specs, "unet", key, src, shape, ndim, st);
+}
+
+// ----------------------------------------------------------------------------------------------
+// CFG-parallel: exchange of the noise prediction + CFG combine + Euler step in one kernel
+// ----------------------------------------------------------------------------------------------
+// Each CTA owns a contiguous slice of the NHWC noise prediction (ld = 8 channels -> one 16-byte word per latent pixel):
+//   1. pushes its slice of THIS rank's prediction into the peer's receive slot (16-byte NVLink stores),
+//   2. publishes a sequence flag with a system-scope release and spins (acquire) on the flag the peer wrote into OUR memory,
+//   3. combines cond (rank 0's prediction) and uncond (rank 1's) exactly like cfg_euler_kernel and applies the Euler step.
+// Both ranks hold the same fp32 latents and perform the same arithmetic in the same order, so their latents stay bitwise
+// identical — and identical to the single-GPU path.  Two receive slots (sequence parity): a rank can run at most one
+// exchange ahead of its peer.  All state is on the device, so the kernel is captured in the denoise CUDA graph.
+__global__ void __launch_bounds__(256) cfg_exchange_euler_kernel(float* lat, const bf16* __restrict__ eps_mine,
+                                                                 unsigned char* xch_local, unsigned char* xch_peer, int rank,
+                                                                 int B, int C, int HW, const float* __restrict__ params) {
+  __shared__ unsigned s_seq;
+  unsigned* flags_local = reinterpret_cast<unsigned*>(xch_local + 2 * kXchSlot);
+  unsigned* flags_peer = reinterpret_cast<unsigned*>(xch_peer + 2 * kXchSlot);
+  unsigned* seq_ptr = flags_local + kXchCtas + blockIdx.x;
+  if (threadIdx.x == 0) s_seq = *seq_ptr;
+  __syncthreads();
+  const unsigned seq = s_seq, parity = seq & 1u;
+  const long n_pix = (long)B * HW;
+  const long per = (n_pix + gridDim.x - 1) / gridDim.x;
+  const long p0 = (long)blockIdx.x * per, p1 = min(n_pix, p0 + per);
+  const uint4* mine = reinterpret_cast<const uint4*>(eps_mine);
+  uint4* out = reinterpret_cast<uint4*>(xch_peer + parity * kXchSlot);
+  for (long i = p0 + threadIdx.x; i < p1; i += blockDim.x) out[i] = mine[i];  // NVLink peer store
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags_peer + blockIdx.x), "r"(seq + 1) : "memory");
+    unsigned long long t0 = 0, now;
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags_local + blockIdx.x) : "memory");
+      if ((int)(v - (seq + 1)) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) {  // 20 s: the peer died — fail loudly instead of hanging the GPU
+        printf("emu_b200: CFG-parallel exchange timed out (rank %d)\n", rank);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  const uint4* theirs = reinterpret_cast<const uint4*>(xch_local + parity * kXchSlot);
+  const float dt = params[1] - params[0], g = params[2];
+  for (long i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+    const uint4 a = mine[i];
+    uint4 o;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "l"(theirs + i));
+    const uint4 cond = rank == 0 ? a : o, unc = rank == 0 ? o : a;
+    const uint32_t cw[4] = {cond.x, cond.y, cond.z, cond.w}, uw[4] = {unc.x, unc.y, unc.z, unc.w};
+    const long b = i / HW, p = i - b * HW;
+    for (int c = 0; c < C && c < 8; ++c) {
+      const float ec = (c & 1) ? bf16_hi(cw[c >> 1]) : bf16_lo(cw[c >> 1]);
+      const float eu = (c & 1) ? bf16_hi(uw[c >> 1]) : bf16_lo(uw[c >> 1]);
+      const float e = round_bf16(eu + round_bf16(g * round_bf16(ec - eu)));  // same rounding points as cfg_euler_kernel
+      lat[((long)b * C + c) * HW + p] += e * dt;
+    }
+  }
+  if (threadIdx.x == 0) *seq_ptr = seq + 1;
+}
+
+int engine_allgather_bytes(EmuEngine* e, const void* src, void* dst, size_t bytes);  // engine.cu (NCCL, host buffers)
+int engine_allreduce_min_int(EmuEngine* e, int* v);
+
+// collective over the pair: allocate, swap IPC handles, map the peer's buffer; leaves m->xch null when unavailable
+static int unet_exchange_setup(EmuEngine* e, UNetModel* m) {
+  if (e->tp_size != 2 || !e->nccl_comm) return EMU_OK;
+  const char* env = getenv("EMU_CFG_PARALLEL");
+  int ok = !(env && atoi(env) == 0);
+  unsigned char* buf = nullptr;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    if (cudaMalloc((void**)&buf, kXchBytes) != cudaSuccess) ok = 0;
+    if (ok && cudaMemset(buf, 0, kXchBytes) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, buf) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+  }
+  char all[2 * sizeof(cudaIpcMemHandle_t)];
+  if (engine_allgather_bytes(e, &mine, all, sizeof(mine)) != EMU_OK) return e->fail(EMU_ERR_NCCL, "CFG-parallel handle exchange failed");
+  void* peer = nullptr;
+  if (ok) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all + (size_t)(1 - e->tp_rank) * sizeof(h), sizeof(h));
+    if (cudaIpcOpenMemHandle(&peer, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  }
+  int all_ok = ok;
+  if (engine_allreduce_min_int(e, &all_ok) != EMU_OK) return e->fail(EMU_ERR_NCCL, "CFG-parallel setup reduce failed");
+  if (!all_ok) {
+    if (peer) cudaIpcCloseMemHandle(peer);
+    if (buf) cudaFree(buf);
+    return EMU_OK;  // both ranks fall back to running the whole CFG batch locally
+  }
+  m->xch = buf;
+  m->xch_peer = (unsigned char*)peer;
+  return EMU_OK;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -605,8 +728,18 @@ extern "C" int emu_denoise_step(EmuEngine* e, float* latents, float sigma, float
   UNetModel* m = e->unet;
   cudaStream_t st = (cudaStream_t)stream;
   const int cfg = guidance > 1.0f ? 1 : 0;  // do_classifier_free_guidance (Emu2/emu/diffusion.py:97)
-  const int B2 = cfg ? 2 * B : B;
+  // CFG-parallel pair: this rank runs only its half of the [cond; uncond] UNet batch (SURVEY.md §8e "UNet, batch 1")
+  const int split = (cfg && m->xch && m->xch_peer && e->tp_size == 2) ? 1 : 0;
+  if (split && (size_t)B * h * w * 16 > kXchSlot) return e->fail(EMU_ERR_INVALID, "batch too large for the CFG-parallel exchange");
+  if (split && (m->cfg.out_channels > 8)) return e->fail(EMU_ERR_UNSUPPORTED, "CFG-parallel exchange: out_channels > 8");
+  const int B2 = (cfg && !split) ? 2 * B : B;
   const int Cin = m->cfg.in_channels, Cp = m->conv_in.cin;
+  const int cd = m->cfg.cross_attention_dim;
+  if (split) {  // the caller passes the full [2B, ...] conditioning on both ranks (same API); take this rank's half
+    ctxv = (const bf16*)ctxv + (size_t)e->tp_rank * B * L * cd;
+    if (text_embeds) text_embeds = (const bf16*)text_embeds + (size_t)e->tp_rank * B * cd;
+    if (time_ids) time_ids = time_ids + (size_t)e->tp_rank * B * 6;
+  }
   // per-step scalars go through device memory so the captured graph is step-independent
   float hp[4] = {sigma, sigma_next, guidance, timestep};
   if (cudaMemcpyAsync(m->step_params, hp, sizeof(hp), cudaMemcpyHostToDevice, st) != cudaSuccess)
@@ -619,16 +752,25 @@ extern "C" int emu_denoise_step(EmuEngine* e, float* latents, float sigma, float
     BUF(eps, "eps", (size_t)B2 * h * w * 8);
     BUF(tdev, "t_dev_big", (size_t)B2 * 2 + 8);
     EMU_TRY(fill_float((float*)tdev, B2, m->step_params + 3, s));
-    EMU_TRY(cfg_prepare(latents, xin, B, Cin, h * w, Cp, m->step_params, cfg ? 2 : 1, s));
+    EMU_TRY(cfg_prepare(latents, xin, B, Cin, h * w, Cp, m->step_params, (cfg && !split) ? 2 : 1, s));
     EMU_TRY(unet_core(c, m, xin, (const float*)tdev, (const bf16*)ctxv, L, (const bf16*)text_embeds, time_ids, h, w, eps));
-    EMU_TRY(cfg_euler(latents, eps, B, m->cfg.out_channels, h * w, 8, m->step_params, cfg, s));
+    if (split) {
+      const long n_pix = (long)B * h * w;
+      int grid = (int)((n_pix + 2047) / 2048);
+      if (grid > kXchCtas) grid = kXchCtas;
+      cfg_exchange_euler_kernel<<<grid, 256, 0, s>>>(latents, eps, m->xch, m->xch_peer, e->tp_rank, B, m->cfg.out_channels,
+                                                     h * w, m->step_params);
+      if (cudaGetLastError() != cudaSuccess) return e->fail(EMU_ERR_CUDA, "CFG-parallel exchange launch failed");
+    } else {
+      EMU_TRY(cfg_euler(latents, eps, B, m->cfg.out_channels, h * w, 8, m->step_params, cfg, s));
+    }
     *nl = c.nl + 3;
     return EMU_OK;
   };
   const char* no_graph = getenv("EMU_NO_GRAPH");
   const bool use_graph = e->use_graphs && !(no_graph && no_graph[0] == '1');
   auto key = std::make_tuple((const void*)latents, (const void*)ctxv, (const void*)text_embeds, (const void*)time_ids, B, h,
-                             w * 2 + cfg, L);
+                             w * 4 + cfg + 2 * split, L);
   auto it = m->graphs.find(key);
   if (use_graph && it != m->graphs.end()) {
     if (cudaGraphLaunch(it->second, st) != cudaSuccess) return e->fail(EMU_ERR_CUDA, "denoise graph launch failed");

@@ -112,6 +112,14 @@ class Emu:
     def generate(self, samples, do_sample=False, num_beams=5, max_new_tokens=50, min_length=1, top_p=0.9,
                  repetition_penalty=1.0, length_penalty=0.0, num_captions=1, temperature=1, penalty_alpha=None,
                  top_k=None, no_repeat_ngram_size=None, **kwargs):
+        # knobs the reference forwards to HF generate (modeling_emu.py:162-179) that this engine does not implement must not
+        # be accepted and silently dropped
+        if penalty_alpha is not None:
+            raise NotImplementedError("contrastive search (penalty_alpha) is not supported")
+        if num_captions != 1:
+            raise NotImplementedError("num_captions (num_return_sequences) > 1 is not supported")
+        if do_sample and num_beams > 1:
+            raise NotImplementedError("beam-sample (do_sample=True with num_beams > 1) is not supported: pass num_beams=1")
         prompt = samples["prompt"] if "prompt" in samples else self.prompt
         if isinstance(prompt, str):
             prompt = [prompt]
@@ -119,13 +127,15 @@ class Emu:
         out = self.generate_from_ids(input_ids, attention_mask, image=samples.get("image"), do_sample=do_sample,
                                      num_beams=num_beams, max_new_tokens=max_new_tokens, min_length=min_length,
                                      top_p=top_p, repetition_penalty=repetition_penalty, length_penalty=length_penalty,
-                                     temperature=temperature, top_k=top_k, **kwargs)
+                                     temperature=temperature, top_k=top_k, no_repeat_ngram_size=no_repeat_ngram_size,
+                                     **kwargs)
         return self.decoder.tokenizer.batch_decode(out, skip_special_tokens=True)
 
     @torch.no_grad()
     def generate_from_ids(self, input_ids, attention_mask, image=None, image_token_id=32003, do_sample=False,
                           num_beams=5, max_new_tokens=50, min_length=1, top_p=0.9, repetition_penalty=1.0,
-                          length_penalty=0.0, temperature=1, top_k=None, eos_token_id=None, pad_token_id=None, **kwargs):
+                          length_penalty=0.0, temperature=1, top_k=None, eos_token_id=None, pad_token_id=None,
+                          no_repeat_ngram_size=None, prefix_allowed_tokens_fn=None, **kwargs):
         tok = self.decoder.tokenizer
         eos = eos_token_id if eos_token_id is not None else tok.eos_token_id
         pad = pad_token_id if pad_token_id is not None else tok.pad_token_id
@@ -137,12 +147,15 @@ class Emu:
         if do_sample:
             return generation.sample_search(self.engine, embeds, attention_mask, max_new_tokens, eos, pad,
                                             min_length=min_length, temperature=temperature, top_k=top_k, top_p=top_p)
-        if num_beams == 1:
+        constrained = bool(no_repeat_ngram_size) or prefix_allowed_tokens_fn is not None or repetition_penalty != 1.0
+        if num_beams == 1 and not constrained:
             return generation.greedy_search(self.engine, embeds, attention_mask, max_new_tokens, eos, pad,
                                             min_length=min_length)
+        # beam search with one beam IS greedy search with the logits processors applied
         return generation.beam_search(self.engine, embeds, attention_mask, num_beams, max_new_tokens, eos, pad,
                                       min_length=min_length, length_penalty=length_penalty,
-                                      repetition_penalty=repetition_penalty)
+                                      repetition_penalty=repetition_penalty, no_repeat_ngram_size=no_repeat_ngram_size or 0,
+                                      prefix_allowed_tokens_fn=prefix_allowed_tokens_fn)
 
     @torch.no_grad()
     def generate_image(self, text: List[str], image: Optional[torch.Tensor] = None,
@@ -158,15 +171,23 @@ class Emu:
         """Cache-equivalent form of the reference's 32 full re-forwards (modeling_emu.py:205-243): prefill the
         prompt ending in [IMG], then feed stu_regress_head(h_last) back as the next input embedding."""
         input_ids, attention_mask = input_ids.to(self.device_), attention_mask.to(self.device_)
-        if bool((attention_mask[:, -1] == 0).any()):
-            raise NotImplementedError("right-padded batches of unequal length: run generate_image one prompt at a time")
+        ragged = bool((attention_mask[:, -1] == 0).any())
+        if ragged:
+            # The tokenizer pads on the RIGHT here (modeling_llama.py:139) and the reference appends the regressed
+            # embeddings before the pads of each row (it re-tokenises the growing strings, modeling_emu.py:205-213), so every
+            # row is an independent sequence at positions 0..len-1.  Same thing in cache form: rotate each row's pads to the
+            # left and let the engine number positions from the first real token (hf_positions).
+            n_pad = (attention_mask == 0).sum(1)
+            idx = (torch.arange(input_ids.shape[1], device=self.device_)[None, :] - n_pad[:, None]) % input_ids.shape[1]
+            input_ids, attention_mask = input_ids.gather(1, idx), attention_mask.gather(1, idx)
         B = input_ids.shape[0]
         embeds = self.engine.llm_embed(input_ids)
         if image is not None:
             f = self.encode_image(image.to(torch.bfloat16))
-            embeds[input_ids == image_token_id] = f.reshape(-1, f.shape[-1])
+            embeds[input_ids == image_token_id] = f.reshape(-1, f.shape[-1])  # row-major order is kept by the rotation
         self.engine.llm_reset()
-        hidden, _ = self.engine.llm_prefill(embeds, attention_mask, hf_positions=False, want_hidden=True, want_logits=False)
+        hidden, _ = self.engine.llm_prefill(embeds, attention_mask, hf_positions=ragged, want_hidden=True,
+                                            want_logits=False)
         last = hidden[:, -1, :].contiguous()
         outs = torch.empty(B, self.n_causal, self.hidden, dtype=torch.bfloat16, device=self.device_)
         hbuf = torch.empty(B, self.hidden, dtype=torch.bfloat16, device=self.device_)

@@ -1,28 +1,37 @@
 """Config dataclasses with the reference's field names and defaults (Emu2/emu/conf/emu_conf.py:7-40)."""
 import json
 import os.path as osp
-from dataclasses import dataclass, field, make_dataclass
+from dataclasses import dataclass
 from typing import Optional
 
 
-# Field names and defaults are the reference's (Emu2/emu/conf/emu_conf.py:7-40) so that existing call sites and JSON configs keep
-# working; only the fields marked "engine" influence this implementation, the others are accepted and must keep their
-# published values (checked in EmuModel.__init__).
-_VISION_FIELDS = [
-    # (name, type, default)                                        # role
-    ("eva_model_name", str, "eva-clip-4b-14-x"),                   # label only
-    ("image_size", int, 448), ("patch_size", int, 14),             # engine: 32 x 32 patches + CLS
-    ("width", int, 1792), ("layers", int, 64), ("head_width", int, 112),   # engine: 16 heads of 112
-    ("mlp_ratio", float, 8.571428571428571),                       # engine: int(1792 * ratio) = 15360
-    ("qkv_bias", bool, True),                                      # engine: q/v bias, k bias is zero
-    ("drop_path_rate", float, 0.), ("init_value", Optional[float], None), ("patch_dropout", float, 0.),   # training only
-    ("rope", bool, False), ("global_average_pool", bool, False), ("xattn", bool, False),
-    ("postnorm", bool, True),                                      # engine: x + LN(f(x)) blocks, no final norm
-    ("pt_hw_seq_len", int, 16), ("intp_freq", bool, False), ("naiveswiglu", bool, False), ("subln", bool, False),
-    ("n_query", int, 64), ("v_query", int, 64),                    # engine: pooled tokens per image / video frame
-]
-CLIPVisionCfg = make_dataclass("CLIPVisionCfg", [(n, t, field(default=d)) for n, t, d in _VISION_FIELDS])
-CLIPVisionCfg.__doc__ = "EVA-CLIP tower hyper-parameters (reference field names and defaults)."
+@dataclass
+class CLIPVisionCfg:
+    """EVA-CLIP tower hyper-parameters: the reference's field names and defaults (Emu2/emu/conf/emu_conf.py:7-33) so that
+    existing call sites and JSON configs keep working.  The engine reads image_size / patch_size / width / layers / head_width
+    / mlp_ratio / postnorm / n_query / v_query; the training-only and variant switches are accepted and must keep their
+    published values (checked in EmuModel.__init__)."""
+    eva_model_name: str = "eva-clip-4b-14-x"
+    image_size: int = 448
+    patch_size: int = 14
+    width: int = 1792
+    layers: int = 64
+    head_width: int = 112
+    mlp_ratio: float = 8.571428571428571   # int(1792 * ratio) = 15360
+    qkv_bias: bool = True                   # q / v bias, the k bias is zero
+    drop_path_rate: float = 0.
+    init_value: Optional[float] = None
+    patch_dropout: float = 0.
+    rope: bool = False
+    global_average_pool: bool = False
+    xattn: bool = False
+    postnorm: bool = True                   # x + LN(f(x)) blocks, no final norm
+    pt_hw_seq_len: int = 16
+    intp_freq: bool = False
+    naiveswiglu: bool = False
+    subln: bool = False
+    n_query: int = 64                       # pooled tokens per image
+    v_query: int = 64                       # ... per video frame
 
 
 @dataclass

@@ -24,9 +24,8 @@ USER_TOKEN, ASSISTANT_TOKEN = "[USER]", "[ASSISTANT]"
 DEFAULT_IMG_PLACEHOLDER, DEFAULT_VID_PLACEHOLDER = "[<IMG_PLH>]", "[<VID_PLH>]"
 
 # ---- system prompts of the chat pipeline (plain / grounding) ----
-_ASSISTANT_PREFIX = "You are a helpful assistant, dedicated to "
-SYSTEM_MESSAGE = _ASSISTANT_PREFIX + "delivering comprehensive and meticulous responses."
-GROUND_SYSTEM_MESSAGE = _ASSISTANT_PREFIX + "provide concise and efficient answers."
+SYSTEM_MESSAGE = "You are a helpful assistant, dedicated to delivering comprehensive and meticulous responses."
+GROUND_SYSTEM_MESSAGE = "You are a helpful assistant, dedicated to provide concise and efficient answers."
 
 
 def special_token_list(instruct=False, quantized_size=256):

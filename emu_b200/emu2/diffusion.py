@@ -5,11 +5,18 @@ num_inference_steps, guidance_scale, crop_info, original_size)`` returning an
 ``EmuVisualGenerationPipelineOutput(image, nsfw_content_detected)`` — with the arithmetic on the B200 engine:
 prompt encoding through ``EmuModel.generate_image`` / ``encode_image``, the denoise loop as one CUDA-graphed
 ``emu_denoise_step`` per iteration (cat + scale_model_input + UNet + CFG + Euler fused), VAE decode on device.
-The safety checker is a post-filter outside the generate path: ``nsfw_content_detected`` is None.
+
+Safety stage.  The reference runs diffusers' ``StableDiffusionSafetyChecker`` on the decoded image and blanks flagged ones
+(Emu2/emu/diffusion.py:154-166, 236-249).  That CLIP classifier is third-party and not part of this engine, so it is NOT
+silently dropped: pass ``safety_checker=callable(images_uint8 [B,H,W,3] numpy) -> (images, [bool])`` to keep the stage
+(e.g. the diffusers module wrapped by the caller), or construct with the default ``safety_checker=None`` and get a
+``UserWarning`` the first time an image is returned unfiltered (``nsfw_content_detected`` is then None, which is what the
+reference reports for a pipeline built without a checker).  ``requires_safety_checker=True`` makes a missing hook an error.
 """
 import json
 import os
 import os.path as osp
+import warnings
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -84,7 +91,12 @@ def vae_config_from_json(cfg: dict) -> "_lib.EmuVAEConfig":
 class EmuVisualGeneration:
     def __init__(self, multimodal_encoder: EmuModel, scheduler: EulerDiscreteScheduler, unet_config: dict,
                  vae_config: Optional[dict] = None, eva_size=EVA_IMAGE_SIZE, eva_mean=OPENAI_DATASET_MEAN,
-                 eva_std=OPENAI_DATASET_STD, **kwargs):
+                 eva_std=OPENAI_DATASET_STD, safety_checker=None, requires_safety_checker: bool = False, **kwargs):
+        if requires_safety_checker and safety_checker is None:
+            raise ValueError("requires_safety_checker=True but no safety_checker callable was given (the reference's "
+                             "StableDiffusionSafetyChecker is third-party and not bundled with this engine)")
+        self.safety_checker = safety_checker
+        self._warned_unfiltered = False
         self.multimodal_encoder = multimodal_encoder
         self.engine = multimodal_encoder.engine
         self.scheduler = scheduler
@@ -111,12 +123,33 @@ class EmuVisualGeneration:
     def load_state_dict(self, sd, strict=True):
         """Keys as saved by the reference pipeline: multimodal_encoder.*, unet.*, vae.* (safety_checker.* ignored)."""
         for k, v in sd.items():
-            if k.startswith("safety_checker.") or k.endswith("rotary_emb.inv_freq"):
+            if k.startswith("safety_checker."):
+                self._note_checker_weights()
+                continue
+            if k.endswith("rotary_emb.inv_freq"):
                 continue
             if k.startswith("vae.") and (self.vae_config is None or ".encoder." in k or k.startswith("vae.quant_conv")):
                 continue  # only the decoder half is on the generate path
             self.engine.load_tensor(k, v)
         return self
+
+    def _note_checker_weights(self):
+        if self.safety_checker is None and not self._warned_unfiltered:
+            warnings.warn("the checkpoint carries safety_checker.* weights but this pipeline was built without a "
+                          "safety_checker hook: images are returned UNFILTERED (pass safety_checker=... to keep the "
+                          "reference's post-filter, Emu2/emu/diffusion.py:236-249)", UserWarning, stacklevel=3)
+            self._warned_unfiltered = True
+
+    def run_safety_checker(self, images_u8: np.ndarray):
+        """Emu2/emu/diffusion.py:236-249: returns (images, has_nsfw list) through the hook, or (images, None) without one."""
+        if self.safety_checker is None:
+            if not self._warned_unfiltered:
+                warnings.warn("EmuVisualGeneration was built without a safety_checker: the image is returned unfiltered "
+                              "and nsfw_content_detected is None", UserWarning, stacklevel=3)
+                self._warned_unfiltered = True
+            return images_u8, None
+        images_u8, flags = self.safety_checker(images_u8)
+        return images_u8, [bool(f) for f in flags]
 
     # ---- Emu2/emu/diffusion.py:77-166 ----
     @torch.no_grad()
@@ -134,8 +167,10 @@ class EmuVisualGeneration:
                                original_size, generator=generator, latents=latents)
         if output_type == "latent":
             return latents
-        images = self.decode_latents_pil(latents)
-        return EmuVisualGenerationPipelineOutput(image=images[0], nsfw_content_detected=None)
+        u8 = self.decode_latents_uint8(latents)
+        u8, flags = self.run_safety_checker(u8)
+        return EmuVisualGenerationPipelineOutput(image=Image.fromarray(u8[0]),
+                                                 nsfw_content_detected=None if flags is None else flags[0])
 
     __call__ = forward
 
@@ -200,12 +235,14 @@ class EmuVisualGeneration:
         img = self.engine.vae_decode(z)  # [B, H, W, 3] fp32 in [0, 1]
         return img.cpu().numpy()
 
-    def decode_latents_pil(self, latents: torch.Tensor):
-        """decode_latents + numpy_to_pil with the uint8 conversion on the device (emu_image_to_uint8): a quarter of the
-        device->host bytes, bit-identical pixels."""
+    def decode_latents_uint8(self, latents: torch.Tensor) -> np.ndarray:
+        """decode_latents + numpy_to_pil's uint8 conversion on the device (emu_image_to_uint8): a quarter of the
+        device->host bytes, bit-identical pixels.  [B, H, W, 3] uint8."""
         z = (latents.float() / self.vae_scaling).to(torch.bfloat16).contiguous()
-        u8 = _lib.op_image_to_uint8(self.engine.vae_decode(z)).cpu().numpy()
-        return [Image.fromarray(im) for im in u8]
+        return _lib.op_image_to_uint8(self.engine.vae_decode(z)).cpu().numpy()
+
+    def decode_latents_pil(self, latents: torch.Tensor):
+        return [Image.fromarray(im) for im in self.decode_latents_uint8(latents)]
 
     def numpy_to_pil(self, images: np.ndarray):
         if images.ndim == 3:
@@ -215,14 +252,16 @@ class EmuVisualGeneration:
 
     # ---- Emu2/emu/diffusion.py:251-318 ----
     @classmethod
-    def from_config(cls, config_path: str, llama_config_path: Optional[str] = None, tokenizer=None, **kwargs):
+    def from_config(cls, config_path: str, llama_config_path: Optional[str] = None, tokenizer=None, safety_checker=None,
+                    requires_safety_checker: bool = False, **kwargs):
         unet_cfg = json.load(open(osp.join(config_path, "unet", "config.json")))
         vae_p = osp.join(config_path, "vae", "config.json")
         vae_cfg = json.load(open(vae_p)) if osp.exists(vae_p) else None
         sched = EulerDiscreteScheduler.from_config(osp.join(config_path, "scheduler"))
         tcfg = TextDecoderCfg(llama_config_path=llama_config_path) if llama_config_path else TextDecoderCfg()
         enc = EmuModel(CLIPVisionCfg(), tcfg, tokenizer=tokenizer, **kwargs)
-        return cls(multimodal_encoder=enc, scheduler=sched, unet_config=unet_cfg, vae_config=vae_cfg)
+        return cls(multimodal_encoder=enc, scheduler=sched, unet_config=unet_cfg, vae_config=vae_cfg,
+                   safety_checker=safety_checker, requires_safety_checker=requires_safety_checker)
 
     @classmethod
     def from_pretrained(cls, model_path: str, config_path: Optional[str] = None, dtype=torch.bfloat16,
@@ -234,6 +273,7 @@ class EmuVisualGeneration:
 
         def keep(k):  # same filter as load_state_dict: no safety checker, only the decoder half of the VAE
             if k.startswith("safety_checker."):
+                ins._note_checker_weights()
                 return None
             if k.startswith("vae.") and (ins.vae_config is None or ".encoder." in k or k.startswith("vae.quant_conv")):
                 return None

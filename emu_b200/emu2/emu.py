@@ -139,6 +139,8 @@ class EmuModel:
         pad = pad_token_id if pad_token_id is not None else tok.pad_token_id
         if penalty_alpha is not None:
             raise NotImplementedError("contrastive search (penalty_alpha) is not supported")
+        if do_sample and num_beams > 1:
+            raise NotImplementedError("beam-sample (do_sample=True with num_beams > 1) is not supported: pass num_beams=1")
         input_ids = input_ids.to(self.device_)
         attention_mask = attention_mask.to(self.device_)
         text_embeds = self.engine.llm_embed(input_ids)  # [B, N, H]

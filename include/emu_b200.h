@@ -176,15 +176,33 @@ int emu_preprocess_image(const uint8_t* rgb_hwc, int H, int W, int out_h, int ou
 int emu_image_to_uint8(const float* image01, uint8_t* out, int64_t n, emu_stream_t s);
 
 /* Device-side beam-search step.  Replaces, inside HF GenerationMixin._beam_search as driven by
- * Emu2/emu/emu.py:213-229 (num_beams=5, length_penalty=-1), the vocabulary-wide work of one step:
- *   log_softmax(logits) -> RepetitionPenaltyLogitsProcessor -> MinLength EOS ban -> + running beam score ->
- *   topk(2*beams) over the flattened [beams*vocab] scores of every batch row.
+ * Emu2/emu/emu.py:213-229 (num_beams=5, length_penalty=-1) and Emu1/models/modeling_emu.py:162-179, the vocabulary-wide
+ * work of one step:
+ *   log_softmax(logits) -> RepetitionPenaltyLogitsProcessor -> NoRepeatNGramLogitsProcessor -> MinLength EOS ban ->
+ *   PrefixConstrainedLogitsProcessor -> + running beam score -> topk(2*beams) over the flattened [beams*vocab] scores of
+ *   every batch row.
  * logits [batch*beams, vocab] fp32 is used as scratch (overwritten); running_scores [batch*beams] may be NULL;
- * prev_tokens [batch*beams, prev_len] int64 (may be NULL); ban_id < 0 disables the ban.  Outputs out_lp / out_idx
- * [batch, keep]: scores (largest first) and flat indices beam*vocab + token. */
+ * prev_tokens: DEVICE int32 rows of the tokens generated so far, row r at prev_tokens + r*prev_stride, prev_len valid (may be
+ * NULL); penalty_on_logits = 1 applies the repetition penalty to the raw logits (HF greedy / sampling) instead of the
+ * log-probabilities (HF beam search); no_repeat_ngram = n-gram size (0 = off); allowed [batch*beams, vocab] bytes, 0 = banned
+ * (the mask prefix_allowed_tokens_fn produces, Emu1/mm_eval/models/emu.py:97-109) or NULL; ban_id < 0 disables the EOS ban.
+ * Outputs out_lp / out_idx [batch, keep]: scores (largest first) and flat indices beam*vocab + token. */
 int emu_beam_topk(float* logits, const float* running_scores, int batch, int beams, int vocab, int keep, int ban_id,
-                  const long long* prev_tokens, int prev_len, float repetition_penalty, float* out_lp, int* out_idx,
-                  emu_stream_t s);
+                  const int32_t* prev_tokens, int prev_len, int prev_stride, float repetition_penalty, int penalty_on_logits,
+                  int no_repeat_ngram, const uint8_t* allowed, float* out_lp, int* out_idx, emu_stream_t s);
+
+/* The hypothesis bookkeeping of the same HF step (running beams, finished beams, early-stopping heuristic) on the device, so
+ * that a beam-search step never synchronises with the host: consumes emu_beam_topk's outputs, updates the state arrays in
+ * place and writes the next step's inputs for emu_llm_decode (next_tokens -> token_ids, beam_src -> beam_src_idx).
+ * State (all DEVICE, caller-allocated): running_seq / sequences [2][batch, beams, max_length] int32 (two planes, the live one
+ * is plane cur_len & 1 before the call and (cur_len + 1) & 1 after), running_scores / beam_scores [batch, beams] fp32,
+ * is_finished / fin_len [batch, beams] int32, unsat [batch] int32 (initially 1), done [1] int32 (initially 0; once set every
+ * later call is a no-op).  fin_div = (cur_len + 1) ** length_penalty, best_div = best_len ** length_penalty (host scalars);
+ * early_stopping: 0 False, 1 True, 2 "never".  batch <= 8, beams <= 16. */
+int emu_beam_step(const float* topk_lp, const int32_t* topk_idx, int batch, int beams, int vocab, int cur_len, int max_length,
+                  int eos_id, float fin_div, float best_div, int early_stopping, int32_t* running_seq, float* running_scores,
+                  int32_t* sequences, float* beam_scores, int32_t* is_finished, int32_t* fin_len, int32_t* unsat,
+                  int32_t* done, int32_t* next_tokens, int32_t* beam_src, emu_stream_t s);
 
 /* Device-side sampling step: HF warper order temperature -> top-k (0 = off) -> top-p (1 = off) and one
  * multinomial draw per row, as GenerationMixin does for do_sample=True (Emu2/emu/chat.py:46-57 forwards the knobs).

@@ -8,6 +8,11 @@ import torch
 from emu_b200 import checkpoint as ck
 
 
+class _Payload:  # a global the weights_only unpickler rejects
+    def __init__(self):
+        self.t = torch.ones(2)
+
+
 class Sink:
     def __init__(self):
         self.got = {}
@@ -70,3 +75,46 @@ def test_lora_merge(tmp_path):
     ck.load_into(s, str(tmp_path / "lora.bin"), lora=True)
     assert set(s.got) == {"decoder.q_proj.weight", "decoder.norm.weight"}
     assert torch.allclose(s.got["decoder.q_proj.weight"], W + (16.0 / 2) * (B @ A), atol=1e-5)
+
+
+def test_lora_merge_legacy_key_layout(tmp_path):
+    """2023-era peft (the Emu1 instruct checkpoint, Emu1/inference.py:40-57): the base weight is `<stem>.weight` right next to
+    `<stem>.lora_A.default.weight` / `lora_B.default.weight`, in either order; it must be merged, never passed through."""
+    g = torch.Generator().manual_seed(2)
+    W, A, B = torch.randn(8, 8, generator=g), torch.randn(4, 8, generator=g), torch.randn(8, 4, generator=g)
+    W2 = torch.randn(8, 8, generator=g)
+    for order in (0, 1):
+        items = [("base_model.model.decoder.q_proj.weight", W), ("base_model.model.decoder.q_proj.lora_A.default.weight", A),
+                 ("base_model.model.decoder.q_proj.lora_B.default.weight", B), ("base_model.model.decoder.k_proj.weight", W2),
+                 ("base_model.model.decoder.norm.weight", torch.ones(8))]
+        if order:
+            items = items[1:3] + items[:1] + items[3:]
+        f = str(tmp_path / ("legacy%d.bin" % order))
+        torch.save(dict(items), f)
+        s = Sink()
+        ck.load_into(s, f, lora=True)
+        assert set(s.got) == {"decoder.q_proj.weight", "decoder.k_proj.weight", "decoder.norm.weight"}
+        assert torch.allclose(s.got["decoder.q_proj.weight"], W + (16.0 / 4) * (B @ A), atol=1e-5)
+        assert torch.equal(s.got["decoder.k_proj.weight"], W2)     # no adapter: untouched
+    # an adapter whose base weight never arrives is an error, not a silent drop
+    torch.save({"x.lora_A.default.weight": A, "x.lora_B.default.weight": B}, str(tmp_path / "orphan.bin"))
+    with pytest.raises(KeyError):
+        ck.load_into(Sink(), str(tmp_path / "orphan.bin"), lora=True)
+
+
+def test_unsafe_pickle_needs_opt_in(tmp_path):
+    """A .bin that is not a plain tensor dict must NOT be re-loaded with the unrestricted unpickler behind the caller's back."""
+    torch.save({"w": torch.ones(2), "meta": _Payload()}, str(tmp_path / "odd.bin"))
+    with pytest.raises(Exception):
+        list(ck.iter_checkpoint(str(tmp_path / "odd.bin")))
+    got = dict(ck.iter_checkpoint(str(tmp_path / "odd.bin"), allow_pickle=True))   # explicit opt-in still works
+    assert set(got) == {"w", "meta"}
+
+
+def test_missing_shard_is_an_error(tmp_path):
+    from safetensors.torch import save_file
+    sd = _sd()
+    save_file({k: sd[k] for k in list(sd)[:2]}, str(tmp_path / "a.safetensors"))
+    json.dump({"weight_map": {"x": "a.safetensors", "y": "b.safetensors"}}, open(tmp_path / "model.safetensors.index.json", "w"))
+    with pytest.raises(FileNotFoundError):
+        ck.load_into(Sink(), str(tmp_path))

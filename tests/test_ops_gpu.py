@@ -241,33 +241,81 @@ def test_gemv_rope_qkv(cuda):
         assert O.rel_err(vc[b, :, int(pos[b])].cpu(), v[b]) < TOL_BF16
 
 
-@pytest.mark.parametrize("Bt,nb,V,prev_len,ban", [(1, 5, 32272, 0, -1), (2, 3, 32272, 7, 2), (1, 1, 1000, 3, -1), (3, 4, 517, 0, 5)])
-def test_beam_topk(cuda, Bt, nb, V, prev_len, ban):
-    """emu_beam_topk vs the torch formulation of one HF _beam_search step (log_softmax -> repetition penalty -> EOS ban
-    -> + running score -> topk(2*beams) over beams*vocab)."""
+@pytest.mark.parametrize("Bt,nb,V,prev_len,ban,raw,ngram,mask", [
+    (1, 5, 32272, 0, -1, False, 0, False), (2, 3, 32272, 7, 2, False, 0, False), (1, 1, 1000, 3, -1, True, 0, False),
+    (3, 4, 517, 0, 5, False, 0, True), (2, 3, 517, 9, -1, False, 2, False), (1, 2, 300, 12, 1, True, 3, True)])
+def test_beam_topk(cuda, Bt, nb, V, prev_len, ban, raw, ngram, mask):
+    """emu_beam_topk vs the torch formulation of one HF _beam_search step (log_softmax -> repetition penalty -> no-repeat
+    n-gram -> EOS ban -> prefix-allowed mask -> + running score -> topk(2*beams) over beams*vocab), incl. the greedy /
+    sampling order (penalty on the raw logits)."""
     from emu_b200 import _lib
+    from test_generation_cpu import torch_beam_topk
     g = torch.Generator().manual_seed(70)
     logits = torch.randn(Bt * nb, V, generator=g) * 3
     running = torch.randn(Bt, nb, generator=g)
     running[:, -1] = -1e9 if nb > 1 else running[:, -1]
-    prev = torch.randint(0, V, (Bt * nb, prev_len), generator=g) if prev_len else None
+    L = prev_len + 5
+    prev = torch.randint(0, 40 if ngram else V, (Bt * nb, L), generator=g, dtype=torch.int32) if prev_len else None
     if prev is not None:
-        prev[:, -1] = prev[:, 0]  # a duplicate: the penalty must apply once
+        prev[:, prev_len - 1] = prev[:, 0]  # a duplicate: the penalty must apply once; also closes a repeated n-gram
+    allowed = (torch.rand(Bt * nb, V, generator=g) < 0.6).to(torch.uint8) if mask else None
     keep, pen = 2 * nb, 1.3
-    lp = torch.log_softmax(logits, -1)
-    if prev is not None:
-        sc = torch.gather(lp, 1, prev)
-        sc = torch.where(sc < 0, sc * pen, sc / pen)
-        lp = lp.scatter(1, prev, sc)
-    if ban >= 0:
-        lp[:, ban] = float("-inf")
-    lp = lp.view(Bt, nb, V) + running[:, :, None]
-    ref_v, ref_i = torch.topk(lp.view(Bt, nb * V), k=keep)
+    ref_v, ref_i = torch_beam_topk(logits, running, Bt, nb, keep, ban, prev, prev_len, pen, raw, ngram, allowed)
     out_v, out_i = _lib.op_beam_topk(logits.cuda(), running.cuda(), Bt, nb, keep, ban_id=ban,
-                                     prev_tokens=None if prev is None else prev.cuda(), repetition_penalty=pen)
+                                     prev_tokens=None if prev is None else prev.cuda(), prev_len=prev_len,
+                                     repetition_penalty=pen, penalty_on_logits=raw, no_repeat_ngram=ngram,
+                                     allowed=None if allowed is None else allowed.cuda())
     real = ref_v > -1e8  # candidates of a dead (-1e9) beam tie at fp32 resolution: order is don't-care
     assert torch.allclose(out_v.cpu()[real], ref_v[real], rtol=1e-5, atol=1e-4)
     assert torch.equal(out_i.cpu()[real], ref_i[real])
+
+
+@pytest.mark.parametrize("Bt,nb,L,lp,es,eos_rate", [(1, 5, 24, -1.0, False, 0.15), (2, 3, 16, 1.0, False, 0.3),
+                                                    (3, 4, 12, 0.0, True, 0.3), (1, 1, 20, 1.0, True, 0.1),
+                                                    (2, 5, 10, 2.0, "never", 0.2)])
+def test_beam_step_matches_torch_formulation(cuda, Bt, nb, L, lp, es, eos_rate):
+    """emu_beam_step (device hypothesis bookkeeping) against the torch formulation that tests/test_generation_cpu.py pins to
+    the reference's own lm.generate: random candidate streams (with EOS hits) are fed to both, every step's outputs that can
+    influence the search must agree exactly — next tokens, cache reorder indices, running / finished scores, finished flags,
+    lengths, the done flag — and so must the final hypotheses."""
+    from types import SimpleNamespace
+    from emu_b200 import _lib
+    from test_generation_cpu import TorchBeamState
+    V, eos, pad = 977, 2, 0
+    g = torch.Generator().manual_seed(1234 + Bt * 100 + nb)
+    eng = SimpleNamespace(lib=_lib.load(), cfg=SimpleNamespace(llm_vocab=V), h=None)
+    dev_st = _lib.BeamState(Bt, nb, L, pad, "cuda")
+    ref_st = TorchBeamState(Bt, nb, L, pad)
+    for cur in range(L):
+        # 2*nb distinct candidates per row, scores descending like a top-k output; some of them EOS
+        sc = ref_st.running_scores.max(dim=1, keepdim=True)[0] - torch.rand(Bt, 2 * nb, generator=g).cumsum(1)
+        beam = torch.randint(0, nb, (Bt, 2 * nb), generator=g)
+        tok = torch.randint(3, V, (Bt, 2 * nb), generator=g)
+        e = torch.rand(Bt, 2 * nb, generator=g) < eos_rate
+        e &= e.long().cumsum(1) <= nb       # top-k over beams x vocab holds at most one EOS per beam
+        tok[e] = eos
+        idx = (beam * V + tok).to(torch.int32)
+        ref_st.step(sc, idx, V, cur, eos, lp, es)
+        _lib.Engine.beam_step(eng, dev_st, sc.cuda(), idx.cuda(), cur, eos, lp, es)
+        assert int(dev_st.done.item()) == int(ref_st.done.item()), cur
+        last = cur + 1 >= L                 # every candidate "hits" on the last step: the running beams tie at -1e9 (unused)
+        if not last:
+            assert torch.equal(dev_st.next_tokens.cpu(), ref_st.next_tokens), cur
+            assert torch.equal(dev_st.beam_src.cpu(), ref_st.beam_src), cur
+            assert torch.equal(dev_st.running_scores.cpu(), ref_st.running_scores), cur
+        fin = ref_st.is_finished.bool()
+        assert torch.equal(dev_st.is_finished.cpu().bool(), fin), cur
+        assert torch.equal(dev_st.beam_scores.cpu()[fin], ref_st.beam_scores[fin]), cur
+        assert torch.equal(dev_st.fin_len.cpu()[fin], ref_st.fin_len[fin]), cur
+        assert torch.equal(dev_st.unsat.cpu(), ref_st.unsat), cur
+        p = (cur + 1) & 1
+        if not last:
+            assert torch.equal(dev_st.running_seq[p].cpu(), ref_st.running_seq[p]), cur
+        assert torch.equal(dev_st.sequences[p].cpu()[fin], ref_st.sequences[p][fin]), cur
+        if ref_st.is_done():
+            break
+    assert ref_st.is_done() and dev_st.is_done()
+    assert torch.equal(dev_st.result(cur + 1).cpu(), ref_st.result(cur + 1))
 
 
 @pytest.mark.parametrize("H,W,S", [(37, 53, 16), (500, 333, 448), (448, 448, 448), (1024, 768, 448), (31, 97, 224),

@@ -83,3 +83,14 @@ def test_tp2_logits_match_oracle():
                         "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tools", "tp_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert "TP_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_cfg_parallel_pair_matches_single_gpu():
+    """UNet denoising split over a CFG-parallel pair: latents bitwise equal on both ranks and to the single-GPU loop."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613",
+                        os.path.join(ROOT, "tools", "cfg_parallel_check.py")], capture_output=True, text=True, timeout=600)
+    assert "CFG_PARALLEL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
