@@ -11,10 +11,16 @@
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, M=128, N=BN, K=16),
 //                 fp32 accumulators double-buffered in TMEM so the epilogue of tile i overlaps tile i+1
 //   warps 2..9  : epilogue — tcgen05.ld accumulator rows to registers (two warps per TMEM lane quarter, alternating
-//                 32-column chunks), fused bias / GELU / residual / SwiGLU / GEGLU with 16-byte operand loads
-//                 prefetched ahead of the accumulator, bf16 or fp32 stores
+//                 32-column slabs), fused bias / GELU / residual / SwiGLU / GEGLU.  bf16 outputs are STAGED: the tile is
+//                 assembled in shared memory as 64B-swizzled [128 rows x 32 columns] slabs (one conflict-free 16-byte
+//                 st.shared per 8 outputs) and leaves with TMA stores; a residual tile arrives the same way (TMA load issued
+//                 while the MMAs still run).  Round 1 stored / loaded rows straight from registers — one row per lane, so
+//                 every 16-byte access of a warp touched 32 different cache lines: 3.3 k cycles (plain) to 7.6 k (residual)
+//                 to 13.8 k (GEGLU) per 128 x 160..224 tile against a 9.7 k-cycle main loop (profiles/r02_gemm_phases_*.txt).
+//                 fp32 outputs, unaligned or very wide (> 192 columns) tiles keep the direct path.
 // A and W are both K-major, so neither operand needs a transpose anywhere in the model.
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "common.cuh"
@@ -26,13 +32,36 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(smem_u32(smem)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
 template <int BN>
 struct GemmSmem {
   static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN: multiple of 32 (epilogue chunks) within the tcgen05 N range");
   static constexpr int kStageBytes = (BM + BN) * BK * 2;
-  static constexpr int kFit = (227 * 1024 - 1024 - 256) / kStageBytes;
-  static constexpr int kStages = kFit > 8 ? 8 : kFit;  // 8 / 8 / 7 / 6 / 5 / 5 / 4 for BN = 64 .. 256
-  static constexpr int kBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // staging for the TMA-store epilogue: [slabs of 32 output columns][128 rows][64 B].  Tiles wider than 192 columns are
+  // only staged by the pair epilogues (SwiGLU / GEGLU), which emit BN / 2 columns.
+  static constexpr int kStagingBytes = BM * (BN <= 192 ? BN : BN / 2) * 2;
+  static constexpr int kFit = (227 * 1024 - 1024 - 512 - kStagingBytes) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;  // 8 / 7 / 6 / 5 / 4 / 4 / 4 for BN = 64 .. 256
+  static constexpr int kBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static_assert(kStages >= 3, "pipeline too shallow");
   // two accumulator stages; tcgen05.alloc wants a power of two
   static constexpr uint32_t kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
 };
@@ -54,6 +83,8 @@ struct GemmParams {
   int conv;        // 0 = plain 2-D A, 1 = 3x3 conv (pad 1), 2 = 3x3 conv stride 2 is NOT handled here
   int H, W, Cin, tw, th;
   int pdl;  // launched with programmatic dependent launch: griddepcontrol.wait before touching activations
+  int staged;    // bf16 output through shared memory + TMA store (tmC)
+  int res_smem;  // residual tile through TMA load into the staging buffer (tmR); else direct global loads
   // diagnostics (emu_debug_gemm_phases): when non-null, every CTA writes 8 x u64 = {globaltimer at entry, clock64 at entry,
   // after set-up, first TMA issued, first stage landed (MMA side), last MMA committed, epilogue released by the MMAs,
   // epilogue done} for its FIRST tile
@@ -75,18 +106,21 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // so W crosses the L2->SM fabric once per pair — the fabric, not the tensor pipe, bounds the BN <= 160 tiles.
 template <int BN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   constexpr int kStages = GemmSmem<BN>::kStages;
   constexpr int kStageBytes = GemmSmem<BN>::kStageBytes;
   constexpr uint32_t kTmemCols = GemmSmem<BN>::kTmemCols;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* staging = smem + kStages * kStageBytes;  // 1024-aligned: kStageBytes is a multiple of 4096
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + GemmSmem<BN>::kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;         // [2] residual slabs of epilogue group 0 / 1 have landed
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,7 +148,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 8);
+      mbar_init(&res_full[i], 1);
     }
+    if (p.staged) tma_prefetch_desc(&tmC);
+    if (p.res_smem) tma_prefetch_desc(&tmR);
     mbar_fence_init();
   }
   if (p.pdl) pdl_launch_dependents();  // the next kernel of the chain may start its own prologue now
@@ -214,6 +251,217 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.pdl) pdl_wait();  // residual / bias2 are predecessor outputs and C may alias a buffer it still reads
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (p.staged) {
+      // ---------- staged epilogue: registers -> 64B-swizzled shared-memory slabs -> TMA store ----------
+      // The two warp groups (half = 0 / 1, four warps = the four TMEM lane quarters each) own the even / odd 32-column
+      // output slabs of the tile and run independently: own named barrier, own elected issuer thread (TMA stores, the
+      // residual loads of the next tile), own residual mbarrier.
+      const bool pair = (p.epi == EPI_SWIGLU || p.epi == EPI_GEGLU);
+      const int n_out = pair ? (p.N >> 1) : p.N;            // output columns of the whole matrix
+      const int bn_out = pair ? BN / 2 : BN;                // ... of one tile
+      const int n_units = bn_out / 32;
+      const int r_in_tile = q * 32 + lane;
+      const uint32_t stg = smem_u32(staging);
+      const uint32_t my_row = (uint32_t)r_in_tile * 64u;
+      const uint32_t swz = (uint32_t)((r_in_tile >> 1) & 3);
+      const bool issuer = (q == 0 && lane == 0);
+      const int bar_id = 1 + half;
+      const bool vec_bias = p.bias != nullptr && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+      const bool vec_b2 = p.bias2 != nullptr && (p.N % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.bias2) & 15) == 0);
+      const bool vec_res = p.residual != nullptr && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+      auto tile_row0 = [&](int tm) -> long {
+        if (!p.conv) return (long)tm * BM;
+        const int tiles_w = p.W / p.tw, tiles_h = p.H / p.th;
+        const int w0 = (tm % tiles_w) * p.tw, h0 = ((tm / tiles_w) % tiles_h) * p.th, img = tm / (tiles_w * tiles_h);
+        return ((long)img * p.H + h0) * p.W + w0;  // a tile is th full-width rows or one 128-pixel run: 128 consecutive rows
+      };
+      auto load_residual = [&](int tile) {  // issuer only: this group's residual slabs of `tile` -> staging
+        const int tm = (tile % units_m) * CL + crank, tn = tile / units_m;
+        int cnt = 0;
+        for (int u = half; u < n_units; u += 2)
+          if (tn * bn_out + u * 32 < n_out) ++cnt;
+        if (tm >= tiles_m) cnt = 0;
+        mbar_expect_tx(&res_full[half], (uint32_t)cnt * 8192u);  // arrive + expect: with 0 bytes the phase completes at once
+        if (cnt == 0) return;
+        const int row0 = (int)tile_row0(tm);
+        for (int u = half; u < n_units; u += 2)
+          if (tn * bn_out + u * 32 < n_out) tma_load_2d(staging + u * 8192, &tmR, &res_full[half], tn * bn_out + u * 32, row0);
+      };
+      if (p.res_smem && issuer && unit0 < num_tiles) load_residual(unit0);
+      uint32_t res_phase = 0;
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+        const int tm = (tile % units_m) * CL + crank, tn = tile / units_m;
+        const long row0 = tile_row0(tm);
+        const long row = row0 + r_in_tile;
+        const bool row_ok = row < p.M && tm < tiles_m;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        if (dbg && tile == unit0 && threadIdx.x == 64) dbg[6] = clk64();
+        if (p.res_smem) mbar_wait(&res_full[half], res_phase);
+#pragma unroll 1
+        for (int u = half; u < n_units; u += 2) {
+          const int oc0 = tn * bn_out + u * 32;  // first output column of this slab
+          if (oc0 >= n_out) break;
+          const uint32_t slab = stg + (uint32_t)u * 8192u + my_row;
+          if (!pair) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + u * 32), v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            const bool full = oc0 + 32 <= p.N;
+            if (p.bias != nullptr) {
+              if (full && vec_bias) {
+                const uint4* bsrc = reinterpret_cast<const uint4*>(p.bias + oc0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint4 b = __ldg(bsrc + i);
+                  const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) { f[8 * i + 2 * j] += bf16_lo(bw[j]); f[8 * i + 2 * j + 1] += bf16_hi(bw[j]); }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (oc0 + i < p.N) f[i] += __bfloat162float(p.bias[oc0 + i]);
+              }
+            }
+            if (p.bias2 != nullptr && row_ok) {
+              const bf16* b2 = p.bias2 + (row / p.bias2_rows) * p.N + oc0;
+              if (full && vec_b2) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint4 b = __ldg(reinterpret_cast<const uint4*>(b2) + i);
+                  const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    f[8 * i + 2 * j] = round_bf16(f[8 * i + 2 * j]) + bf16_lo(bw[j]);
+                    f[8 * i + 2 * j + 1] = round_bf16(f[8 * i + 2 * j + 1]) + bf16_hi(bw[j]);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (oc0 + i < p.N) f[i] = round_bf16(f[i]) + __bfloat162float(b2[i]);
+              }
+            }
+            if (p.epi == EPI_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = gelu_erf_fast(round_bf16(f[i]));
+            } else if (p.epi == EPI_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (p.res_smem) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 r = lds128(slab + (((uint32_t)i ^ swz) << 4));
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  f[8 * i + 2 * j] = round_bf16(f[8 * i + 2 * j]) + bf16_lo(rw[j]);
+                  f[8 * i + 2 * j + 1] = round_bf16(f[8 * i + 2 * j + 1]) + bf16_hi(rw[j]);
+                }
+              }
+            } else if (p.residual != nullptr && row_ok) {
+              const bf16* rsd = p.residual + row * p.ldr + oc0;
+              if (full && vec_res) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint4 r = __ldg(reinterpret_cast<const uint4*>(rsd) + i);
+                  const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    f[8 * i + 2 * j] = round_bf16(f[8 * i + 2 * j]) + bf16_lo(rw[j]);
+                    f[8 * i + 2 * j + 1] = round_bf16(f[8 * i + 2 * j + 1]) + bf16_hi(rw[j]);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (oc0 + i < p.N) f[i] = round_bf16(f[i]) + __bfloat162float(rsd[i]);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 w;
+              w.x = pack_bf16(f[8 * i], f[8 * i + 1]);
+              w.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+              w.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+              w.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+              sts128(slab + (((uint32_t)i ^ swz) << 4), w);
+            }
+          } else {
+            // interleaved (a_j, b_j) accumulator column pairs -> one output column: slab u <- accumulator chunks 2u, 2u+1
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+              const int ac0 = tn * BN + (2 * u + hc) * 32;  // first accumulator column of this chunk
+              uint32_t v[32];
+              tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + (2 * u + hc) * 32), v);
+              tmem_ld_wait();
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+              if (p.bias != nullptr) {
+                if (ac0 + 32 <= p.N && vec_bias) {
+                  const uint4* bsrc = reinterpret_cast<const uint4*>(p.bias + ac0);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const uint4 b = __ldg(bsrc + i);
+                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { f[8 * i + 2 * j] += bf16_lo(bw[j]); f[8 * i + 2 * j + 1] += bf16_hi(bw[j]); }
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (ac0 + i < p.N) f[i] += __bfloat162float(p.bias[ac0 + i]);
+                }
+              }
+              float o[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float a = round_bf16(f[2 * i]), b = round_bf16(f[2 * i + 1]);
+                if (p.epi == EPI_SWIGLU) o[i] = round_bf16(silu(a)) * b;
+                else o[i] = a * round_bf16(gelu_erf_fast(b));
+              }
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                uint4 w;
+                w.x = pack_bf16(o[8 * i], o[8 * i + 1]);
+                w.y = pack_bf16(o[8 * i + 2], o[8 * i + 3]);
+                w.z = pack_bf16(o[8 * i + 4], o[8 * i + 5]);
+                w.w = pack_bf16(o[8 * i + 6], o[8 * i + 7]);
+                sts128(slab + (((uint32_t)(hc * 2 + i) ^ swz) << 4), w);
+              }
+            }
+          }
+        }
+        // the accumulator is drained: hand the TMEM stage back before the stores leave
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        fence_async_smem();        // generic-proxy slab writes -> visible to the TMA engine
+        named_bar(bar_id, 128);
+        if (issuer) {
+          if (tm < tiles_m) {
+            for (int u = half; u < n_units; u += 2) {
+              const int oc0 = tn * bn_out + u * 32;
+              if (oc0 < n_out) tma_store_2d(&tmC, staging + u * 8192, oc0, (int)row0);
+            }
+          }
+          bulk_commit();
+          bulk_wait_read0();       // the slabs may be overwritten once the stores have READ them
+          if (p.res_smem && tile + unit_step < num_tiles) load_residual(tile + unit_step);
+        }
+        named_bar(bar_id, 128);    // nobody of the group touches the slabs before the issuer got here
+        if (dbg && tile == unit0 && threadIdx.x == 64) dbg[7] = clk64();
+        res_phase ^= 1;
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (issuer) bulk_wait0();    // all stores complete (global writes performed) before the CTA retires
+    } else
     for (int tile = unit0; tile < num_tiles; tile += unit_step) {
       const int tm = (tile % units_m) * CL + crank, tn = tile / units_m;
       // output row owned by this thread
@@ -433,6 +681,21 @@ int make_tmap_2d(CUtensorMap* out, const void* base, long rows, long cols, long 
   return r == CUDA_SUCCESS ? EMU_OK : EMU_ERR_CUDA;
 }
 
+// bf16 [rows, cols] output / residual matrix for the staged epilogue: box = 128 rows x 32 columns (64 B), 64B swizzle.
+// TMA clips the rows / columns of a box that fall outside the matrix on a store and zero-fills them on a load.
+int make_tmap_out(CUtensorMap* out, const void* base, long rows, long cols, long ld) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return EMU_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? EMU_OK : EMU_ERR_CUDA;
+}
+
 // 4-D NHWC bf16 activation [NB, H, W, C]; box = {64 ch, tw, th, 1}; out-of-bounds (the conv halo) reads as zero
 int make_tmap_nhwc(CUtensorMap* out, const void* base, int NB, int H, int W, int C, int tw, int th) {
   PFN_encodeTiled enc = get_encode();
@@ -482,7 +745,8 @@ int make_tmap_bnhd(CUtensorMap* out, const void* base, int D, long N, int H, int
 }
 
 template <int BN, int CL>
-static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                          const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
   static int max_ctas = kNumSMs;
   if (!attr_set) {
@@ -528,7 +792,7 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, tmA, tmB, p) == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, tmA, tmB, tmC, tmR, p) == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
 // Cluster mode (W tile TMA-multicast over a 2-CTA cluster).  Measured on B200 (profiles/r01_gemm_bench_cluster.txt):
@@ -548,20 +812,46 @@ static bool use_cluster(int M, int force, bool is_conv) {
   return tiles_m >= 2 && (tiles_m % 2 == 0 || tiles_m >= 7);
 }
 
-// Tile width: minimise  waves(BN) x time-per-tile(BN)  over the instantiated widths.  Per K=16 step a tile costs
-// max(tensor pipe: 128*BN/256 cycles, shared-memory operand reads: (128 + BN) * 32 B at 128 B/cycle); odd widths such
-// as 160 exist because e.g. M=2048, N=1280 is 160 tiles at BN=128 (two waves on 148 SMs, the second 8 % full) but 128
-// tiles at BN=160 (one wave).
-static int pick_bn(int M, int N) {
+// Can this problem use the staged (shared memory + TMA store) epilogue at tile width bn?
+static bool can_stage(const GemmEpilogue& e, int N, int bn) {
+  if (e.out_fp32 || e.C == nullptr) return false;
+  const bool pair = e.mode == EPI_SWIGLU || e.mode == EPI_GEGLU;
+  const int n_out = pair ? N / 2 : N;
+  if ((reinterpret_cast<uintptr_t>(e.C) & 15) || (e.ldc % 8) || (n_out % 8)) return false;
+  if (pair) return bn % 64 == 0;  // a 32-column output slab = 64 accumulator columns
+  return bn <= 192;               // the staging buffer holds at most 192 columns
+}
+static bool env_no_stage() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("EMU_GEMM_DIRECT");
+    v = (s && atoi(s) == 1) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// Tile width: minimise the modelled time of one CTA's tile stream over the instantiated widths.  Per tile the main loop
+// costs kblocks x max(tensor pipe: 2 x bn cycles per 64-deep k block, L2 -> shared-memory operand traffic: (128 + bn) x 128 B at
+// ~75 B/cycle/SM) and the epilogue, which overlaps the NEXT tile's main loop (double-buffered TMEM), costs per output
+// column ~6 cycles staged and 21 (plain) / 47 (residual) / 60 (GELU, GEGLU) direct — all measured with
+// emu_debug_gemm_phases (profiles/r02_gemm_phases_*.txt).  Odd widths such as 160 exist because e.g. M=2048, N=1280 is 160
+// tiles at BN=128 (two waves on 148 SMs, the second 8 % full) but 128 tiles at BN=160 (one wave).
+static int pick_bn(int M, int N, int K, const GemmEpilogue& e) {
   static const int cand[] = {256, 224, 192, 160, 128, 96, 64};
   const long tm = (M + BM - 1) / BM;
+  const long kb = (K + BK - 1) / BK;
+  const bool act = e.mode == EPI_GELU || e.mode == EPI_SWIGLU || e.mode == EPI_GEGLU;
   int best = 128;
   double best_cost = 1e30;
   for (int bn : cand) {
     const long tiles = tm * ((N + bn - 1) / bn);
     const long waves = (tiles + kNumSMs - 1) / kNumSMs;
-    const double mma = 128.0 * bn / 256.0, smem = (128.0 + bn) * 32.0 / 128.0;
-    const double cost = (double)waves * (mma > smem ? mma : smem) + 4.0 * waves;  // + per-tile fixed overhead
+    const double mma = 2.0 * bn, l2 = (128.0 + bn) * 128.0 / 75.0;
+    const double ml = (double)kb * (mma > l2 ? mma : l2) + 1500.0;  // + pipeline fill
+    const bool staged = !env_no_stage() && can_stage(e, N, bn);
+    double per_col = staged ? (act ? 20.0 : 6.0) : (act ? 60.0 : (e.residual ? 47.0 : 21.0));
+    const double epi = per_col * bn + 400.0;
+    const double cost = (double)(waves - 1) * (ml > epi ? ml : epi) + ml + epi;
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = bn;
@@ -584,6 +874,25 @@ static int dispatch_bn(int bn, F&& f) {
   return EMU_ERR_INVALID;
 }
 
+// decide the epilogue style of this launch and build the tensor maps it needs (dummies otherwise: the kernel never touches
+// a map whose flag is off)
+static int setup_staging(GemmParams& p, const GemmEpilogue& e, int M, int N, int bn, CUtensorMap* tmC, CUtensorMap* tmR) {
+  memset(tmC, 0, sizeof(*tmC));
+  memset(tmR, 0, sizeof(*tmR));
+  p.staged = 0;
+  p.res_smem = 0;
+  const bool forced_direct = (e.force_bn & 4096) != 0;
+  if (forced_direct || env_no_stage() || !can_stage(e, N, bn)) return EMU_OK;
+  const bool pair = e.mode == EPI_SWIGLU || e.mode == EPI_GEGLU;
+  const int n_out = pair ? N / 2 : N;
+  if (make_tmap_out(tmC, e.C, M, n_out, e.ldc) != EMU_OK) return EMU_OK;  // odd geometry: keep the direct path
+  p.staged = 1;
+  if (e.residual != nullptr && !pair && (e.ldr % 8 == 0) && !(reinterpret_cast<uintptr_t>(e.residual) & 15) &&
+      make_tmap_out(tmR, e.residual, M, n_out, e.ldr) == EMU_OK)
+    p.res_smem = 1;
+  return EMU_OK;
+}
+
 int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& e,
               cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return EMU_ERR_INVALID;
@@ -596,16 +905,18 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
   p.C = e.C; p.ldc = e.ldc; p.bias = e.bias; p.residual = e.residual; p.ldr = e.ldr;
   p.bias2 = e.bias2; p.bias2_rows = e.bias2_rows > 0 ? e.bias2_rows : 1;
   p.epi = e.mode; p.out_fp32 = e.out_fp32; p.conv = 0; p.pdl = g_pdl_chain; p.dbg = e.dbg;
-  const int bn = (e.force_bn & 1023) ? (e.force_bn & 1023) : pick_bn(M, N);
+  const int bn = (e.force_bn & 1023) ? (e.force_bn & 1023) : pick_bn(M, N, K, e);
   const bool cl = use_cluster(M, e.force_bn, false);
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmR;
   int rc = make_tmap_2d(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
   rc = make_tmap_2d(&tmB, W, N, K, ldw, cl ? bn / 2 : bn);
   if (rc) return rc;
+  rc = setup_staging(p, e, M, N, bn, &tmC, &tmR);
+  if (rc) return rc;
   return dispatch_bn(bn, [&](auto w) {
     constexpr int kBN = decltype(w)::value;
-    return cl ? launch_gemm_cl<kBN, 2>(tmA, tmB, p, st) : launch_gemm_cl<kBN, 1>(tmA, tmB, p, st);
+    return cl ? launch_gemm_cl<kBN, 2>(tmA, tmB, tmC, tmR, p, st) : launch_gemm_cl<kBN, 1>(tmA, tmB, tmC, tmR, p, st);
   });
 }
 
@@ -623,16 +934,18 @@ int conv3x3_bf16(const bf16* X, int NB, int H, int W, int Cin, const bf16* Wk, i
   p.bias2 = e.bias2; p.bias2_rows = e.bias2_rows > 0 ? e.bias2_rows : 1;
   p.epi = e.mode; p.out_fp32 = e.out_fp32; p.pdl = g_pdl_chain; p.dbg = e.dbg;
   p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tw = tw; p.th = th;
-  const int bn = (e.force_bn & 1023) ? (e.force_bn & 1023) : pick_bn(p.M, Cout);
+  const int bn = (e.force_bn & 1023) ? (e.force_bn & 1023) : pick_bn(p.M, Cout, 9 * Cin, e);
   const bool cl = use_cluster(p.M, e.force_bn, true);
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmR;
   int rc = make_tmap_nhwc(&tmA, X, NB, H, W, Cin, tw, th);
   if (rc) return rc;
   rc = make_tmap_2d(&tmB, Wk, Cout, 9L * Cin, 9L * Cin, cl ? bn / 2 : bn);
   if (rc) return rc;
+  rc = setup_staging(p, e, p.M, Cout, bn, &tmC, &tmR);
+  if (rc) return rc;
   return dispatch_bn(bn, [&](auto w) {
     constexpr int kBN = decltype(w)::value;
-    return cl ? launch_gemm_cl<kBN, 2>(tmA, tmB, p, st) : launch_gemm_cl<kBN, 1>(tmA, tmB, p, st);
+    return cl ? launch_gemm_cl<kBN, 2>(tmA, tmB, tmC, tmR, p, st) : launch_gemm_cl<kBN, 1>(tmA, tmB, tmC, tmR, p, st);
   });
 }
 

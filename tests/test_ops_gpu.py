@@ -40,6 +40,46 @@ def test_gemm_plain(cuda, M, N, K, bn):
     assert O.rel_err(out16, ref) < TOL_BF16
 
 
+@pytest.mark.parametrize("M,N,K", [(200, 384, 256), (2048, 1280, 1280), (700, 1000, 320), (4100, 640, 192), (129, 72, 64)])
+@pytest.mark.parametrize("bn", [0, 64, 96, 128, 160, 192, 4096 + 160, 256])
+def test_gemm_staged_epilogue(cuda, M, N, K, bn):
+    """bf16 outputs leave through shared memory + TMA stores and the residual arrives by TMA load (bn <= 192); bn = 256 and
+    4096 + bn (forced) take the direct register path.  Every epilogue flavour, ragged M / N, several tiles per CTA, and the
+    in-place form x = x + lin(a) that the models use."""
+    from emu_b200 import _lib
+    A, W, b, r = _rand((M, K), 11), _rand((N, K), 12, 0.05), _rand((N,), 13), _rand((M, N), 14)
+    lin = O.op_linear(A, W, b)
+    bf = lambda t: t.to(torch.bfloat16)
+    Ac, Wc, bc = A.cuda(), W.cuda(), b.cuda()
+    assert O.rel_err(_lib.op_gemm(Ac, Wc, force_bn=bn).cpu(), O.op_linear(A, W)) < TOL_BF16
+    assert O.rel_err(_lib.op_gemm(Ac, Wc, bias=bc, force_bn=bn).cpu(), lin) < TOL_BF16
+    assert O.rel_err(_lib.op_gemm(Ac, Wc, bias=bc, epi=_lib.EPI_GELU, force_bn=bn).cpu(),
+                     torch.nn.functional.gelu(bf(lin))) < TOL_BF16
+    want = bf(lin).float() + r.float()
+    assert O.rel_err(_lib.op_gemm(Ac, Wc, bias=bc, residual=r.cuda(), force_bn=bn).cpu(), want) < TOL_BF16
+    # in place: C aliases the residual (h = h + o_proj(attn)), every tile reads its own residual before it is overwritten
+    h = r.cuda().clone()
+    lib = _lib.load()
+    _lib.check(lib.emu_op_gemm(_lib._ptr(Ac), K, _lib._ptr(Wc), K, M, N, K, _lib._ptr(bc), _lib._ptr(h), N, 0, _lib._ptr(h), N,
+                               0, bn, _lib._stream()))
+    assert O.rel_err(h.cpu(), want) < TOL_BF16
+
+
+@pytest.mark.parametrize("M,N,K", [(200, 384, 256), (2048, 2560, 640), (300, 400, 128)])
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 224, 256])
+def test_gemm_pair_epilogues_all_widths(cuda, M, N, K, bn):
+    """SwiGLU / GEGLU with interleaved weight rows at every tile width (staged for multiples of 64, direct at 224)."""
+    from emu_b200 import _lib
+    A, W, b = _rand((M, K), 21), _rand((N, K), 22, 0.05), _rand((N,), 23)
+    bf = lambda t: t.to(torch.bfloat16)
+    g, u = O.op_linear(A, W[0::2]), O.op_linear(A, W[1::2])
+    assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), epi=_lib.EPI_SWIGLU, force_bn=bn).cpu(),
+                     torch.nn.functional.silu(bf(g)) * bf(u)) < TOL_BF16
+    hb, gb = O.op_linear(A, W[0::2], b[0::2]), O.op_linear(A, W[1::2], b[1::2])
+    assert O.rel_err(_lib.op_gemm(A.cuda(), W.cuda(), bias=b.cuda(), epi=_lib.EPI_GEGLU, force_bn=bn).cpu(),
+                     bf(hb) * torch.nn.functional.gelu(bf(gb))) < TOL_BF16
+
+
 def test_gemm_epilogues(cuda):
     from emu_b200 import _lib
     M, N, K = 200, 384, 256
@@ -71,6 +111,20 @@ def test_conv3x3(cuda, NB, H, W, Cin, Cout):
     x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
     wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous().cuda()  # k = (r*3+s)*Cin + c
     out = _lib.op_conv3x3(x_nhwc, wk, bias=b.cuda()).cpu()
+    assert O.rel_err(out, ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(2, 32, 32, 128, 320), (1, 64, 64, 64, 640), (2, 16, 16, 256, 1280)])
+def test_conv3x3_residual(cuda, NB, H, W, Cin, Cout):
+    """ResnetBlock2D's conv2 + shortcut: the residual tile arrives by TMA load into the staged epilogue (Cout multi-tile)"""
+    from emu_b200 import _lib
+    x, w, b = _rand((NB, Cin, H, W), 27), _rand((Cout, Cin, 3, 3), 28, 0.05), _rand((Cout,), 29)
+    r = _rand((NB, H, W, Cout), 30)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
+    ref = ref.to(torch.bfloat16).float() + r.float()
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous().cuda()
+    out = _lib.op_conv3x3(x_nhwc, wk, bias=b.cuda(), residual=r.cuda()).cpu()
     assert O.rel_err(out, ref) < TOL_BF16
 
 
