@@ -31,7 +31,7 @@ constexpr int kTpThreads = 256;
 struct TpLayout {
   size_t red_slot;     // floats per reduce slot  (Bmax * hidden)
   size_t gat_slot;     // floats per gather slot  (Bmax * Vl)
-  size_t red_off, gat_off, flag_red_off, flag_gat_off, seq_off, ll_off, step_off, total;  // in floats / 4-byte words
+  size_t red_off, gat_off, flag_red_off, flag_gat_off, seq_off, ll_off, step_off, xin_off, total;  // in floats / 4-byte words
 };
 static TpLayout tp_layout(int n, int bmax, int hidden, int vl) {
   TpLayout L;
@@ -44,7 +44,8 @@ static TpLayout tp_layout(int n, int bmax, int hidden, int vl) {
   L.seq_off = L.flag_gat_off + (size_t)8 * kTpMaxCtas;
   L.ll_off = (L.seq_off + 2 * kTpMaxCtas + 3) / 4 * 4;  // {value, flag} words: 2 floats per element
   L.step_off = L.ll_off + 2 * 2 * (size_t)n * L.red_slot;
-  L.total = L.step_off + 4;
+  L.xin_off = L.step_off + 4;  // 256 epoch words of the in-kernel input reduce (GemvArgs::xin_flags)
+  L.total = L.xin_off + 256;
   return L;
 }
 
@@ -233,6 +234,17 @@ int tp_ll_prepare(EmuEngine* e, GemvArgs& g, int idx) {
   g.ll_step = reinterpret_cast<const unsigned*>(e->tp_peer[e->tp_rank] + L.step_off);
   return EMU_OK;
 }
+// fill the pending-input-exchange fields of the GEMV that consumes h after exchange idx (see GemvArgs::xin_*)
+int tp_xin_prepare(EmuEngine* e, GemvArgs& g, int idx) {
+  if (!e->tp_p2p || !e->tp_ll) return EMU_ERR_UNSUPPORTED;
+  const TpLayout L = tp_layout(e->tp_size, e->cfg.llm_max_batch, e->cfg.llm_hidden, e->Vl);
+  g.xin_ll = e->tp_peer[e->tp_rank] + L.ll_off;
+  g.xin_n = e->tp_size; g.xin_idx = idx; g.xin_red = 32;
+  g.xin_slot_elems = (long)L.red_slot;
+  g.xin_step = reinterpret_cast<const unsigned*>(e->tp_peer[e->tp_rank] + L.step_off);
+  g.xin_flags = reinterpret_cast<unsigned*>(e->tp_peer[e->tp_rank] + L.xin_off);
+  return EMU_OK;
+}
 unsigned* tp_step_counter(EmuEngine* e) {
   if (!e->tp_p2p) return nullptr;
   const TpLayout L = tp_layout(e->tp_size, e->cfg.llm_max_batch, e->cfg.llm_hidden, e->Vl);
@@ -316,6 +328,8 @@ int tp_exchange_setup(EmuEngine* e, int (*allgather_bytes)(EmuEngine*, const voi
   {
     const char* ll = getenv("EMU_TP_LL");
     e->tp_ll = !(ll && atoi(ll) == 0);
+    const char* fold = getenv("EMU_TP_FOLD");
+    e->tp_fold = e->tp_ll && !(fold && atoi(fold) == 0);
   }
   if (getenv("EMU_TP_DEBUG")) fprintf(stderr, "emu_b200: rank %d/%d NVLink peer exchange enabled\n", e->tp_rank, n);
   return EMU_OK;
