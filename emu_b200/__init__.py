@@ -1,7 +1,7 @@
 """emu_b200 — B200-native (sm_100a) engine for baaivision/Emu's multimodal generate path.
 
-Python host code mirrors the reference's public API (EmuModel.generate / generate_image / encode_image,
-EmuChatGeneration, EmuVisualGeneration, Emu, EmuGenerationPipeline) and calls hand-written CUDA through the C ABI
-declared in include/emu_b200.h (libemu_b200.so).  There is no CPU fallback.
+Python host code mirrors the reference's public API — emu2.emu.EmuModel (generate / generate_image / encode_image),
+emu2.chat.EmuChatGeneration, emu2.diffusion.EmuVisualGeneration, emu1.modeling_emu.Emu, emu1.pipeline.EmuGenerationPipeline —
+and calls hand-written CUDA through the C ABI declared in include/emu_b200.h (libemu_b200.so).  There is no CPU fallback.
 """
 __version__ = "0.1.0"

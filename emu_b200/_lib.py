@@ -44,7 +44,7 @@ class EmuUNetConfig(C.Structure):
         ("block_out_channels", C.c_int * 4), ("layers_per_block", C.c_int), ("transformer_layers", C.c_int * 4),
         ("head_dim", C.c_int), ("cross_attention_dim", C.c_int), ("use_linear_projection", C.c_int),
         ("addition_time_embed_dim", C.c_int), ("projection_class_embeddings_input_dim", C.c_int),
-        ("norm_groups", C.c_int), ("norm_eps", C.c_float),
+        ("norm_groups", C.c_int), ("norm_eps", C.c_float), ("mid_transformer_layers", C.c_int), ("num_heads", C.c_int),
     ]
 
 
@@ -60,7 +60,7 @@ SYMBOLS = [
     "emu_beam_topk", "emu_beam_step", "emu_sample_tokens", "emu_image_to_uint8", "emu_preprocess_image", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
     "emu_vit_forward", "emu_llm_reset", "emu_llm_embed", "emu_llm_prefill", "emu_llm_decode", "emu_llm_cur_len",
     "emu_project", "emu_cformer_forward", "emu_unet_configure", "emu_unet_forward", "emu_denoise_step",
-    "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
+    "emu_denoise_step_multistep", "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
     "emu_op_attn_prefill", "emu_op_attn_decode", "emu_op_rmsnorm", "emu_op_layernorm", "emu_launch_count",
     "emu_debug_gemm_phases",
     "emu_version",
@@ -276,6 +276,16 @@ class Engine:
         check(self.lib.emu_denoise_step(self.h, _ptr(latents_f32), C.c_float(float(sigma)), C.c_float(float(sigma_next)),
                                         C.c_float(float(timestep)), C.c_float(float(guidance)), _ptr(ctx), ctx.shape[1],
                                         _ptr(text_embeds), _ptr(time_ids), B, h, w, _stream()), self.h)
+
+    def denoise_step_multistep(self, latents_f32, state_f32, coef8, timestep, guidance, ctx):
+        """One PNDM / PLMS iteration (emu_denoise_step_multistep): latents [B,4,h,w] fp32 in place, state [4,B,4,h,w] fp32."""
+        B, _, h, w = latents_f32.shape
+        assert latents_f32.dtype == torch.float32 and latents_f32.is_contiguous()
+        assert state_f32.dtype == torch.float32 and state_f32.is_contiguous() and state_f32.numel() == 4 * latents_f32.numel()
+        coef = (C.c_float * 8)(*[float(v) for v in coef8])
+        check(self.lib.emu_denoise_step_multistep(self.h, _ptr(latents_f32), _ptr(state_f32), coef, C.c_float(float(timestep)),
+                                                  C.c_float(float(guidance)), _ptr(ctx), ctx.shape[1], B, h, w, _stream()),
+              self.h)
 
     def project(self, which: int, x: torch.Tensor, out_dim: int):
         x2 = x.reshape(-1, x.shape[-1]).to(torch.bfloat16).contiguous()

@@ -413,7 +413,7 @@ static int launch_fa(const AttnArgs& a, cudaStream_t st) {
 }
 
 int attn_prefill(const AttnArgs& a, cudaStream_t st) {
-  if (a.D % 8 || a.D > 128 || a.Nq < 1 || a.Nk < 1) return EMU_ERR_INVALID;
+  if (a.D % 8 || a.D > 160 || a.Nq < 1 || a.Nk < 1) return EMU_ERR_INVALID;
   // strides must keep 16-byte alignment of every row
   if ((a.q_ts % 8) || (a.k_ts % 8) || (a.v_ts % 8) || (a.q_hs % 8) || (a.k_hs % 8) || (a.v_hs % 8) ||
       (a.q_bs % 8) || (a.k_bs % 8) || (a.v_bs % 8) || (a.o_ts % 2) || (a.o_hs % 2) || (a.o_bs % 2))
@@ -432,7 +432,8 @@ int attn_prefill(const AttnArgs& a, cudaStream_t st) {
   if (a.D <= 64) return launch_fa<64>(a, st);
   if (a.D <= 96) return launch_fa<96>(a, st);
   if (a.D <= 112) return launch_fa<112>(a, st);
-  return launch_fa<128>(a, st);
+  if (a.D <= 128) return launch_fa<128>(a, st);
+  return launch_fa<160>(a, st);  // SD-1.5 class UNets: 8 heads of 160 at the 1280-channel levels (Emu1 pipeline)
 }
 
 }  // namespace emu

@@ -38,6 +38,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// two values at once: one F2FP pack + two bit moves on the ALU pipe instead of two F2F conversions on the quarter-rate
+// XU pipe (the GEMM epilogues round 2-3 times per output: this was their bottleneck, profiles/r02_gemm_phases_*.txt)
+__device__ __forceinline__ void round_bf16x2(float& a, float& b) {
+  const uint32_t p = pack_bf16(a, b);
+  a = bf16_lo(p);
+  b = bf16_hi(p);
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -72,17 +89,18 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // ex2 + a 5-term Horner instead of erff's ~60 instructions; used in the GEMM epilogues where the exact one is the bound
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.f));  // argument >= 1: no denormal / range guard needed
   float pl = fmaf(1.061405429f, t, -1.453152027f);
   pl = fmaf(pl, t, 1.421413741f);
   pl = fmaf(pl, t, -0.284496736f);
   pl = fmaf(pl, t, 0.254829592f);
-  const float e = exp2f(-ax * ax * 1.4426950408889634f);
+  const float e = ex2_approx_ftz(-ax * ax * 1.4426950408889634f);  // <= 1, flushes to 0 far out in the tail
   const float y = 1.f - pl * t * e;
   return copysignf(y, x);
 }
 __device__ __forceinline__ float gelu_erf_fast(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return x * rcp_approx(1.f + ex2_approx_ftz(-x * 1.4426950408889634f)); }
 
 // streaming 16-byte global load that does not pollute L1 (weights are read exactly once)
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {

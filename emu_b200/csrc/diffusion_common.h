@@ -32,6 +32,8 @@ int cfg_prepare(const float* lat, bf16* xin, int B, int C, int HW, int Cp, const
                 cudaStream_t st);
 int cfg_euler(float* lat, const bf16* eps_nhwc, int B, int C, int HW, int ld, const float* params, int cfg,
               cudaStream_t st);
+int cfg_multistep(float* lat, const bf16* eps_nhwc, float* hist, float* saved, int B, int C, int HW, int ld,
+                  const float* params, int cfg, cudaStream_t st);
 int int_to_float(const int* x, float* y, int n, cudaStream_t st);
 int fill_float(float* y, int n, const float* src_scalar, cudaStream_t st);
 
@@ -51,7 +53,7 @@ struct TBlockW {
   Lin o1, o2, ff1, ff2;
   long kv_off = -1;  // column offset of this block's [k | v] in the batched cross-attention projection (unet.cu)
 };
-struct TransW { Norm gn; Lin pin, pout; std::vector<TBlockW> blocks; int c = 0; };
+struct TransW { Norm gn; Lin pin, pout; std::vector<TBlockW> blocks; int c = 0, hd = 64; };
 
 enum LoadKind { LK_COPY = 0, LK_CONV3 = 1, LK_ROWS = 2, LK_GEGLU_W = 3, LK_GEGLU_B = 4 };
 struct LoadSpec {

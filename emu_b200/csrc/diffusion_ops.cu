@@ -365,6 +365,45 @@ int cfg_euler(float* lat, const bf16* eps_nhwc, int B, int C, int HW, int ld, co
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
+// CFG combine + one linear-multistep (PNDM / PLMS) update, the scheduler of the Emu1 pipeline (Emu1/models/pipeline.py:112-127
+// with diffusers PNDMScheduler, skip_prk_steps):  e = CFG(eps);  m = wc*e + w0*h0 + w1*h1 + w2*h2 (h0 = newest stored eps);
+// x_prev = a * x + b * m, where x is the latent or the sample saved at the first step.  params (device, fp32):
+// [0] a, [1] b, [2] wc, [3] w0, [4] w1, [5] w2, [6] guidance, [7] flags as float: bit 0 push e into the history,
+// bit 1 read x from `saved`, bit 2 store the incoming latent in `saved`.  hist = [3][n] fp32 planes (newest first).
+__global__ void cfg_multistep_kernel(float* lat, const bf16* __restrict__ eps_nhwc, float* hist, float* saved, int B, int C,
+                                     int HW, int ld, const float* __restrict__ params, int cfg) {
+  const float a = params[0], b = params[1], wc = params[2], w0 = params[3], w1 = params[4], w2 = params[5], g = params[6];
+  const int flags = (int)params[7];
+  const long total = (long)B * C * HW;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long p = idx % HW;
+    const int c = (idx / HW) % C;
+    const int bb = idx / ((long)HW * C);
+    const float ec = __bfloat162float(eps_nhwc[((long)bb * HW + p) * ld + c]);
+    float e = ec;
+    if (cfg) {
+      const float eu = __bfloat162float(eps_nhwc[((long)(B + bb) * HW + p) * ld + c]);
+      e = round_bf16(eu + round_bf16(g * round_bf16(ec - eu)));  // same rounding points as cfg_euler_kernel
+    }
+    const float h0 = hist[idx], h1 = hist[total + idx], h2 = hist[2 * total + idx];
+    const float m = wc * e + w0 * h0 + w1 * h1 + w2 * h2;
+    const float x_in = lat[idx];
+    const float x = (flags & 2) ? saved[idx] : x_in;
+    if (flags & 4) saved[idx] = x_in;
+    if (flags & 1) {
+      hist[2 * total + idx] = h1;
+      hist[total + idx] = h0;
+      hist[idx] = e;
+    }
+    lat[idx] = a * x + b * m;
+  }
+}
+int cfg_multistep(float* lat, const bf16* eps_nhwc, float* hist, float* saved, int B, int C, int HW, int ld,
+                  const float* params, int cfg, cudaStream_t st) {
+  cfg_multistep_kernel<<<2 * kNumSMs, 256, 0, st>>>(lat, eps_nhwc, hist, saved, B, C, HW, ld, params, cfg);
+  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+}
+
 // mean over tokens: ctx [B, L, C] -> [B, C]   (text_embeds = prompt_embeds.mean(1), Emu2/emu/diffusion.py:113)
 __global__ void mean_tokens_kernel(const bf16* __restrict__ x, bf16* y, int L, int C) {
   const int b = blockIdx.x;

@@ -841,20 +841,20 @@ extern "C" int emu_llm_prefill(EmuEngine* e, const void* inputs_embeds, const in
 // tensor-parallel tail of a row-parallel projection (o_proj / down_proj) in the decode loop: h += sum over ranks of W_r x_r.
 // Preferred: fp32 partial -> NVLink peer-memory push + flag + fixed-order reduce in ONE kernel (tp_exchange.cu);
 // otherwise NCCL all-reduce of the bf16 partial + add.
-static int row_parallel_tail(EmuEngine* e, GemvArgs& g, bf16* h, int B, int Hd, int idx, cudaStream_t st, int* nl,
-                             int* pending) {
+static int row_parallel_tail(EmuEngine* e, GemvArgs& g, bf16* h, int B, int Hd, int idx, cudaStream_t st, int* nl) {
   if (e->tp_p2p && e->tp_ll) {
     // fused: the GEMV epilogue itself pushes {value, flag} words to every rank; the poll + fixed-order reduce + residual
-    // add runs inside the next GEMV that reads h (tp_fold) or as one small kernel
+    // add is done by the first CTAs of the same kernel once their rows are out (tp_fold) or by one small kernel
     GemvArgs f = g;
     f.ldy = Hd;
     if (tp_ll_prepare(e, f, idx) == EMU_OK) {
+      if (e->tp_fold) {
+        f.ll_h = h;
+        f.ll_red = 32;
+      }
       const int rc = gemv_bf16(f, st);
       if (rc == EMU_OK) {
-        if (e->tp_fold) {
-          *pending = idx;
-          return EMU_OK;
-        }
+        if (e->tp_fold) return EMU_OK;
         EMU_TRY(tp_ll_reduce(e, h, (long)B * Hd, idx, g.pdl, st));
         *nl += 1;
         return EMU_OK;
@@ -883,13 +883,6 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
   const EmuConfig& c = e->cfg;
   const int Hd = c.llm_hidden, D = c.llm_head_dim, Hl = e->Hl, Fl = e->Fl;
   int nl = 0;
-  int pending = -1;  // tensor-parallel exchange whose reduce has not been applied to h yet (tp_fold)
-  auto take_pending = [&](GemvArgs& g) -> int {  // the GEMV reading h finishes the exchange in its prologue
-    if (pending < 0) return EMU_OK;
-    EMU_TRY(tp_xin_prepare(e, g, pending));
-    pending = -1;
-    return EMU_OK;
-  };
   bf16* h = e->dec_h;
   if (token_ids) {
     EMU_TRY(embed_gather(e->embed, token_ids, h, B, Hd, st));
@@ -910,7 +903,6 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
     q.y = e->dec_q; q.ldy = Hl * D; q.n_heads = Hl; q.head_dim = D;
     q.rope_cos = e->rope_cos; q.rope_sin = e->rope_sin; q.pos = e->d_pos; q.pos_off = e->d_posoff;
     q.k_cache = kc; q.v_cache = vc; q.t_max = c.llm_max_seq; q.pdl = (l > 0 || token_ids) ? pdl : 0;
-    EMU_TRY(take_pending(q));
     EMU_TRY(gemv_bf16(q, st));
     EMU_TRY(attn_decode(e->dec_q, kc, vc, B, Hl, D, c.llm_max_seq, e->d_pos, e->d_start, scale, e->dec_attn,
                         e->dec_attn_ws, e->dec_counters, c.llm_max_seq, pdl, st));
@@ -920,13 +912,12 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
       o.residual = h; o.ldr = Hd; o.y = h; o.ldy = Hd;
       EMU_TRY(gemv_bf16(o, st));
     } else {
-      EMU_TRY(row_parallel_tail(e, o, h, B, Hd, 2 * l, st, &nl, &pending));
+      EMU_TRY(row_parallel_tail(e, o, h, B, Hd, 2 * l, st, &nl));
     }
     GemvArgs g;
     g.W = L.wgu; g.N = 2 * Fl; g.K = Hd; g.x = h; g.ldx = Hd; g.B = B;
     g.norm_w = L.ln2; g.norm_eps = c.llm_rms_eps; g.mode = EPI_SWIGLU; g.y = e->dec_act; g.ldy = Fl;
     g.pdl = pdl;
-    EMU_TRY(take_pending(g));
     EMU_TRY(gemv_bf16(g, st));
     GemvArgs d;
     d.W = L.wdown; d.N = Hd; d.K = Fl; d.x = e->dec_act; d.ldx = Fl; d.B = B; d.pdl = pdl;
@@ -934,14 +925,9 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
       d.residual = h; d.ldr = Hd; d.y = h; d.ldy = Hd;
       EMU_TRY(gemv_bf16(d, st));
     } else {
-      EMU_TRY(row_parallel_tail(e, d, h, B, Hd, 2 * l + 1, st, &nl, &pending));
+      EMU_TRY(row_parallel_tail(e, d, h, B, Hd, 2 * l + 1, st, &nl));
     }
     nl += 5;
-  }
-  if (pending >= 0 && (hidden || !(logits || next_ids))) {  // no GEMV left to fold the last exchange into
-    EMU_TRY(tp_ll_reduce(e, h, (long)B * Hd, pending, pdl, st));
-    pending = -1;
-    ++nl;
   }
   if (hidden) {
     EMU_TRY(rmsnorm(h, e->final_norm, (bf16*)hidden, B, Hd, c.llm_rms_eps, 0, st));
@@ -953,7 +939,6 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
     g.W = e->lm_head; g.N = e->Vl; g.K = Hd; g.x = h; g.ldx = Hd; g.B = B;
     g.norm_w = e->final_norm; g.norm_eps = c.llm_rms_eps;
     g.out_fp32 = 1; g.pdl = pdl;
-    EMU_TRY(take_pending(g));
     if (e->tp_size == 1) {
       g.y = lg; g.ldy = c.llm_vocab;
       EMU_TRY(gemv_bf16(g, st));

@@ -48,7 +48,7 @@ struct EmuEngine {
   // NVLink peer-memory exchange for the decode loop (tp_exchange.cu); tp_peer[r] = rank r's exchange buffer mapped here
   bool tp_p2p = false;
   bool tp_ll = false;  // row-parallel GEMVs push {value, flag} words to the peers from their epilogue
-  bool tp_fold = false;  // ... and the poll + reduce runs inside the NEXT GEMV (GemvArgs::xin_*) instead of its own launch
+  bool tp_fold = false;  // ... and the first CTAs of the same GEMV finish the exchange (poll + reduce + residual add) in their tail
   float* tp_comm = nullptr;
   float* tp_peer[8] = {};
   float* dec_part = nullptr;  // this rank's fp32 partial of a row-parallel projection [Bmax, hidden]
@@ -113,7 +113,6 @@ void tp_exchange_teardown(EmuEngine* e);
 int tp_reduce_add(EmuEngine* e, const float* part, bf16* h, long n_elem, int pdl, cudaStream_t st);
 int tp_gather_logits(EmuEngine* e, const float* shard, float* logits, int B, int pdl, cudaStream_t st);
 int tp_ll_prepare(EmuEngine* e, GemvArgs& g, int idx);
-int tp_xin_prepare(EmuEngine* e, GemvArgs& g, int idx);
 int tp_ll_reduce(EmuEngine* e, bf16* h, long n_elem, int idx, int pdl, cudaStream_t st);
 unsigned* tp_step_counter(EmuEngine* e);
 

@@ -336,8 +336,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    f[8 * i + 2 * j] = round_bf16(f[8 * i + 2 * j]) + bf16_lo(bw[j]);
-                    f[8 * i + 2 * j + 1] = round_bf16(f[8 * i + 2 * j + 1]) + bf16_hi(bw[j]);
+                    round_bf16x2(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
+                    f[8 * i + 2 * j] += bf16_lo(bw[j]);
+                    f[8 * i + 2 * j + 1] += bf16_hi(bw[j]);
                   }
                 }
               } else {
@@ -348,7 +349,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (p.epi == EPI_GELU) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = gelu_erf_fast(round_bf16(f[i]));
+              for (int i = 0; i < 32; i += 2) {
+                round_bf16x2(f[i], f[i + 1]);
+                f[i] = gelu_erf_fast(f[i]);
+                f[i + 1] = gelu_erf_fast(f[i + 1]);
+              }
             } else if (p.epi == EPI_RELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
@@ -360,8 +365,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  f[8 * i + 2 * j] = round_bf16(f[8 * i + 2 * j]) + bf16_lo(rw[j]);
-                  f[8 * i + 2 * j + 1] = round_bf16(f[8 * i + 2 * j + 1]) + bf16_hi(rw[j]);
+                  round_bf16x2(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
+                  f[8 * i + 2 * j] += bf16_lo(rw[j]);
+                  f[8 * i + 2 * j + 1] += bf16_hi(rw[j]);
                 }
               }
             } else if (p.residual != nullptr && row_ok) {
@@ -373,8 +379,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    f[8 * i + 2 * j] = round_bf16(f[8 * i + 2 * j]) + bf16_lo(rw[j]);
-                    f[8 * i + 2 * j + 1] = round_bf16(f[8 * i + 2 * j + 1]) + bf16_hi(rw[j]);
+                    round_bf16x2(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
+                    f[8 * i + 2 * j] += bf16_lo(rw[j]);
+                    f[8 * i + 2 * j + 1] += bf16_hi(rw[j]);
                   }
                 }
               } else {
@@ -419,12 +426,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (ac0 + i < p.N) f[i] += __bfloat162float(p.bias[ac0 + i]);
                 }
               }
+              // rounding points of the reference (Linear -> bf16, activation -> bf16, product -> bf16), two values per
+              // conversion: (a_i, b_i) together, then the activations of two neighbouring outputs together
               float o[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float a = round_bf16(f[2 * i]), b = round_bf16(f[2 * i + 1]);
-                if (p.epi == EPI_SWIGLU) o[i] = round_bf16(silu(a)) * b;
-                else o[i] = a * round_bf16(gelu_erf_fast(b));
+              for (int i = 0; i < 16; i += 2) {
+                round_bf16x2(f[2 * i], f[2 * i + 1]);
+                round_bf16x2(f[2 * i + 2], f[2 * i + 3]);
+                float g0, g1;
+                if (p.epi == EPI_SWIGLU) { g0 = silu(f[2 * i]); g1 = silu(f[2 * i + 2]); }
+                else { g0 = gelu_erf_fast(f[2 * i + 1]); g1 = gelu_erf_fast(f[2 * i + 3]); }
+                round_bf16x2(g0, g1);
+                if (p.epi == EPI_SWIGLU) { o[i] = g0 * f[2 * i + 1]; o[i + 1] = g1 * f[2 * i + 3]; }
+                else { o[i] = f[2 * i] * g0; o[i + 1] = f[2 * i + 2] * g1; }
               }
 #pragma unroll
               for (int i = 0; i < 2; ++i) {

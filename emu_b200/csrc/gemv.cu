@@ -371,7 +371,7 @@ int gemv_bf16(const GemvArgs& a, cudaStream_t st) {
     const int rc = gemv_tma_bf16(a, st);
     if (rc != EMU_ERR_UNSUPPORTED) return rc;
   }
-  if (a.ll_n > 0 || a.xin_n > 0) return EMU_ERR_UNSUPPORTED;  // the fused exchange paths exist in the TMA kernel only
+  if (a.ll_n > 0) return EMU_ERR_UNSUPPORTED;  // the fused exchange epilogue exists in the TMA kernel only
   return gemv_reg_bf16(a, st);
 }
 

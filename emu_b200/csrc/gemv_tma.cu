@@ -20,57 +20,39 @@
 
 namespace emu {
 
-// consumer threads (256) of every CTA: finish the tensor-parallel exchange that feeds x (GemvArgs::xin_*)
-static __device__ __forceinline__ void gemv_reduce_pending_input(const GemvArgs& a) {
-  const unsigned epoch = __ldcg(a.xin_step) * 256u + (unsigned)a.xin_idx + 1u;
-  const int R = a.xin_red;
-  if ((int)blockIdx.x < R) {
-    const uint4* base = reinterpret_cast<const uint4*>(a.xin_ll) + ((size_t)(a.xin_idx & 1) * a.xin_n * a.xin_slot_elems) / 2;
-    const long n2 = ((long)a.B * a.K) >> 1;  // element pairs (h is [B, K] contiguous, K even)
-    const long per = (n2 + R - 1) / R;
-    const long i0 = (long)blockIdx.x * per, i1 = min(n2, i0 + per);
-    uint32_t* h = reinterpret_cast<uint32_t*>(const_cast<bf16*>(a.x));
-    for (long i = i0 + threadIdx.x; i < i1; i += 256) {
-      float a0 = 0.f, a1 = 0.f;
-      for (int r = 0; r < a.xin_n; ++r) {
-        const uint4* w = base + ((size_t)r * a.xin_slot_elems) / 2 + i;
-        uint4 v;
-        unsigned long long t0 = 0, now;
-        for (;;) {
-          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(w));
-          if (v.y == epoch && v.w == epoch) break;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-          if (t0 == 0) t0 = now;
-          else if (now - t0 > 20000000000ull) {  // 20 s: a peer died — fail loudly instead of hanging the GPU
-            printf("emu_b200: tensor-parallel exchange %d timed out waiting for rank %d\n", a.xin_idx, r);
-            __trap();
-          }
+// consumer threads (256) of the first ll_red CTAs, after their own rows are pushed: finish the tensor-parallel exchange
+// (GemvArgs::ll_h).  The words polled here are written by the epilogues of this very kernel — on this rank (all CTAs are
+// resident: grid <= SM count) and on the peers.
+static __device__ __forceinline__ void gemv_tail_reduce(const GemvArgs& a) {
+  const unsigned epoch = __ldcg(a.ll_step) * 256u + (unsigned)a.ll_idx + 1u;
+  const int R = a.ll_red;
+  const uint4* base = reinterpret_cast<const uint4*>(a.ll_peer[a.ll_rank]) + ((size_t)(a.ll_idx & 1) * a.ll_n * a.ll_slot_elems) / 2;
+  const long n2 = ((long)a.B * a.ldy) >> 1;  // element pairs of h [B, ldy]
+  const long per = (n2 + R - 1) / R;
+  const long i0 = (long)blockIdx.x * per, i1 = min(n2, i0 + per);
+  uint32_t* h = reinterpret_cast<uint32_t*>(a.ll_h);
+  for (long i = i0 + threadIdx.x; i < i1; i += 256) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = 0; r < a.ll_n; ++r) {
+      const uint4* w = base + ((size_t)r * a.ll_slot_elems) / 2 + i;
+      uint4 v;
+      unsigned long long t0 = 0, now;
+      for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(w));
+        if (v.y == epoch && v.w == epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) {  // 20 s: a peer died — fail loudly instead of hanging the GPU
+          printf("emu_b200: tensor-parallel exchange %d timed out waiting for rank %d\n", a.ll_idx, r);
+          __trap();
         }
-        a0 += __uint_as_float(v.x);  // fixed rank order: bitwise identical on every rank
-        a1 += __uint_as_float(v.z);
       }
-      const uint32_t hv = __ldcg(h + i);
-      h[i] = pack_bf16(bf16_lo(hv) + round_bf16(a0), bf16_hi(hv) + round_bf16(a1));
+      a0 += __uint_as_float(v.x);  // fixed rank order: bitwise identical on every rank
+      a1 += __uint_as_float(v.z);
     }
-    __threadfence();
-    consumer_bar();
-    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.xin_flags + blockIdx.x), "r"(epoch) : "memory");
+    const uint32_t hv = __ldcg(h + i);
+    h[i] = pack_bf16(bf16_lo(hv) + round_bf16(a0), bf16_hi(hv) + round_bf16(a1));
   }
-  if ((int)threadIdx.x < R) {
-    unsigned long long t0 = 0, now;
-    for (;;) {
-      unsigned v;
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.xin_flags + threadIdx.x) : "memory");
-      if ((int)(v - epoch) >= 0) break;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 25000000000ull) {
-        printf("emu_b200: waiting for the in-kernel exchange reduce %d timed out\n", a.xin_idx);
-        __trap();
-      }
-    }
-  }
-  consumer_bar();
 }
 
 __global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_constant__ CUtensorMap tmW,
@@ -110,10 +92,10 @@ __global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_con
     return;
   }
   if (p.a.pdl) pdl_wait();
-  if (p.a.xin_n > 0) gemv_reduce_pending_input(p.a);
   const int xsc = (p.xsc > 0 && p.xsc < p.cpt) ? p.xsc : p.cpt;
   tma_stage_x(p, xs, s_ss, s_rstd, (int)(c0 % p.cpt) / xsc);
   tma_consume(&s_params, c0, c1, ring, full_bar, empty_bar, red, fin, xs, &s_last, stage, phase, s_rstd);
+  if (p.a.ll_n > 0 && p.a.ll_h != nullptr && (int)blockIdx.x < p.a.ll_red) gemv_tail_reduce(p.a);
 }
 
 static float* g_tws = nullptr;
@@ -188,10 +170,9 @@ int gemv_tma_bf16(const GemvArgs& a, cudaStream_t st) {
   const long max_grid = (long)groups * (kTMaxParts - 3);
   if (grid > max_grid) grid = max_grid;
   p.geff = (int)grid;
-  if (p.a.xin_n > 0) {
-    if (p.a.xin_red < 1 || !p.a.xin_flags || !p.a.xin_ll || !p.a.xin_step || (a.K & 1) || a.ldx != a.K) return EMU_ERR_INVALID;
-    if (p.a.xin_red > (int)grid) p.a.xin_red = (int)grid;
-    if (p.a.xin_red > 256) p.a.xin_red = 256;
+  if (p.a.ll_n > 0 && p.a.ll_h) {
+    if (p.a.ll_red < 1 || (a.ldy & 1)) return EMU_ERR_INVALID;
+    if (p.a.ll_red > (int)grid) p.a.ll_red = (int)grid;
   }
   CUtensorMap tm;
   if (make_tmap_2d(&tm, a.W, a.N, a.K, a.K, kTRows) != EMU_OK) return EMU_ERR_UNSUPPORTED;

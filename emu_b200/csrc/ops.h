@@ -72,16 +72,12 @@ struct GemvArgs {
   int ll_n = 0, ll_rank = 0, ll_idx = 0;
   long ll_slot_elems = 0;
   const unsigned* ll_step = nullptr;
-  // Pending tensor-parallel exchange on the INPUT side (x is the residual stream h, [B, K] contiguous): the row-parallel
-  // GEMV that produced exchange xin_idx only PUSHED its {value, flag} words; before x is staged, the first xin_red CTAs of
-  // THIS kernel poll the words of all xin_n ranks in this rank's receive buffer xin_ll, add their fixed-order sum to h in
-  // place (projection rounded to bf16 first, like the unsharded model) and publish the epoch in xin_flags; every CTA
-  // waits for those flags.  Replaces the separate poll + reduce launch; the weight ring keeps filling meanwhile.
-  const void* xin_ll = nullptr;
-  int xin_n = 0, xin_idx = 0, xin_red = 0;
-  long xin_slot_elems = 0;
-  const unsigned* xin_step = nullptr;
-  unsigned* xin_flags = nullptr;  // [>= xin_red] device words, monotonically increasing epochs
+  // ... and, when ll_h is set, the first ll_red CTAs of the SAME kernel finish the exchange once their own rows are out:
+  // they poll the {value, flag} words of all ranks in this rank's receive buffer (ll_peer[ll_rank]), add the fixed-order sum
+  // to the residual stream ll_h [B, ldy] in place (projection rounded to bf16 first, like the unsharded model).  No
+  // separate poll + reduce launch, and the successor's CTAs start filling their weight rings on the SMs that are done.
+  bf16* ll_h = nullptr;
+  int ll_red = 0;
 };
 constexpr int GEMV_ROPE_QKV = 16;
 int gemv_bf16(const GemvArgs& a, cudaStream_t st);

@@ -31,7 +31,7 @@ constexpr int kTpThreads = 256;
 struct TpLayout {
   size_t red_slot;     // floats per reduce slot  (Bmax * hidden)
   size_t gat_slot;     // floats per gather slot  (Bmax * Vl)
-  size_t red_off, gat_off, flag_red_off, flag_gat_off, seq_off, ll_off, step_off, xin_off, total;  // in floats / 4-byte words
+  size_t red_off, gat_off, flag_red_off, flag_gat_off, seq_off, ll_off, step_off, total;  // in floats / 4-byte words
 };
 static TpLayout tp_layout(int n, int bmax, int hidden, int vl) {
   TpLayout L;
@@ -44,8 +44,7 @@ static TpLayout tp_layout(int n, int bmax, int hidden, int vl) {
   L.seq_off = L.flag_gat_off + (size_t)8 * kTpMaxCtas;
   L.ll_off = (L.seq_off + 2 * kTpMaxCtas + 3) / 4 * 4;  // {value, flag} words: 2 floats per element
   L.step_off = L.ll_off + 2 * 2 * (size_t)n * L.red_slot;
-  L.xin_off = L.step_off + 4;  // 256 epoch words of the in-kernel input reduce (GemvArgs::xin_flags)
-  L.total = L.xin_off + 256;
+  L.total = L.step_off + 4;
   return L;
 }
 
@@ -232,17 +231,6 @@ int tp_ll_prepare(EmuEngine* e, GemvArgs& g, int idx) {
   g.ll_n = e->tp_size; g.ll_rank = e->tp_rank; g.ll_idx = idx;
   g.ll_slot_elems = (long)L.red_slot;
   g.ll_step = reinterpret_cast<const unsigned*>(e->tp_peer[e->tp_rank] + L.step_off);
-  return EMU_OK;
-}
-// fill the pending-input-exchange fields of the GEMV that consumes h after exchange idx (see GemvArgs::xin_*)
-int tp_xin_prepare(EmuEngine* e, GemvArgs& g, int idx) {
-  if (!e->tp_p2p || !e->tp_ll) return EMU_ERR_UNSUPPORTED;
-  const TpLayout L = tp_layout(e->tp_size, e->cfg.llm_max_batch, e->cfg.llm_hidden, e->Vl);
-  g.xin_ll = e->tp_peer[e->tp_rank] + L.ll_off;
-  g.xin_n = e->tp_size; g.xin_idx = idx; g.xin_red = 32;
-  g.xin_slot_elems = (long)L.red_slot;
-  g.xin_step = reinterpret_cast<const unsigned*>(e->tp_peer[e->tp_rank] + L.step_off);
-  g.xin_flags = reinterpret_cast<unsigned*>(e->tp_peer[e->tp_rank] + L.xin_off);
   return EMU_OK;
 }
 unsigned* tp_step_counter(EmuEngine* e) {

@@ -90,6 +90,7 @@ static void reg_resnet(UNetModel* m, const std::string& p, ResnetW& r, int cin, 
 }
 static void reg_trans(UNetModel* m, const std::string& p, TransW& t, int c, int layers, int cd) {
   t.c = c;
+  t.hd = m->cfg.head_dim > 0 ? m->cfg.head_dim : c / m->cfg.num_heads;
   reg_norm(m->specs, p + "norm", t.gn, c);
   reg_lin(m->specs, p + "proj_in", t.pin, c, c);
   reg_lin(m->specs, p + "proj_out", t.pout, c, c);
@@ -122,7 +123,13 @@ using namespace emu;
 
 extern "C" int emu_unet_configure(EmuEngine* e, const EmuUNetConfig* cfg) {
   if (!e || !cfg) return EMU_ERR_INVALID;
-  if (cfg->n_blocks < 2 || cfg->n_blocks > 4 || cfg->head_dim != 64) return e->fail(EMU_ERR_UNSUPPORTED, "unet config");
+  if (cfg->n_blocks < 2 || cfg->n_blocks > 4) return e->fail(EMU_ERR_UNSUPPORTED, "unet config: 2..4 blocks");
+  for (int i = 0; i < cfg->n_blocks; ++i) {  // head width per level: fixed (SDXL) or C / num_heads (SD-1.5)
+    if (cfg->transformer_layers[i] <= 0 && !(i == cfg->n_blocks - 1 && cfg->mid_transformer_layers > 0)) continue;
+    const int C = cfg->block_out_channels[i];
+    const int hd = cfg->head_dim > 0 ? cfg->head_dim : (cfg->num_heads > 0 ? C / cfg->num_heads : 0);
+    if (hd < 8 || hd > 160 || hd % 8 || C % hd) return e->fail(EMU_ERR_UNSUPPORTED, "unet config: head width");
+  }
   if (e->unet) { unet_destroy(e->unet); e->unet = nullptr; }
   UNetModel* m = new UNetModel();
   m->cfg = *cfg;
@@ -157,7 +164,8 @@ extern "C" int emu_unet_configure(EmuEngine* e, const EmuUNetConfig* cfg) {
     }
   }
   reg_resnet(m, "mid_block.resnets.0.", m->mid_r0, cin, cin, temb);
-  if (tl[nb - 1] > 0) reg_trans(m, "mid_block.attentions.0.", m->mid_att, cin, tl[nb - 1], cd);
+  const int mid_layers = cfg->mid_transformer_layers > 0 ? cfg->mid_transformer_layers : tl[nb - 1];
+  if (mid_layers > 0) reg_trans(m, "mid_block.attentions.0.", m->mid_att, cin, mid_layers, cd);
   reg_resnet(m, "mid_block.resnets.1.", m->mid_r1, cin, cin, temb);
   for (int i = 0; i < nb; ++i) {
     const int ri = nb - 1 - i;
@@ -175,7 +183,7 @@ extern "C" int emu_unet_configure(EmuEngine* e, const EmuUNetConfig* cfg) {
   }
   reg_norm(m->specs, "conv_norm_out", m->norm_out, boc[0]);
   reg_conv(m->specs, "conv_out", m->conv_out, cfg->out_channels, boc[0], 3);
-  m->step_params = (float*)e->dmalloc(8 * sizeof(float));
+  m->step_params = (float*)e->dmalloc(16 * sizeof(float));
   if (!m->step_params) { delete m; return e->fail(EMU_ERR_NOMEM, "unet params alloc"); }
   // engines created as a pair (tp_size == 2) set up the CFG-parallel exchange here: COLLECTIVE over both ranks
   const int xrc = unet_exchange_setup(e, m);
@@ -449,7 +457,7 @@ static int resnet(Ctx& c, const ResnetW& r, const bf16* x, bf16* y, int NB, int 
 
 // Transformer2DModel (linear projections): x [NB, T, C] (NHWC tokens) -> y
 static int transformer2d(Ctx& c, const TransW& t, const bf16* x, bf16* y, int NB, int T, const bf16* ctxv, int L, int cd) {
-  const int C = t.c, Hh = C / 64;
+  const int C = t.c, hd = t.hd, Hh = C / hd;
   const long M = (long)NB * T;
   BUF(n, "tf_norm", M * C);
   BUF(h, "tf_h", M * C);
@@ -459,7 +467,7 @@ static int transformer2d(Ctx& c, const TransW& t, const bf16* x, bf16* y, int NB
   BUF(ff, "tf_ff", M * 4 * C);
   EMU_TRY(gnorm(c, x, t.gn, n, NB, T, 1e-6f, 0));
   EMU_TRY(lin_rows(c, n, (int)M, t.pin, h));
-  const float scale = 0.125f;  // 64^-0.5
+  const float scale = 1.0f / sqrtf((float)hd);
   for (const TBlockW& b : t.blocks) {
     // self-attention
     EMU_TRY(layernorm(h, b.n1.w, b.n1.b, nullptr, n, (int)M, C, 1e-5f, c.st));
@@ -468,9 +476,9 @@ static int transformer2d(Ctx& c, const TransW& t, const bf16* x, bf16* y, int NB
     EMU_TRY(gemm_bf16(n, C, b.wqkv, C, (int)M, 3 * C, C, e1, c.st));
     AttnArgs a;
     a.q = qkv; a.k = qkv + C; a.v = qkv + 2 * C;
-    a.q_bs = a.k_bs = a.v_bs = (long)T * 3 * C; a.q_ts = a.k_ts = a.v_ts = 3 * C; a.q_hs = a.k_hs = a.v_hs = 64;
-    a.out = att; a.o_bs = (long)T * C; a.o_ts = C; a.o_hs = 64;
-    a.B = NB; a.H = Hh; a.Nq = T; a.Nk = T; a.D = 64; a.scale = scale;
+    a.q_bs = a.k_bs = a.v_bs = (long)T * 3 * C; a.q_ts = a.k_ts = a.v_ts = 3 * C; a.q_hs = a.k_hs = a.v_hs = hd;
+    a.out = att; a.o_bs = (long)T * C; a.o_ts = C; a.o_hs = hd;
+    a.B = NB; a.H = Hh; a.Nq = T; a.Nk = T; a.D = hd; a.scale = scale;
     EMU_TRY(attn_prefill(a, c.st));
     EMU_TRY(lin_rows(c, att, (int)M, b.o1, h, h));
     // cross-attention to the 64 regressed visual tokens
@@ -479,18 +487,18 @@ static int transformer2d(Ctx& c, const TransW& t, const bf16* x, bf16* y, int NB
     e2.C = qkv; e2.ldc = C;
     EMU_TRY(gemm_bf16(n, C, b.wq2, C, (int)M, C, C, e2, c.st));
     AttnArgs x2;
-    x2.q = qkv; x2.q_bs = (long)T * C; x2.q_ts = C; x2.q_hs = 64;
+    x2.q = qkv; x2.q_bs = (long)T * C; x2.q_ts = C; x2.q_hs = hd;
     if (c.kv_all && b.kv_off >= 0) {
       x2.k = c.kv_all + b.kv_off; x2.v = x2.k + C;
-      x2.k_bs = x2.v_bs = (long)L * c.kv_ld; x2.k_ts = x2.v_ts = c.kv_ld; x2.k_hs = x2.v_hs = 64;
+      x2.k_bs = x2.v_bs = (long)L * c.kv_ld; x2.k_ts = x2.v_ts = c.kv_ld; x2.k_hs = x2.v_hs = hd;
     } else {
       GemmEpilogue e3;
       e3.C = kv; e3.ldc = 2 * C;
       EMU_TRY(gemm_bf16(ctxv, cd, b.wkv2, cd, NB * L, 2 * C, cd, e3, c.st));
-      x2.k = kv; x2.v = kv + C; x2.k_bs = x2.v_bs = (long)L * 2 * C; x2.k_ts = x2.v_ts = 2 * C; x2.k_hs = x2.v_hs = 64;
+      x2.k = kv; x2.v = kv + C; x2.k_bs = x2.v_bs = (long)L * 2 * C; x2.k_ts = x2.v_ts = 2 * C; x2.k_hs = x2.v_hs = hd;
     }
-    x2.out = att; x2.o_bs = (long)T * C; x2.o_ts = C; x2.o_hs = 64;
-    x2.B = NB; x2.H = Hh; x2.Nq = T; x2.Nk = L; x2.D = 64; x2.scale = scale;
+    x2.out = att; x2.o_bs = (long)T * C; x2.o_ts = C; x2.o_hs = hd;
+    x2.B = NB; x2.H = Hh; x2.Nq = T; x2.Nk = L; x2.D = hd; x2.scale = scale;
     EMU_TRY(attn_prefill(x2, c.st));
     EMU_TRY(lin_rows(c, att, (int)M, b.o2, h, h));
     // GEGLU feed-forward
@@ -720,9 +728,11 @@ extern "C" int emu_unet_forward(EmuEngine* e, const void* latents_nchw, float ti
   return EMU_OK;
 }
 
-extern "C" int emu_denoise_step(EmuEngine* e, float* latents, float sigma, float sigma_next, float timestep,
-                                float guidance, const void* ctxv, int L, const void* text_embeds,
-                                const int32_t* time_ids, int B, int h, int w, emu_stream_t stream) {
+// One denoise iteration.  ms == nullptr: Euler (Emu2-Gen); otherwise the 8 linear-multistep scalars of cfg_multistep_kernel
+// (PNDM, Emu1) with `state` = [4][B*C*h*w] fp32 (3 history planes + the saved sample).
+static int denoise_step_impl(EmuEngine* e, float* latents, float sigma, float sigma_next, float timestep, float guidance,
+                             const float* ms, float* state, const void* ctxv, int L, const void* text_embeds,
+                             const int32_t* time_ids, int B, int h, int w, emu_stream_t stream) {
   if (!e || !latents || !ctxv || B < 1) return EMU_ERR_INVALID;
   EMU_TRY(unet_ready(e));
   UNetModel* m = e->unet;
@@ -741,7 +751,13 @@ extern "C" int emu_denoise_step(EmuEngine* e, float* latents, float sigma, float
     if (time_ids) time_ids = time_ids + (size_t)e->tp_rank * B * 6;
   }
   // per-step scalars go through device memory so the captured graph is step-independent
-  float hp[4] = {sigma, sigma_next, guidance, timestep};
+  float hp[12] = {sigma, sigma_next, guidance, timestep, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (ms) {
+    for (int i = 0; i < 6; ++i) hp[4 + i] = ms[i];
+    hp[10] = guidance;
+    hp[11] = ms[7];
+  }
+  if (ms && split) return e->fail(EMU_ERR_UNSUPPORTED, "CFG-parallel exchange with the multistep scheduler");
   if (cudaMemcpyAsync(m->step_params, hp, sizeof(hp), cudaMemcpyHostToDevice, st) != cudaSuccess)
     return e->fail(EMU_ERR_CUDA, "step params copy");
   cudaStreamSynchronize(st);  // hp is a stack buffer
@@ -761,6 +777,9 @@ extern "C" int emu_denoise_step(EmuEngine* e, float* latents, float sigma, float
       cfg_exchange_euler_kernel<<<grid, 256, 0, s>>>(latents, eps, m->xch, m->xch_peer, e->tp_rank, B, m->cfg.out_channels,
                                                      h * w, m->step_params);
       if (cudaGetLastError() != cudaSuccess) return e->fail(EMU_ERR_CUDA, "CFG-parallel exchange launch failed");
+    } else if (ms) {
+      const long n = (long)B * m->cfg.out_channels * h * w;
+      EMU_TRY(cfg_multistep(latents, eps, state, state + 3 * n, B, m->cfg.out_channels, h * w, 8, m->step_params + 4, cfg, s));
     } else {
       EMU_TRY(cfg_euler(latents, eps, B, m->cfg.out_channels, h * w, 8, m->step_params, cfg, s));
     }
@@ -769,8 +788,8 @@ extern "C" int emu_denoise_step(EmuEngine* e, float* latents, float sigma, float
   };
   const char* no_graph = getenv("EMU_NO_GRAPH");
   const bool use_graph = e->use_graphs && !(no_graph && no_graph[0] == '1');
-  auto key = std::make_tuple((const void*)latents, (const void*)ctxv, (const void*)text_embeds, (const void*)time_ids, B, h,
-                             w * 4 + cfg + 2 * split, L);
+  auto key = std::make_tuple((const void*)latents, (const void*)ctxv, (const void*)text_embeds,
+                             ms ? (const void*)state : (const void*)time_ids, B, h, w * 4 + cfg + 2 * split, L);
   auto it = m->graphs.find(key);
   if (use_graph && it != m->graphs.end()) {
     if (cudaGraphLaunch(it->second, st) != cudaSuccess) return e->fail(EMU_ERR_CUDA, "denoise graph launch failed");
@@ -812,4 +831,18 @@ extern "C" int emu_denoise_step(EmuEngine* e, float* latents, float sigma, float
   if (cudaGraphLaunch(exec, st) != cudaSuccess) return e->fail(EMU_ERR_CUDA, "denoise graph launch failed");
   count_launch(nl);
   return EMU_OK;
+}
+
+extern "C" int emu_denoise_step(EmuEngine* e, float* latents, float sigma, float sigma_next, float timestep,
+                                float guidance, const void* ctxv, int L, const void* text_embeds,
+                                const int32_t* time_ids, int B, int h, int w, emu_stream_t stream) {
+  return denoise_step_impl(e, latents, sigma, sigma_next, timestep, guidance, nullptr, nullptr, ctxv, L, text_embeds, time_ids,
+                           B, h, w, stream);
+}
+
+extern "C" int emu_denoise_step_multistep(EmuEngine* e, float* latents, float* state, const float* host_coef8, float timestep,
+                                          float guidance, const void* ctxv, int L, int B, int h, int w, emu_stream_t stream) {
+  if (!state || !host_coef8) return EMU_ERR_INVALID;
+  return denoise_step_impl(e, latents, 0.f, 0.f, timestep, guidance, host_coef8, state, ctxv, L, nullptr, nullptr, B, h, w,
+                           stream);
 }

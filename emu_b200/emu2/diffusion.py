@@ -64,17 +64,28 @@ def unet_config_from_json(cfg: dict) -> "_lib.EmuUNetConfig":
         u.block_out_channels[i] = c
         u.transformer_layers[i] = tl[i] if "CrossAttn" in cfg["down_block_types"][i] else 0
     u.layers_per_block = cfg["layers_per_block"]
-    ahd = cfg["attention_head_dim"]
-    # SDXL configs store the number of heads in `attention_head_dim`; the head width is C / heads
-    heads = ahd if isinstance(ahd, (list, tuple)) else [ahd] * len(boc)
-    u.head_dim = boc[-1] // heads[-1]
+    # the mid block (UNetMidBlock2DCrossAttn) takes transformer_layers_per_block[-1] whatever the last down block is
+    u.mid_transformer_layers = tl[-1] if cfg.get("mid_block_type", "UNetMidBlock2DCrossAttn") == "UNetMidBlock2DCrossAttn" else 0
+    ahd = cfg.get("num_attention_heads") or cfg["attention_head_dim"]
+    # diffusers UNet2DConditionModel reads `attention_head_dim` as the NUMBER OF HEADS per level (a long-standing naming quirk):
+    # SDXL [5, 10, 20] -> width 64 everywhere; SD-1.5 8 -> widths 40 / 80 / 160 / 160 (the Emu1 visual decoder)
+    heads = list(ahd) if isinstance(ahd, (list, tuple)) else [ahd] * len(boc)
+    has_attn = [u.transformer_layers[i] > 0 for i in range(len(boc))]
+    has_attn[-1] = has_attn[-1] or u.mid_transformer_layers > 0
+    widths = {c // h for c, h, t in zip(boc, heads, has_attn) if t}
+    if len(widths) == 1:
+        u.head_dim, u.num_heads = widths.pop(), 0
+    elif len(set(heads)) == 1:
+        u.head_dim, u.num_heads = 0, heads[0]
+    else:
+        raise NotImplementedError("attention heads %r over channels %r" % (heads, boc))
     u.cross_attention_dim = cfg["cross_attention_dim"]
     u.use_linear_projection = 1 if cfg.get("use_linear_projection") else 0
     u.addition_time_embed_dim = cfg.get("addition_time_embed_dim") or 0
     u.projection_class_embeddings_input_dim = cfg.get("projection_class_embeddings_input_dim") or 0
     u.norm_groups, u.norm_eps = cfg["norm_num_groups"], cfg["norm_eps"]
-    if not u.use_linear_projection:
-        raise NotImplementedError("conv proj_in/proj_out (SD-1.5 style) is not wired yet")
+    # use_linear_projection=False (SD-1.5): proj_in / proj_out are 1x1 convolutions — on NHWC tokens that is the same
+    # Linear, and the engine accepts their [C, C, 1, 1] weights as they are
     return u
 
 

@@ -117,13 +117,17 @@ typedef struct EmuUNetConfig {
   int block_out_channels[4];
   int layers_per_block;
   int transformer_layers[4];       /* per down block; 0 = no attention in that block */
-  int head_dim;                    /* 64 */
+  int head_dim;                    /* attention head width (SDXL: 64); 0 = use num_heads instead */
   int cross_attention_dim;
   int use_linear_projection;
   int addition_time_embed_dim;     /* 0 = no text_time conditioning (SD-1.5 class) */
   int projection_class_embeddings_input_dim;
   int norm_groups;
   float norm_eps;
+  int mid_transformer_layers;      /* transformer layers of the mid block; 0 = as many as the last down block (SDXL).  SD-1.5 has
+                                      a plain last down block but one cross-attention layer in the mid block */
+  int num_heads;                   /* used when head_dim == 0: the same head COUNT at every level (SD-1.5: 8 heads, i.e. head
+                                      widths 40 / 80 / 160 — the Emu1 pipeline, Emu1/models/pipeline.py:37-39) */
 } EmuUNetConfig;
 int emu_unet_configure(EmuEngine* e, const EmuUNetConfig* cfg);
 int emu_unet_forward(EmuEngine* e, const void* latents_nchw /*[B2,C,h,w] bf16*/, float timestep,
@@ -134,6 +138,15 @@ int emu_unet_forward(EmuEngine* e, const void* latents_nchw /*[B2,C,h,w] bf16*/,
 int emu_denoise_step(EmuEngine* e, float* latents_inout, float sigma, float sigma_next, float timestep, float guidance,
                      const void* ctx, int L, const void* text_embeds, const int32_t* time_ids, int B, int h, int w,
                      emu_stream_t s);
+/* The same fused iteration with a linear multistep scheduler instead of Euler — PNDM / PLMS as the Emu1 pipeline runs it
+ * (Emu1/models/pipeline.py:112-127: scale_model_input = identity, unet, CFG, PNDMScheduler.step with skip_prk_steps):
+ *   e = CFG(eps);  m = wc*e + w0*h0 + w1*h1 + w2*h2;  x_prev = a * x + b * m
+ * host_coef8 (HOST, 8 floats) = {a, b, wc, w0, w1, w2, unused, flags}; flags bit 0: push e into the eps history, bit 1: x is the
+ * sample saved earlier (PLMS repeats its first timestep), bit 2: save the incoming latent.  state: DEVICE fp32 [4][B*C*h*w]
+ * (three history planes, newest first, + the saved sample), zero-initialised by the caller.  ctx = [cond; uncond] [2B, L, Cc]
+ * when guidance > 1.  The scalars are computed by emu_b200/emu1/scheduler.py from the scheduler config. */
+int emu_denoise_step_multistep(EmuEngine* e, float* latents_inout, float* state, const float* host_coef8, float timestep,
+                               float guidance, const void* ctx, int L, int B, int h, int w, emu_stream_t s);
 typedef struct EmuVAEConfig {
   int latent_channels, out_channels, n_blocks;
   int block_out_channels[4];

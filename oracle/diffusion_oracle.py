@@ -24,6 +24,13 @@ EMU2_UNET = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 12
                  transformer_layers_per_block=(0, 2, 10),  # block 0 is DownBlock2D: its "1" is unused
                  attention_head_dim=64, cross_attention_dim=1792, addition_time_embed_dim=256,
                  projection_class_embeddings_input_dim=3328, norm_num_groups=32, norm_eps=1e-5)
+# Emu1 visual decoder: Stable-Diffusion-1.5 topology (the reference loads it from <ckpt>/unet/config.json,
+# Emu1/models/pipeline.py:37-39): 1x1-conv proj_in / proj_out, 8 heads per level (widths 40 / 80 / 160), no added conditioning,
+# cross-attention over the 32 regressed embeddings of width 5120
+EMU1_UNET = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+                 transformer_layers_per_block=(1, 1, 1, 0), num_heads=8, cross_attention_dim=5120, use_linear_projection=False,
+                 norm_num_groups=32, norm_eps=1e-5)
+EMU1_SCHED = dict(beta_start=0.00085, beta_end=0.012, num_train_timesteps=1000, steps_offset=1)
 EMU2_SCHED = dict(beta_start=0.00085, beta_end=0.012, num_train_timesteps=1000, steps_offset=1)
 EMU2_VAE = dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                 norm_num_groups=32, scaling_factor=0.13025)
@@ -41,7 +48,10 @@ def timestep_embedding(t, dim, dtype):
 
 
 def linear(sd, p, x):
-    return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
+    w = sd[p + ".weight"]
+    if w.dim() == 4:  # a 1x1 convolution applied to channel-last tokens (SD-1.5 proj_in / proj_out)
+        w = w.reshape(w.shape[0], w.shape[1])
+    return F.linear(x, w, sd.get(p + ".bias"))
 
 
 def conv(sd, p, x, stride=1, padding=1):
@@ -107,8 +117,10 @@ def transformer_2d(sd, p, x, ctx, n_layers, groups, head_dim):
 def unet_forward(sd, cfg, sample, timestep, ctx, text_embeds=None, time_ids=None, prefix=""):
     """sample [B,4,h,w]; timestep scalar; ctx [B,L,cross_dim]; text_embeds [B,cross_dim]; time_ids [B,6].
     Returns the predicted noise [B,4,h,w].  Call site: Emu2/emu/diffusion.py:136-141."""
-    g, eps, hd = cfg["norm_num_groups"], cfg["norm_eps"], cfg["attention_head_dim"]
+    g, eps = cfg["norm_num_groups"], cfg["norm_eps"]
     boc = cfg["block_out_channels"]
+    # head width: fixed (SDXL, `attention_head_dim`) or channels / num_heads (SD-1.5: the same head COUNT at every level)
+    hd_of = (lambda c: cfg["attention_head_dim"]) if cfg.get("attention_head_dim") else (lambda c: c // cfg["num_heads"])
     tl = cfg["transformer_layers_per_block"]
     lpb = cfg["layers_per_block"]
     nb = len(boc)
@@ -128,14 +140,17 @@ def unet_forward(sd, cfg, sample, timestep, ctx, text_embeds=None, time_ids=None
         for j in range(lpb):
             h = resnet_block(sd, f"{P}down_blocks.{i}.resnets.{j}.", h, emb, g, eps)
             if tl[i] > 0:
-                h = transformer_2d(sd, f"{P}down_blocks.{i}.attentions.{j}.", h, ctx, tl[i], g, hd)
+                h = transformer_2d(sd, f"{P}down_blocks.{i}.attentions.{j}.", h, ctx, tl[i], g, hd_of(boc[i]))
             skips.append(h)
         if i < nb - 1:
             h = conv(sd, f"{P}down_blocks.{i}.downsamplers.0.conv", h, stride=2, padding=1)
             skips.append(h)
     h = resnet_block(sd, P + "mid_block.resnets.0.", h, emb, g, eps)
-    if tl[-1] > 0:
-        h = transformer_2d(sd, P + "mid_block.attentions.0.", h, ctx, tl[-1], g, hd)
+    if (P + "mid_block.attentions.0.norm.weight") in sd:
+        h = transformer_2d(sd, P + "mid_block.attentions.0.", h, ctx, cfg.get("mid_block_layers", max(tl[-1], 1)), g,
+                           hd_of(boc[-1]))
+    elif tl[-1] > 0:
+        h = transformer_2d(sd, P + "mid_block.attentions.0.", h, ctx, tl[-1], g, hd_of(boc[-1]))
     h = resnet_block(sd, P + "mid_block.resnets.1.", h, emb, g, eps)
     for i in range(nb):
         ri = nb - 1 - i  # reversed block index
@@ -143,7 +158,7 @@ def unet_forward(sd, cfg, sample, timestep, ctx, text_embeds=None, time_ids=None
             h = torch.cat([h, skips.pop()], dim=1)
             h = resnet_block(sd, f"{P}up_blocks.{i}.resnets.{j}.", h, emb, g, eps)
             if tl[ri] > 0:
-                h = transformer_2d(sd, f"{P}up_blocks.{i}.attentions.{j}.", h, ctx, tl[ri], g, hd)
+                h = transformer_2d(sd, f"{P}up_blocks.{i}.attentions.{j}.", h, ctx, tl[ri], g, hd_of(boc[ri]))
         if i < nb - 1:
             h = F.interpolate(h, scale_factor=2.0, mode="nearest")
             h = conv(sd, f"{P}up_blocks.{i}.upsamplers.0.conv", h)
@@ -181,9 +196,17 @@ def unet_param_shapes(cfg):
         if cin != cout:
             cv(p + "conv_shortcut", cout, cin, 1)
 
+    conv_proj = cfg.get("use_linear_projection", True) is False
+
+    def proj(p, c):
+        if conv_proj:
+            cv(p, c, c, 1)
+        else:
+            lin(p, c, c)
+
     def tfm(p, c, n):
         nrm(p + "norm", c)
-        lin(p + "proj_in", c, c)
+        proj(p + "proj_in", c)
         for k in range(n):
             q = f"{p}transformer_blocks.{k}."
             for a, kd in (("attn1.", c), ("attn2.", cd)):
@@ -195,7 +218,7 @@ def unet_param_shapes(cfg):
                 nrm(q + n_, c)
             lin(q + "ff.net.0.proj", 8 * c, c)
             lin(q + "ff.net.2", c, 4 * c)
-        lin(p + "proj_out", c, c)
+        proj(p + "proj_out", c)
 
     cv("conv_in", boc[0], cfg["in_channels"])
     lin("time_embedding.linear_1", temb, boc[0])
@@ -216,8 +239,9 @@ def unet_param_shapes(cfg):
             cv(f"down_blocks.{i}.downsamplers.0.conv", cin, cin)
             skip_ch.append(cin)
     resnet("mid_block.resnets.0.", cin, cin)
-    if tl[-1] > 0:
-        tfm("mid_block.attentions.0.", cin, tl[-1])
+    mid_layers = cfg.get("mid_block_layers", tl[-1])
+    if mid_layers > 0:
+        tfm("mid_block.attentions.0.", cin, mid_layers)
     resnet("mid_block.resnets.1.", cin, cin)
     for i in range(nb):
         ri = nb - 1 - i
@@ -282,6 +306,75 @@ def denoise_loop(unet_fn, latents, ctx, text_embeds, time_ids, num_inference_ste
         cond, uncond = noise.chunk(2)                           # (cond, uncond) order, :145
         noise = uncond + guidance_scale * (cond - uncond)
         latents = latents + noise * (sigma_next - sigma)        # Euler step, epsilon prediction, s_churn = 0
+    return latents
+
+
+# ------------------------------------------------------------------------------------------------
+# PNDMScheduler, skip_prk_steps=True (PLMS) — the scheduler of the Emu1 pipeline (Emu1/models/pipeline.py:43-45, 94-127)
+# ------------------------------------------------------------------------------------------------
+class PNDMOracle:
+    """Literal restatement of diffusers PNDMScheduler.set_timesteps / step_plms / _get_prev_sample (Stable-Diffusion-1.5
+    configuration: scaled-linear betas, set_alpha_to_one=False, steps_offset=1, epsilon prediction), list-of-tensors state
+    like the original — deliberately NOT in the coefficient form the product uses (emu_b200/emu1/scheduler.py)."""
+
+    def __init__(self, cfg=EMU1_SCHED):
+        n = cfg["num_train_timesteps"]
+        betas = torch.linspace(cfg["beta_start"] ** 0.5, cfg["beta_end"] ** 0.5, n, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = self.alphas_cumprod[0]
+        self.n, self.offset = n, cfg["steps_offset"]
+
+    def set_timesteps(self, steps):
+        self.steps = steps
+        ratio = self.n // steps
+        base = (torch.arange(0, steps) * ratio).round().long() + self.offset
+        self.timesteps = torch.cat([base[:-1], base[-2:-1], base[-1:]]).flip(0)
+        self.ets, self.counter, self.cur_sample = [], 0, None
+
+    def _get_prev_sample(self, sample, timestep, prev_timestep, model_output):
+        a_t = self.alphas_cumprod[timestep]
+        a_p = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        b_t, b_p = 1 - a_t, 1 - a_p
+        sample_coeff = (a_p / a_t) ** 0.5
+        denom = a_t * b_p ** 0.5 + (a_t * b_t * a_p) ** 0.5
+        return sample_coeff * sample - (a_p - a_t) * model_output / denom
+
+    def step(self, model_output, timestep, sample):
+        ratio = self.n // self.steps
+        prev_timestep = timestep - ratio
+        if self.counter != 1:
+            self.ets = self.ets[-3:]
+            self.ets.append(model_output)
+        else:
+            prev_timestep = timestep
+            timestep = timestep + ratio
+        if len(self.ets) == 1 and self.counter == 0:
+            self.cur_sample = sample
+        elif len(self.ets) == 1 and self.counter == 1:
+            model_output = (model_output + self.ets[-1]) / 2
+            sample = self.cur_sample
+            self.cur_sample = None
+        elif len(self.ets) == 2:
+            model_output = (3 * self.ets[-1] - self.ets[-2]) / 2
+        elif len(self.ets) == 3:
+            model_output = (23 * self.ets[-1] - 16 * self.ets[-2] + 5 * self.ets[-3]) / 12
+        else:
+            model_output = (1 / 24) * (55 * self.ets[-1] - 59 * self.ets[-2] + 37 * self.ets[-3] - 9 * self.ets[-4])
+        self.counter += 1
+        return self._get_prev_sample(sample, timestep, prev_timestep, model_output)
+
+
+def pndm_denoise_loop(unet_fn, latents, ctx, num_inference_steps, guidance_scale):
+    """EmuGenerationPipeline.forward step 4 (Emu1/models/pipeline.py:108-127); ctx is [cond; uncond], latents ~ N(0, 1)."""
+    sch = PNDMOracle()
+    sch.set_timesteps(num_inference_steps)
+    for t in sch.timesteps.tolist():
+        x = torch.cat([latents] * 2) if guidance_scale > 1.0 else latents   # scale_model_input is the identity for PNDM
+        noise = unet_fn(x.to(latents.dtype), float(t), ctx)
+        if guidance_scale > 1.0:
+            cond, uncond = noise.chunk(2)
+            noise = uncond + guidance_scale * (cond - uncond)
+        latents = sch.step(noise, t, latents)
     return latents
 
 

@@ -25,10 +25,12 @@ def make_engine(cfg, sd):
         u.block_out_channels[i] = c
         u.transformer_layers[i] = cfg["transformer_layers_per_block"][i]
     u.layers_per_block = cfg["layers_per_block"]
-    u.head_dim, u.cross_attention_dim = cfg["attention_head_dim"], cfg["cross_attention_dim"]
-    u.use_linear_projection = 1
-    u.addition_time_embed_dim = cfg["addition_time_embed_dim"]
-    u.projection_class_embeddings_input_dim = cfg["projection_class_embeddings_input_dim"]
+    u.head_dim, u.cross_attention_dim = cfg.get("attention_head_dim", 0), cfg["cross_attention_dim"]
+    u.num_heads = cfg.get("num_heads", 0)
+    u.mid_transformer_layers = cfg.get("mid_block_layers", 0)
+    u.use_linear_projection = 1 if cfg.get("use_linear_projection", True) else 0
+    u.addition_time_embed_dim = cfg.get("addition_time_embed_dim") or 0
+    u.projection_class_embeddings_input_dim = cfg.get("projection_class_embeddings_input_dim") or 0
     u.norm_groups, u.norm_eps = cfg["norm_num_groups"], cfg["norm_eps"]
     eng.unet_configure(u)
     eng.load_state_dict({"unet." + k: v for k, v in sd.items()})
@@ -93,3 +95,58 @@ def test_denoise_graph_matches_eager(setup):
         outs.append(lat.clone())
     os.environ.pop("EMU_NO_GRAPH", None)
     assert torch.equal(outs[0], outs[1])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Emu1 visual decoder: Stable-Diffusion-1.5 topology at its real widths (320 / 640 / 1280 / 1280, 8 heads per level = head
+# widths 40 / 80 / 160, 1x1-conv projections, mid-block attention after a plain last down block, 32 context tokens of width
+# 5120, no added conditioning), one resnet per block to keep the CPU oracle quick; PNDM / PLMS loop
+# ------------------------------------------------------------------------------------------------------------------
+SD15 = dict(D.EMU1_UNET, layers_per_block=1, mid_block_layers=1)
+
+
+@pytest.fixture(scope="module")
+def sd15(cuda):
+    sd = D.random_state_dict(D.unet_param_shapes(SD15), seed=5)
+    eng = make_engine(SD15, sd)
+    g = torch.Generator().manual_seed(15)
+    ctx = torch.randn(2, 32, 5120, generator=g).to(torch.bfloat16)
+    return sd, eng, ctx
+
+
+def test_sd15_unet_forward(sd15):
+    sd, eng, ctx = sd15
+    g = torch.Generator().manual_seed(16)
+    x = torch.randn(2, 4, 32, 32, generator=g).to(torch.bfloat16)
+    bsd = {k: v.to(torch.bfloat16) for k, v in sd.items()}
+    with torch.no_grad():
+        ref32 = D.unet_forward(sd, SD15, x.float(), 961.0, ctx.float())
+        ref16 = D.unet_forward(bsd, SD15, x, 961.0, ctx).float()
+    out = eng.unet_forward(x.cuda(), 961.0, ctx.cuda()).float().cpu()
+    e_eng, e_bf = O.rel_err(out, ref32), O.rel_err(ref16, ref32)
+    print("\n[sd15] unet forward: engine-vs-fp32 %.3e | bf16-oracle-vs-fp32 %.3e | ratio %.2f" % (e_eng, e_bf, e_eng / e_bf))
+    assert e_eng <= 1.5 * e_bf, (e_eng, e_bf)
+
+
+def test_sd15_pndm_loop(sd15):
+    """6 PLMS steps (7 UNet evaluations, graph replays from the 3rd on) under CFG 7.5 vs the literal oracle loop"""
+    from emu_b200.emu1.scheduler import PNDMScheduler
+    sd, eng, ctx = sd15
+    steps, guidance = 6, 7.5
+    g = torch.Generator().manual_seed(17)
+    lat0 = torch.randn(1, 4, 32, 32, generator=g).to(torch.bfloat16).float()
+    bsd = {k: v.to(torch.bfloat16) for k, v in sd.items()}
+    with torch.no_grad():
+        ref32 = D.pndm_denoise_loop(lambda x, t, c: D.unet_forward(sd, SD15, x, t, c), lat0.clone(), ctx.float(), steps, guidance)
+        ref16 = D.pndm_denoise_loop(lambda x, t, c: D.unet_forward(bsd, SD15, x.to(torch.bfloat16), t, c).float(), lat0.clone(),
+                                    ctx, steps, guidance)
+    sch = PNDMScheduler()
+    sch.set_timesteps(steps)
+    lat = lat0.clone().cuda().contiguous()
+    state = torch.zeros(4, *lat.shape, dtype=torch.float32, device="cuda")
+    ctx_d = ctx.cuda()
+    for i, t in enumerate(sch.timesteps.tolist()):
+        eng.denoise_step_multistep(lat, state, sch.step_coefficients(i), float(t), guidance, ctx_d)
+    e_eng, e_bf = O.rel_err(lat.cpu(), ref32), O.rel_err(ref16, ref32)
+    print("\n[sd15] PNDM loop: engine-vs-fp32 %.3e | bf16-oracle-vs-fp32 %.3e | ratio %.2f" % (e_eng, e_bf, e_eng / e_bf))
+    assert e_eng <= max(1.5 * e_bf, 1e-2), (e_eng, e_bf)
