@@ -62,7 +62,7 @@ SYMBOLS = [
     "emu_project", "emu_cformer_forward", "emu_unet_configure", "emu_unet_forward", "emu_denoise_step",
     "emu_denoise_step_multistep", "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
     "emu_op_attn_prefill", "emu_op_attn_decode", "emu_op_rmsnorm", "emu_op_layernorm", "emu_launch_count",
-    "emu_debug_gemm_phases",
+    "emu_debug_gemm_phases", "emu_debug_gemv_phases",
     "emu_version",
 ]
 

@@ -49,6 +49,18 @@ extern "C" int emu_op_gemv(const void* W, int N, int K, const void* x, int ldx, 
   return gemv_bf16(a, (cudaStream_t)s);
 }
 
+extern "C" int emu_debug_gemv_phases(const void* W, int N, int K, const void* x, int ldx, int B, const void* norm_w, float eps,
+                                     int mode, const void* residual, int ldr, void* y, int ldy, int pdl,
+                                     unsigned long long* stamps /*[148][8] device*/, emu_stream_t s) {
+  if (!W || !x || !y || !stamps) return EMU_ERR_INVALID;
+  GemvArgs a;
+  a.W = (const bf16*)W; a.N = N; a.K = K; a.x = (const bf16*)x; a.ldx = ldx; a.B = B;
+  a.norm_w = (const bf16*)norm_w; a.norm_eps = eps; a.mode = mode;
+  a.residual = (const bf16*)residual; a.ldr = ldr; a.y = y; a.ldy = ldy; a.pdl = pdl; a.dbg = stamps;
+  count_launch();
+  return gemv_bf16(a, (cudaStream_t)s);
+}
+
 extern "C" int emu_op_gemv_rope_qkv(const void* W, int n_heads, int head_dim, int K, const void* x, int ldx, int B,
                                     const void* norm_w, float eps, const void* rope_cos, const void* rope_sin,
                                     const int32_t* pos, const int32_t* pos_off, void* q_out, void* k_cache,

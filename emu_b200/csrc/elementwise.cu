@@ -197,8 +197,9 @@ int layernorm(const bf16* x, const bf16* w, const bf16* b, const bf16* residual,
 // ----------------------------------------------------------------------------------------------
 __global__ void rope_kv_write_kernel(bf16* qkv, int B, int N, int H, int D, const bf16* __restrict__ cos_t,
                                      const bf16* __restrict__ sin_t, const int* pos_off, int pos0, bf16* k_cache,
-                                     bf16* v_cache, int t_max) {
+                                     bf16* v_cache, int t_max, const int* __restrict__ pos_dev) {
   const int half = D >> 1;
+  if (pos_dev) pos0 = pos_dev[0];  // CUDA-graphed decode: the cache slot of the new token lives on the device
   const long total = (long)B * N * H * half;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int j = idx % half;
@@ -224,10 +225,10 @@ __global__ void rope_kv_write_kernel(bf16* qkv, int B, int N, int H, int D, cons
 }
 
 int rope_kv_write(bf16* qkv, int B, int N, int H, int D, const bf16* cos_t, const bf16* sin_t, const int* pos_off,
-                  int pos0, bf16* k_cache, bf16* v_cache, int t_max, cudaStream_t st) {
+                  int pos0, bf16* k_cache, bf16* v_cache, int t_max, cudaStream_t st, const int* pos_dev) {
   const long total = (long)B * N * H * (D / 2);
   const int grid = (int)((total + 255) / 256 < 4 * kNumSMs ? (total + 255) / 256 : 4 * kNumSMs);
-  rope_kv_write_kernel<<<grid, 256, 0, st>>>(qkv, B, N, H, D, cos_t, sin_t, pos_off, pos0, k_cache, v_cache, t_max);
+  rope_kv_write_kernel<<<grid, 256, 0, st>>>(qkv, B, N, H, D, cos_t, sin_t, pos_off, pos0, k_cache, v_cache, t_max, pos_dev);
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
@@ -357,14 +358,15 @@ int vit_pool(const bf16* x, bf16* out, int B, int G, int dim, int stride, cudaSt
 // cache is viewed as [outer, B, H*t_max*D-with-holes]; each thread owns one 16-byte column position
 // for ALL beams, so the in-place permutation needs no scratch.
 // ----------------------------------------------------------------------------------------------
+template <int MAXB>
 __global__ void kv_reorder_kernel(bf16* cache, const int* __restrict__ src_idx, int outer, int B, int Bcap, int H,
                                   int t_max, int D, int n_tok) {
   const int vec_per_tok = D >> 3;
   const long per_outer = (long)H * n_tok * vec_per_tok;
   const long total = (long)outer * per_outer;
-  int src[8];
+  int src[MAXB];
 #pragma unroll
-  for (int b = 0; b < 8; ++b) src[b] = b < B ? src_idx[b] : 0;
+  for (int b = 0; b < MAXB; ++b) src[b] = b < B ? src_idx[b] : 0;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int v = idx % vec_per_tok;
     const int t = (idx / vec_per_tok) % n_tok;
@@ -373,20 +375,21 @@ __global__ void kv_reorder_kernel(bf16* cache, const int* __restrict__ src_idx, 
     // the cache holds Bcap sequences per (layer, k/v) slab; only the first B are live
     uint4* base = reinterpret_cast<uint4*>(cache) + ((o * Bcap * H + h) * (long)t_max + t) * vec_per_tok + v;
     const long bstride = (long)H * t_max * vec_per_tok;
-    uint4 vals[8];
+    uint4 vals[MAXB];
 #pragma unroll
-    for (int b = 0; b < 8; ++b)
+    for (int b = 0; b < MAXB; ++b)
       if (b < B) vals[b] = base[src[b] * bstride];
 #pragma unroll
-    for (int b = 0; b < 8; ++b)
+    for (int b = 0; b < MAXB; ++b)
       if (b < B) base[b * bstride] = vals[b];
   }
 }
 int kv_reorder(bf16* cache, int Bcap, const int* src_idx, int B, long outer, int n_used_tokens, int H, int D, int t_max,
                cudaStream_t st) {
-  if (B > 8 || D % 8) return EMU_ERR_INVALID;
+  if (B > 32 || D % 8) return EMU_ERR_INVALID;
   if (n_used_tokens <= 0) return EMU_OK;
-  kv_reorder_kernel<<<8 * kNumSMs, 256, 0, st>>>(cache, src_idx, (int)outer, B, Bcap, H, t_max, D, n_used_tokens);
+  if (B <= 8) kv_reorder_kernel<8><<<8 * kNumSMs, 256, 0, st>>>(cache, src_idx, (int)outer, B, Bcap, H, t_max, D, n_used_tokens);
+  else kv_reorder_kernel<32><<<8 * kNumSMs, 256, 0, st>>>(cache, src_idx, (int)outer, B, Bcap, H, t_max, D, n_used_tokens);
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 

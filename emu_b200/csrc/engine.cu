@@ -274,7 +274,7 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
   const EmuConfig& c = e->cfg;
   if (c.llm_layers > 0) {
     if (c.llm_ffn % tp_size || c.llm_max_batch < 1 ||
-        c.llm_max_batch > 8 || c.llm_hidden % 32 || c.llm_ffn % (32 * tp_size) || (c.llm_head_dim != 64 && c.llm_head_dim != 128)) {
+        c.llm_max_batch > kLlmMaxRows || c.llm_hidden % 32 || c.llm_ffn % (32 * tp_size) || (c.llm_head_dim != 64 && c.llm_head_dim != 128)) {
       delete e;
       return EMU_ERR_UNSUPPORTED;
     }
@@ -293,9 +293,17 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
     e->rope_sin = (bf16*)e->dmalloc((size_t)max_pos * half * 2);
     const size_t kv_elems = (size_t)c.llm_layers * 2 * c.llm_max_batch * e->Hl * c.llm_max_seq * c.llm_head_dim;
     e->kv = (bf16*)e->dmalloc(kv_elems * 2);
-    e->d_pos = (int*)e->dmalloc(3 * 8 * sizeof(int));
-    e->d_start = e->d_pos + 8;
-    e->d_posoff = e->d_pos + 16;
+    e->d_pos = (int*)e->dmalloc(3 * kLlmMaxRows * sizeof(int));
+    e->d_start = e->d_pos + kLlmMaxRows;
+    e->d_posoff = e->d_pos + 2 * kLlmMaxRows;
+    if (c.llm_max_batch > 8) {  // wide decode (more than 8 cache rows: the C4 workload, 4 prompts x 5 beams) runs on the GEMM path
+      e->dec_xn = (bf16*)e->dmalloc((size_t)c.llm_max_batch * c.llm_hidden * 2);
+      e->dec_qkv = (bf16*)e->dmalloc((size_t)c.llm_max_batch * 3 * e->Hl * c.llm_head_dim * 2);
+      if (!e->dec_xn || !e->dec_qkv) {
+        emu_engine_destroy(e);
+        return EMU_ERR_NOMEM;
+      }
+    }
     const int Bm = c.llm_max_batch;
     e->dec_h = (bf16*)e->dmalloc((size_t)Bm * c.llm_hidden * 2);
     e->dec_q = (bf16*)e->dmalloc((size_t)Bm * e->Hl * c.llm_head_dim * 2);
@@ -315,7 +323,7 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
     }
     rope_table_kernel<<<2 * kNumSMs, 256>>>(e->rope_cos, e->rope_sin, max_pos, half, c.llm_rope_theta);
     cudaMemset(e->dec_counters, 0, (size_t)Bm * e->Hl * sizeof(int));
-    cudaMemset(e->d_pos, 0, 3 * 8 * sizeof(int));
+    cudaMemset(e->d_pos, 0, 3 * kLlmMaxRows * sizeof(int));
   }
   if (c.vit_layers > 0) {
     if (c.vit_width % c.vit_heads || c.vit_image % c.vit_patch || c.vit_width % 8) {
@@ -701,7 +709,7 @@ extern "C" int emu_llm_reset(EmuEngine* e, emu_stream_t s) {
   if (!e) return EMU_ERR_INVALID;
   e->cur_len = 0;
   e->cache_B = 0;
-  if (e->d_pos && cudaMemsetAsync(e->d_pos, 0, 3 * 8 * sizeof(int), (cudaStream_t)s) != cudaSuccess) return EMU_ERR_CUDA;
+  if (e->d_pos && cudaMemsetAsync(e->d_pos, 0, 3 * kLlmMaxRows * sizeof(int), (cudaStream_t)s) != cudaSuccess) return EMU_ERR_CUDA;
   return EMU_OK;
 }
 extern "C" int emu_llm_cur_len(EmuEngine* e) { return e ? e->cur_len : -1; }
@@ -760,7 +768,7 @@ extern "C" int emu_llm_prefill(EmuEngine* e, const void* inputs_embeds, const in
     return e->fail(EMU_ERR_CUDA, "embeds copy failed");
   if (pos0 == 0) {
     if (attention_mask) mask_start_kernel<<<B, 32, 0, st>>>(attention_mask, N, e->d_start, e->d_posoff, hf_positions, 0);
-    else cudaMemsetAsync(e->d_start, 0, 2 * 8 * sizeof(int), st);
+    else cudaMemsetAsync(e->d_start, 0, 2 * kLlmMaxRows * sizeof(int), st);
     count_launch();
     e->cache_B = B;
   }
@@ -812,13 +820,33 @@ extern "C" int emu_llm_prefill(EmuEngine* e, const void* inputs_embeds, const in
     count_launch(8);
   }
   e->cur_len = pos0 + N;
-  set_int_kernel<<<1, 32, 0, st>>>(e->d_pos, 8, e->cur_len);  // slot of the next token
+  set_int_kernel<<<1, 32, 0, st>>>(e->d_pos, kLlmMaxRows, e->cur_len);  // slot of the next token
   count_launch();
   if (last_hidden) {
     EMU_TRY(rmsnorm(h, e->final_norm, (bf16*)last_hidden, (int)M, Hd, c.llm_rms_eps, 0, st));
     count_launch();
   }
-  if (logits_last) {
+  if (logits_last && B > 8) {
+    // more rows than the skinny GEMV takes: final norm of the last position of every sequence, then the tcgen05 GEMM
+    EMU_TRY(e->ensure(e->pf_last, (size_t)B * Hd * 2));
+    bf16* last = (bf16*)e->pf_last.p;
+    if (cudaMemcpy2DAsync(last, (size_t)Hd * 2, h + (size_t)(N - 1) * Hd, (size_t)N * Hd * 2, (size_t)Hd * 2, B,
+                          cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return e->fail(EMU_ERR_CUDA, "last-position gather failed");
+    EMU_TRY(rmsnorm(last, e->final_norm, last, B, Hd, c.llm_rms_eps, 0, st));
+    GemmEpilogue el;
+    el.out_fp32 = 1;
+    if (e->tp_size == 1) {
+      el.C = logits_last; el.ldc = c.llm_vocab;
+      EMU_TRY(gemm_bf16(last, Hd, e->lm_head, Hd, B, e->Vl, Hd, el, st));
+    } else {
+      el.C = e->dec_logits_shard; el.ldc = e->Vl;
+      EMU_TRY(gemm_bf16(last, Hd, e->lm_head, Hd, B, e->Vl, Hd, el, st));
+      EMU_TRY(gather_logits(e, e->dec_logits_shard, e->dec_logits_gather, logits_last, B, st));
+      count_launch(2);
+    }
+    count_launch(2);
+  } else if (logits_last) {
     GemvArgs g;
     g.W = e->lm_head; g.N = e->Vl; g.K = Hd;
     g.x = h + (size_t)(N - 1) * Hd; g.ldx = N * Hd; g.B = B;
@@ -877,9 +905,107 @@ static int row_parallel_tail(EmuEngine* e, GemvArgs& g, bf16* h, int B, int Hd, 
   return EMU_OK;
 }
 
+// One decode step for MORE than 8 cache rows (BASELINE config 4: 4 prompts x 5 beams = 20 rows): the skinny GEMV takes at most
+// 8 activation rows, so the projections run on the tcgen05 GEMM with M = B (one 128-row tile, weights streamed once — still
+// HBM-bound), RoPE + cache append as in prefill but at the device-side slot, the split-KV decode attention over the cache,
+// NCCL all-reduce on the row-parallel outputs under tensor parallelism.  Same arithmetic / rounding points as the narrow
+// path; captured into the same CUDA-graph cache.
+static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const void* embeds, int B, float* logits,
+                                 void* hidden, int32_t* next_ids, int ban_id, cudaStream_t st, int* n_launch) {
+  const EmuConfig& c = e->cfg;
+  const int Hd = c.llm_hidden, D = c.llm_head_dim, Hl = e->Hl, Fl = e->Fl;
+  int nl = 0;
+  bf16* h = e->dec_h;
+  bf16* xn = e->dec_xn;
+  bf16* qkv = e->dec_qkv;
+  if (token_ids) {
+    EMU_TRY(embed_gather(e->embed, token_ids, h, B, Hd, st));
+    ++nl;
+  } else if (cudaMemcpyAsync(h, embeds, (size_t)B * Hd * 2, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+    return e->fail(EMU_ERR_CUDA, "embeds copy failed");
+  }
+  const float scale = 1.0f / sqrtf((float)D);
+  PdlScope pdl_chain(1);
+  for (int l = 0; l < c.llm_layers; ++l) {
+    const LlmLayer& L = e->layers[l];
+    bf16* kc = kv_layer(e, l, 0);
+    bf16* vc = kv_layer(e, l, 1);
+    EMU_TRY(rmsnorm(h, L.ln1, xn, B, Hd, c.llm_rms_eps, 0, st));
+    GemmEpilogue ep;
+    ep.C = qkv; ep.ldc = 3 * Hl * D;
+    EMU_TRY(gemm_bf16(xn, Hd, L.wqkv, Hd, B, 3 * Hl * D, Hd, ep, st));
+    EMU_TRY(rope_kv_write(qkv, B, 1, Hl, D, e->rope_cos, e->rope_sin, e->d_posoff, 0, kc, vc, c.llm_max_seq, st, e->d_pos));
+    if (cudaMemcpy2DAsync(e->dec_q, (size_t)Hl * D * 2, qkv, (size_t)3 * Hl * D * 2, (size_t)Hl * D * 2, B,
+                          cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return e->fail(EMU_ERR_CUDA, "q gather failed");
+    EMU_TRY(attn_decode(e->dec_q, kc, vc, B, Hl, D, c.llm_max_seq, e->d_pos, e->d_start, scale, e->dec_attn, e->dec_attn_ws,
+                        e->dec_counters, c.llm_max_seq, 0, st));
+    GemmEpilogue eo;
+    if (e->tp_size == 1) {
+      eo.C = h; eo.ldc = Hd; eo.residual = h; eo.ldr = Hd;
+      EMU_TRY(gemm_bf16(e->dec_attn, Hl * D, L.wo, Hl * D, B, Hd, Hl * D, eo, st));
+    } else {
+      eo.C = e->dec_tmp; eo.ldc = Hd;
+      EMU_TRY(gemm_bf16(e->dec_attn, Hl * D, L.wo, Hl * D, B, Hd, Hl * D, eo, st));
+      EMU_TRY(nccl_allreduce_bf16(e, e->dec_tmp, (size_t)B * Hd, st));
+      EMU_TRY(add_rows(h, e->dec_tmp, h, (long)B * Hd, st));
+      nl += 2;
+    }
+    EMU_TRY(rmsnorm(h, L.ln2, xn, B, Hd, c.llm_rms_eps, 0, st));
+    GemmEpilogue eg;
+    eg.C = e->dec_act; eg.ldc = Fl; eg.mode = EPI_SWIGLU;
+    EMU_TRY(gemm_bf16(xn, Hd, L.wgu, Hd, B, 2 * Fl, Hd, eg, st));
+    GemmEpilogue ed;
+    if (e->tp_size == 1) {
+      ed.C = h; ed.ldc = Hd; ed.residual = h; ed.ldr = Hd;
+      EMU_TRY(gemm_bf16(e->dec_act, Fl, L.wdown, Fl, B, Hd, Fl, ed, st));
+    } else {
+      ed.C = e->dec_tmp; ed.ldc = Hd;
+      EMU_TRY(gemm_bf16(e->dec_act, Fl, L.wdown, Fl, B, Hd, Fl, ed, st));
+      EMU_TRY(nccl_allreduce_bf16(e, e->dec_tmp, (size_t)B * Hd, st));
+      EMU_TRY(add_rows(h, e->dec_tmp, h, (long)B * Hd, st));
+      nl += 2;
+    }
+    nl += 9;
+  }
+  if (hidden) {
+    EMU_TRY(rmsnorm(h, e->final_norm, (bf16*)hidden, B, Hd, c.llm_rms_eps, 0, st));
+    ++nl;
+  }
+  if (logits || next_ids) {
+    float* lg = logits ? logits : e->dec_logits_local;
+    EMU_TRY(rmsnorm(h, e->final_norm, xn, B, Hd, c.llm_rms_eps, 0, st));
+    GemmEpilogue el;
+    el.out_fp32 = 1;
+    if (e->tp_size == 1) {
+      el.C = lg; el.ldc = c.llm_vocab;
+      EMU_TRY(gemm_bf16(xn, Hd, e->lm_head, Hd, B, e->Vl, Hd, el, st));
+    } else {
+      el.C = e->dec_logits_shard; el.ldc = e->Vl;
+      EMU_TRY(gemm_bf16(xn, Hd, e->lm_head, Hd, B, e->Vl, Hd, el, st));
+      EMU_TRY(gather_logits(e, e->dec_logits_shard, e->dec_logits_gather, lg, B, st));
+      nl += 2;
+    }
+    nl += 2;
+    if (next_ids) {
+      if (ban_id >= 0) {
+        argmax_ban_kernel<<<B, 1, 0, st>>>(lg, c.llm_vocab, ban_id);
+        ++nl;
+      }
+      EMU_TRY(argmax_rows(lg, B, c.llm_vocab, next_ids, st));
+      ++nl;
+    }
+  }
+  advance_pos_kernel<<<1, 32, 0, st>>>(e->d_pos, kLlmMaxRows, tp_step_counter(e));
+  ++nl;
+  *n_launch = nl;
+  return EMU_OK;
+}
+
 // the kernels of one decode step (captured into a CUDA graph by emu_llm_decode)
 static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* embeds, int B, float* logits,
                             void* hidden, int32_t* next_ids, int ban_id, cudaStream_t st, int* n_launch) {
+  if (B > 8) return decode_step_body_wide(e, token_ids, embeds, B, logits, hidden, next_ids, ban_id, st, n_launch);
   const EmuConfig& c = e->cfg;
   const int Hd = c.llm_hidden, D = c.llm_head_dim, Hl = e->Hl, Fl = e->Fl;
   int nl = 0;
@@ -963,7 +1089,7 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
       ++nl;
     }
   }
-  advance_pos_kernel<<<1, 32, 0, st>>>(e->d_pos, 8, tp_step_counter(e));
+  advance_pos_kernel<<<1, 32, 0, st>>>(e->d_pos, kLlmMaxRows, tp_step_counter(e));
   ++nl;
   *n_launch = nl;
   return EMU_OK;

@@ -30,6 +30,8 @@ struct VitBlock {
   unsigned bias_loaded = 0;  // bit 0 q_bias, bit 1 v_bias (they share the fused qkv bias buffer)
 };
 
+constexpr int kLlmMaxRows = 32;  // sequences x beams held in the KV cache
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -69,12 +71,13 @@ struct EmuEngine {
   int proj_up_in = 0, proj_up_out = 0, proj_down_in = 0, proj_down_out = 0, stu_in = 0, stu_out = 0;
   // decode workspaces
   emu::bf16 *dec_h = nullptr, *dec_q = nullptr, *dec_attn = nullptr, *dec_act = nullptr, *dec_tmp = nullptr;
+  emu::bf16 *dec_xn = nullptr, *dec_qkv = nullptr;  // wide decode (> 8 cache rows) only
   float* dec_attn_ws = nullptr;
   int* dec_counters = nullptr;
   float* dec_logits_local = nullptr;
   float *dec_logits_shard = nullptr, *dec_logits_gather = nullptr;
   // prefill workspaces (grown on demand)
-  emu::DevBuf pf_h, pf_xn, pf_qkv, pf_attn, pf_act, pf_tmp;
+  emu::DevBuf pf_h, pf_xn, pf_qkv, pf_attn, pf_act, pf_tmp, pf_last;
   // decode graphs keyed by the baked-in arguments
   typedef std::tuple<int, const void*, const void*, const void*, const void*, const void*, const void*, int> GraphKey;
   std::map<GraphKey, cudaGraphExec_t> graphs;

@@ -56,7 +56,7 @@ static __device__ __forceinline__ void gemv_tail_reduce(const GemvArgs& a) {
 }
 
 __global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_constant__ CUtensorMap tmW,
-                                                                const GemvTmaParams p) {
+                                                                const __grid_constant__ GemvTmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;                                                   // nstages x 16 KB
@@ -71,10 +71,23 @@ __global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_con
   __shared__ GemvTmaParams s_params;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // diagnostics: {globaltimer at entry; clock64 at entry, barriers ready, dependency resolved, x staged, first weight chunk
+  // landed (consumer side), own chunks consumed + rows flushed, exit}
+  unsigned long long* dbg = p.a.dbg ? p.a.dbg + (size_t)blockIdx.x * 8 : nullptr;
+  auto clk = [] { unsigned long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; };
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    dbg[0] = g;
+    dbg[1] = clk();
+  }
   const long G = p.geff;  // == gridDim.x for this kernel
   const long c0 = (long)blockIdx.x * p.total / G, c1 = ((long)blockIdx.x + 1) * p.total / G;
+  // the launch parameters are re-read from shared memory by the flush routine: copy them with the whole CTA (one word
+  // per thread) instead of one thread walking ~350 bytes
+  for (int i = threadIdx.x; i < (int)(sizeof(GemvTmaParams) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&s_params)[i] = reinterpret_cast<const uint32_t*>(&p)[i];
   if (threadIdx.x == 0) {
-    s_params = p;
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < kTStages; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -83,6 +96,7 @@ __global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_con
     mbar_fence_init();
   }
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[2] = clk();
   if (p.a.pdl) pdl_launch_dependents();
   int stage = 0;
   uint32_t phase = 0;
@@ -91,11 +105,21 @@ __global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_con
     if (lane == 0) tma_produce(&tmW, p.cpt, c0, c1, ring, full_bar, empty_bar, p.nstages, stage, phase);
     return;
   }
+  XPre pre;
+  tma_prefetch_norm_w(p, pre);  // weights of the fused RMSNorm: independent of the predecessor, fetched while it drains
   if (p.a.pdl) pdl_wait();
+  if (dbg && threadIdx.x == 0) dbg[3] = clk();
   const int xsc = (p.xsc > 0 && p.xsc < p.cpt) ? p.xsc : p.cpt;
-  tma_stage_x(p, xs, s_ss, s_rstd, (int)(c0 % p.cpt) / xsc);
+  tma_stage_x(p, xs, s_ss, s_rstd, (int)(c0 % p.cpt) / xsc, &pre);
+  if (dbg && threadIdx.x == 0) {
+    dbg[4] = clk();
+    if (c0 < c1) mbar_wait(&full_bar[0], 0);  // (diagnostic only) when did the first chunk land?
+    dbg[5] = clk();
+  }
   tma_consume(&s_params, c0, c1, ring, full_bar, empty_bar, red, fin, xs, &s_last, stage, phase, s_rstd);
+  if (dbg && threadIdx.x == 0) dbg[6] = clk();
   if (p.a.ll_n > 0 && p.a.ll_h != nullptr && (int)blockIdx.x < p.a.ll_red) gemv_tail_reduce(p.a);
+  if (dbg && threadIdx.x == 0) dbg[7] = clk();
 }
 
 static float* g_tws = nullptr;

@@ -148,45 +148,75 @@ static __device__ __forceinline__ void tma_produce(const CUtensorMap* tm, int cp
 }
 
 // ---- consumers: stage x (optionally RMS-normalised, zero padded to kpad) into shared memory ----
+// Staging sits on the critical path of every GEMV (the weight ring is full long before it ends), so it is written for
+// latency: loads are issued four deep per thread before anything is consumed (round 1 walked one 16-byte load at a time:
+// 4.2 k cycles without and 8.9 k with the RMSNorm for K = 6656, profiles/r02_gemv_phases_*.txt), and the norm weights —
+// which do not depend on the predecessor kernel — are fetched by the caller before griddepcontrol.wait (XPre).
+struct XPre {
+  uint4 w[4];  // this thread's norm-weight vectors of columns (threadIdx.x + 256 j) * 8, j < 4 (K <= 8192)
+  bool have = false;
+};
+static __device__ __forceinline__ void tma_prefetch_norm_w(const GemvTmaParams& p, XPre& pre) {
+  const GemvArgs& a = p.a;
+  pre.have = false;
+  if (a.norm_w == nullptr || (a.K >> 3) > 1024) return;
+  const uint4* wsrc = reinterpret_cast<const uint4*>(a.norm_w);
+  const int vec_per_row = a.K >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int gi = (int)threadIdx.x + 256 * j;
+    pre.w[j] = gi < vec_per_row ? __ldg(wsrc + gi) : make_uint4(0, 0, 0, 0);
+  }
+  pre.have = true;
+}
+
 // columns [seg * xsc * 256, (seg + 1) * xsc * 256) of every batch row (the whole row when xsc covers it)
-static __device__ __forceinline__ void tma_stage_x_seg(const GemvTmaParams& p, bf16* xs, const float* s_rstd, int seg) {
+static __device__ __forceinline__ void tma_stage_x_seg(const GemvTmaParams& p, bf16* xs, const float* s_rstd, int seg,
+                                                       const XPre* pre = nullptr) {
   const GemvArgs& a = p.a;
   const int K = a.K, B = a.B;
   const int vec_per_row = K >> 3;
   const int xsc = (p.xsc > 0 && p.xsc < p.cpt) ? p.xsc : p.cpt;
   const int v0 = seg * xsc * (kTCols >> 3);                       // first 16-byte vector of the segment
   const int nv = min(xsc, p.cpt - seg * xsc) * (kTCols >> 3);     // vectors in this segment (zero padded past K)
+  const bool use_pre = pre != nullptr && pre->have && v0 == 0;
+  const uint4* wsrc = reinterpret_cast<const uint4*>(a.norm_w);
   for (int b = 0; b < B; ++b) {
     const float rstd = a.norm_w ? s_rstd[b] : 1.f;
     const uint4* src = reinterpret_cast<const uint4*>(a.x + (long)b * a.ldx);
-    const uint4* wsrc = reinterpret_cast<const uint4*>(a.norm_w);
     uint4* dst = reinterpret_cast<uint4*>(xs + (long)b * p.ldxs);
-    for (int i = threadIdx.x; i < nv; i += 256) {
-      uint4 o = make_uint4(0, 0, 0, 0);
-      const int gi = v0 + i;
-      if (gi < vec_per_row) {
-        const uint4 v = __ldcg(src + gi);  // activations may have been produced by other CTAs of this very kernel
+    for (int i0 = 0; i0 < nv; i0 += 1024) {
+      uint4 v[4], w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // four independent loads in flight per thread
+        const int gi = v0 + i0 + (int)threadIdx.x + 256 * j;
+        // activations may have been produced by other CTAs of this very kernel's predecessor: bypass L1
+        v[j] = (i0 + (int)threadIdx.x + 256 * j < nv && gi < vec_per_row) ? __ldcg(src + gi) : make_uint4(0, 0, 0, 0);
+        if (a.norm_w) w[j] = (use_pre && i0 == 0) ? pre->w[j] : (gi < vec_per_row ? __ldg(wsrc + gi) : make_uint4(0, 0, 0, 0));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + (int)threadIdx.x + 256 * j;
+        if (i >= nv) continue;
+        uint4 o = v[j];
         if (a.norm_w) {
-          const uint4 w = wsrc[gi];
-          const uint32_t v4[4] = {v.x, v.y, v.z, v.w}, w4[4] = {w.x, w.y, w.z, w.w};
+          const uint32_t v4[4] = {v[j].x, v[j].y, v[j].z, v[j].w}, w4[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
           uint32_t o4[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
-            o4[j] = pack_bf16(round_bf16(bf16_lo(v4[j]) * rstd) * bf16_lo(w4[j]),
-                              round_bf16(bf16_hi(v4[j]) * rstd) * bf16_hi(w4[j]));
+          for (int q = 0; q < 4; ++q)  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
+            o4[q] = pack_bf16(round_bf16(bf16_lo(v4[q]) * rstd) * bf16_lo(w4[q]),
+                              round_bf16(bf16_hi(v4[q]) * rstd) * bf16_hi(w4[q]));
           o = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-        } else {
-          o = v;
         }
+        dst[i] = o;
       }
-      dst[i] = o;
     }
   }
   consumer_bar();
 }
 
 static __device__ __forceinline__ void tma_stage_x(const GemvTmaParams& p, bf16* xs, float (*s_ss)[8], float* s_rstd,
-                                                   int seg = 0) {
+                                                   int seg = 0, const XPre* pre = nullptr) {
   const GemvArgs& a = p.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = a.K, B = a.B;
@@ -198,13 +228,21 @@ static __device__ __forceinline__ void tma_stage_x(const GemvTmaParams& p, bf16*
     for (int b = 0; b < B; ++b) {
       const uint4* src = reinterpret_cast<const uint4*>(a.x + (long)b * a.ldx);
       float s = 0.f;
-      for (int i = threadIdx.x; i < vec_per_row; i += 256) {
-        const uint4 v = __ldcg(src + i);
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+      for (int i0 = 0; i0 < vec_per_row; i0 += 1024) {
+        uint4 v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float lo = bf16_lo(w4[j]), hi = bf16_hi(w4[j]);
-          s += lo * lo + hi * hi;
+          const int i = i0 + (int)threadIdx.x + 256 * j;
+          v[j] = i < vec_per_row ? __ldcg(src + i) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t w4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float lo = bf16_lo(w4[q]), hi = bf16_hi(w4[q]);
+            s += lo * lo + hi * hi;
+          }
         }
       }
       ss[b] = warp_sum(s);
@@ -222,7 +260,7 @@ static __device__ __forceinline__ void tma_stage_x(const GemvTmaParams& p, bf16*
     }
     consumer_bar();
   }
-  tma_stage_x_seg(p, xs, s_rstd, seg);
+  tma_stage_x_seg(p, xs, s_rstd, seg, pre);
 }
 
 // ---- consumers: pull this CTA's chunks [c0, c1) out of the ring, mma them against xs, finish row groups ----

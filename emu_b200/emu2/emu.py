@@ -25,6 +25,32 @@ def build_tokenizer(llama_config_path, instruct=False):
     return tok
 
 
+def dp_image_slices(n_images: int, world: int):
+    """Contiguous per-rank slices of a batch of images for the data-parallel ViT ("EVA ViT — data-parallel over
+    images, all-gather once"): rank r encodes images [lo_r, hi_r); every rank gets ceil(n / world) or fewer, in order."""
+    per = (n_images + world - 1) // world
+    return [(min(r * per, n_images), min((r + 1) * per, n_images)) for r in range(world)]
+
+
+def encode_images_data_parallel(encode_local, image: torch.Tensor, rank: int, world: int, group=None):
+    """Each tensor-parallel rank runs the (replicated) ViT on its slice of the image batch only; one all-gather of the pooled
+    tokens puts the full [B, n_query, width] result on every rank, in the original order.  Bitwise identical to encoding the
+    whole batch on one GPU (every image is independent of its batch neighbours in every kernel)."""
+    import torch.distributed as dist
+    B = image.shape[0]
+    slices = dp_image_slices(B, world)
+    per = slices[0][1] - slices[0][0]
+    lo, hi = slices[rank]
+    local = encode_local(image[lo:hi]) if hi > lo else None
+    probe = local if local is not None else encode_local(image[:1])  # shape / dtype of one result row (rank without work)
+    buf = torch.zeros(per, *probe.shape[1:], dtype=probe.dtype, device=probe.device)
+    if local is not None:
+        buf[: hi - lo] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    return torch.cat([parts[r][: slices[r][1] - slices[r][0]] for r in range(world)], dim=0)
+
+
 class _Decoder:
     """Mirror of the attribute surface callers touch on ``model.decoder`` (tokenizer, config, special ids)."""
 
@@ -69,6 +95,7 @@ class EmuModel:
         if vision_cfg.rope or vision_cfg.naiveswiglu or vision_cfg.subln or vision_cfg.init_value:
             raise NotImplementedError("EVA variants with rope / swiglu / subln / layer-scale are not used by Emu2")
         self.engine = _lib.Engine(c, tp_rank=tp_rank, tp_size=tp_size, nccl_uid=nccl_uid)
+        self.tp_rank, self.tp_size = tp_rank, tp_size
         self.hidden = c.llm_hidden
 
         self.n_query = vision_cfg.n_query
@@ -97,7 +124,18 @@ class EmuModel:
     @torch.no_grad()
     def encode_image(self, image: torch.Tensor, *, n_query=None):
         n_query = n_query if n_query is not None else self.n_query
-        return self.engine.vit_forward(image.to(self.device_), n_query, pool=True)
+        image = image.to(self.device_)
+        local = lambda x: self.engine.vit_forward(x, n_query, pool=True)
+        if self.tp_size > 1 and image.shape[0] > 1 and self._dist_matches_tp():
+            # several images under tensor parallelism (8-shot prompts, video frames): the ViT is replicated, so split the
+            # IMAGES over the ranks instead of running all of them everywhere
+            return encode_images_data_parallel(local, image, self.tp_rank, self.tp_size)
+        return local(image)
+
+    def _dist_matches_tp(self):
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() == self.tp_size \
+            and dist.get_rank() == self.tp_rank
 
     def _tokenize(self, text):
         inputs = self.decoder.tokenizer(text, padding="longest", return_tensors="pt")

@@ -52,7 +52,7 @@ typedef struct EmuConfig {
   /* --- LLaMA decoder (Emu2/emu/conf/llama_config/config.json; Emu1/models/llama_config) --- */
   int llm_hidden, llm_layers, llm_heads, llm_head_dim, llm_ffn, llm_vocab;
   float llm_rms_eps, llm_rope_theta;
-  int llm_max_batch; /* sequences x beams held in the KV cache, <= 8 */
+  int llm_max_batch; /* sequences x beams held in the KV cache, <= 32 (more than 8 rows decode on the GEMM path) */
   int llm_max_seq;   /* KV slots per sequence */
   /* --- EVA-CLIP ViT (Emu2/emu/conf/emu_conf.py:7-33; Emu1/models/Emu-14B.json) --- */
   int vit_image, vit_patch, vit_width, vit_layers, vit_heads, vit_mlp;
@@ -231,6 +231,13 @@ int emu_sample_tokens(const float* logits, int rows, int vocab, float temperatur
 int emu_debug_gemm_phases(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const void* bias,
                           const void* residual, int ldr, int epi_mode, void* C, int ldc, int force_bn,
                           unsigned long long* stamps, emu_stream_t s);
+
+/* Diagnostics: emu_op_gemv (bf16 output) with per-CTA phase time stamps.  stamps: DEVICE [148][8] uint64, per CTA {globaltimer
+ * ns at entry, then SM clock64 at: entry, barriers ready, dependency resolved (griddepcontrol.wait), x staged, first weight
+ * chunk landed, own chunks consumed and rows flushed, exit}.  tools/gemv_phases.py prints the table under profiles/. */
+int emu_debug_gemv_phases(const void* W, int N, int K, const void* x, int ldx, int B, const void* norm_w, float eps, int mode,
+                          const void* residual, int ldr, void* y, int ldy, int pdl, unsigned long long* stamps,
+                          emu_stream_t s);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t emu_launch_count(void);

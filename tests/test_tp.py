@@ -62,6 +62,45 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from emu_b200.emu2.emu import encode_images_data_parallel
+    ok = True
+    for B in (1, 2, 3, 5, 8):      # fewer images than ranks, ragged, even
+        imgs = torch.arange(B, dtype=torch.float32).view(B, 1, 1, 1).expand(B, 3, 4, 4).contiguous()
+        seen = []
+
+        def encode_local(x):       # stand-in for the ViT: one "token" row per image that names the image
+            seen.append(x[:, 0, 0, 0].tolist())
+            return x[:, 0, :2, :2].reshape(x.shape[0], 4, 1) * 10.0
+        out = encode_images_data_parallel(encode_local, imgs, rank, world)
+        ok = ok and out.shape == (B, 4, 1) and torch.equal(out[:, 0, 0], torch.arange(B, dtype=torch.float32) * 10.0)
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_vit_data_parallel_sharding_gloo_world2():
+    """Data-parallel ViT under tensor parallelism: slices tile the batch in order, the gathered result
+    is the batch in its original order on every rank — also when a rank has no image."""
+    from emu_b200.emu2.emu import dp_image_slices
+    for n, w in [(32, 8), (4, 8), (1, 2), (5, 4), (9, 2)]:
+        sl = dp_image_slices(n, w)
+        assert len(sl) == w and sl[0][0] == 0 and sl[-1][1] == n and all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+    assert dp_image_slices(32, 8) == [(4 * r, 4 * r + 4) for r in range(8)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 1000
+    ps = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def test_gloo_world2_rendezvous_and_sharding():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
