@@ -666,6 +666,147 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: interleaved 8-shot prompts (seq ~4k), batch 4, the reference's default 5-beam decoding, LLaMA-33B tensor
+# parallel over the box (Emu2/README.md:221-246, Emu2/emu/emu.py:189-229)
+# ------------------------------------------------------------------------------------------------
+def c4_prompt_ids(n_query=64, shots=8, n_text=440, batch=4, seed=0):
+    from emu_b200.emu2.synthetic import IDS
+    g = torch.Generator().manual_seed(seed)
+    span = torch.tensor([IDS["[IMG]"]] + [IDS["<image>"]] * n_query + [IDS["[/IMG]"]])
+    rows = []
+    for _ in range(batch):
+        parts = [torch.tensor([IDS["bos"]])]
+        for _ in range(shots):
+            parts += [span, torch.randint(100, 31000, (n_text,), generator=g)]
+        rows.append(torch.cat(parts))
+    ids = torch.stack(rows)
+    return ids, torch.ones_like(ids)
+
+
+def run_c4(args):
+    import hashlib
+    import torch.distributed as dist
+    from emu_b200 import _lib
+    from emu_b200.emu2.conf import TextDecoderCfg
+    from emu_b200.emu2.emu import EmuModel
+    from emu_b200.emu2 import synthetic
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            import ctypes
+            raw = ctypes.create_string_buffer(128)
+            _lib.check(_lib.load().emu_nccl_unique_id(raw))
+            buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+    vc, lc = emu2_cfgs(args.small)
+    vocab = synthetic.VOCAB_EMU2
+    shots, n_text, batch, beams = (8, 440, 4, 5) if not args.small else (2, 6, 2, 3)
+    ids_host, mask_host = c4_prompt_ids(vc.n_query, shots, n_text, batch)
+    prompt_len = ids_host.shape[1]
+    new_tokens = NEW_TOKENS if not args.small else 8
+    model = EmuModel(vc, TextDecoderCfg(), tokenizer=synthetic.SyntheticTokenizer(vocab), llama_config=lc,
+                     max_batch=batch * beams, max_seq=prompt_len + new_tokens + 8, tp_rank=rank, tp_size=world, nccl_uid=uid)
+    synthetic.load_random_weights(model, vc, lc, vocab, seed=0)
+    g = torch.Generator().manual_seed(4321)
+    images_host = torch.randn(batch * shots, 3, vc.image_size, vc.image_size, generator=g).to(torch.bfloat16).pin_memory()
+    ids_host, mask_host = ids_host.pin_memory(), mask_host.pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        img = images_host.to("cuda", non_blocking=True)
+        ids = ids_host.to("cuda", non_blocking=True)
+        msk = mask_host.to("cuda", non_blocking=True)
+        return model.generate_from_ids(ids, msk, image=img, num_beams=beams, max_new_tokens=new_tokens, min_len=new_tokens,
+                                       length_penalty=-1).cpu()
+    for _ in range(max(1, args.warmup - 2)):
+        one_step()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = _lib.launch_count()
+    ev0.record()
+    for _ in range(args.steps):
+        toks = one_step()
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # the pieces, timed separately on the same inputs
+    img, ids, msk = images_host.cuda(), ids_host.cuda(), mask_host.cuda()
+
+    def ev_ms(fn):
+        fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        out = fn()
+        b.record()
+        barrier()
+        return a.elapsed_time(b), out
+    vit_ms, e = ev_ms(lambda: model.encode_image(img))
+    emb = model.engine.llm_embed(ids)
+    emb[ids == 32003] = model._project_up(e.reshape(-1, e.shape[-1]))
+
+    def prefill():
+        model.engine.llm_reset()
+        return model.engine.llm_prefill(emb, msk, hf_positions=True, want_logits=True)
+    prefill_ms, _ = ev_ms(prefill)
+    decode_ms = ms / args.steps - vit_ms - prefill_ms
+    step_ms = decode_ms / max(1, new_tokens - 1)
+    H, L = lc["hidden_size"], lc["num_hidden_layers"]
+    tokens = batch * prompt_len
+    prefill_flops = 2.0 * (llm_bytes_per_token(lc, vocab) / 2) * tokens + 4.0 * L * batch * prompt_len * prompt_len / 2 * H
+    kv_bytes = kv_bytes_per_ctx_token(lc) * (prompt_len + new_tokens / 2.0) * batch * beams
+    alg_bytes = (llm_bytes_per_token(lc, vocab) + kv_bytes) / world
+    peak, peak_src = measured_peaks()
+    bf16_peak = 1480.4
+    try:
+        bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        pass
+    if rank == 0:
+        emit({
+            "metric": "emu2_c4_interleaved_tok_per_s", "value": args.steps * batch * new_tokens / (ms / 1000.0), "unit": "tok/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Emu2 interleaved in-context (BASELINE configs[3]): %d prompts x %d shots of (66-token image "
+                                   "span + %d text tokens) = %d prompt tokens each, %d images through the ViT (data-parallel over "
+                                   "ranks), LLaMA-33B, %d beams (reference default, length_penalty -1) -> %d cache rows, %d new "
+                                   "tokens per prompt" % (batch, shots, n_text, prompt_len, batch * shots, beams, batch * beams,
+                                                          new_tokens),
+                       "parallelism": "tp%d" % world, "global_batch": batch},
+            "e2e": {"value": args.steps * batch * new_tokens / (ms / 1000.0), "unit": "tok/s",
+                    "h2d_bytes_per_step": int(images_host.numel() * 2 + ids_host.numel() * 16), "d2h_bytes_per_step": int(batch * new_tokens * 8)},
+            "gpu_launches": int(launches),
+            "vit_ms": vit_ms, "prefill_ms": prefill_ms, "decode_ms": decode_ms, "decode_step_ms": step_ms,
+            "tokens_sha1": hashlib.sha1(toks.to(torch.int64).numpy().tobytes()).hexdigest()[:16],
+            "roofline": {"bound": "hbm", "kernel": "wide decode step (tcgen05 GEMM with M = %d cache rows + split-KV attention)" % (batch * beams),
+                         "achieved": alg_bytes / (step_ms / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg_bytes / (step_ms / 1000.0) / 1e9 / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step_per_gpu": alg_bytes, "traffic": None},
+            "prefill_roofline": {"bound": "tensor", "achieved": prefill_flops / world / (prefill_ms / 1000.0) / 1e12, "peak": bf16_peak,
+                                 "unit": "TFLOP/s per GPU", "frac": prefill_flops / world / (prefill_ms / 1000.0) / 1e12 / bf16_peak,
+                                 "flops": prefill_flops},
+        })
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -696,12 +837,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-denoise", action="store_true", help="skip the Emu2-Gen denoise-loop measurement")
     ap.add_argument("--no-beam", action="store_true", help="skip the secondary 5-beam measurement")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4"],
+                    help="c2 = BASELINE configs[1] (the headline, default); c4 = configs[3]: 8-shot interleaved prompts "
+                         "(seq ~4k), batch 4, 5 beams, LLaMA-33B tensor parallel over --gpus (needs >= 2 GPUs for the KV cache)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    if args.config == "c4":
+        run_c4(args)
+        return
     run_cuda(args)
 
 

@@ -58,7 +58,7 @@ class EmuVAEConfig(C.Structure):
 # every symbol declared in include/emu_b200.h (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "emu_beam_topk", "emu_beam_step", "emu_sample_tokens", "emu_image_to_uint8", "emu_preprocess_image", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
-    "emu_vit_forward", "emu_llm_reset", "emu_llm_embed", "emu_llm_prefill", "emu_llm_decode", "emu_llm_cur_len",
+    "emu_vit_forward", "emu_llm_reset", "emu_llm_embed", "emu_llm_prefill", "emu_llm_decode", "emu_llm_cur_len", "emu_llm_expand",
     "emu_project", "emu_cformer_forward", "emu_unet_configure", "emu_unet_forward", "emu_denoise_step",
     "emu_denoise_step_multistep", "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
     "emu_op_attn_prefill", "emu_op_attn_decode", "emu_op_rmsnorm", "emu_op_layernorm", "emu_launch_count",
@@ -204,6 +204,11 @@ class Engine:
 
     def cur_len(self):
         return self.lib.emu_llm_cur_len(self.h)
+
+    def llm_expand(self, src_idx, new_B):
+        """cache row b <- row src_idx[b] for b < new_B (beam search: one prefill per prompt, then num_beams cache rows)"""
+        src = src_idx.to(torch.int32).contiguous()
+        check(self.lib.emu_llm_expand(self.h, _ptr(src), int(new_B), _stream()), self.h)
 
     def sample_tokens(self, logits, temperature=1.0, top_k=0, top_p=1.0, ban_id=-1, seed=0, offset=0):
         return op_sample_tokens(logits, temperature, top_k, top_p, -1 if ban_id is None else ban_id, seed, offset)

@@ -714,6 +714,33 @@ extern "C" int emu_llm_reset(EmuEngine* e, emu_stream_t s) {
 }
 extern "C" int emu_llm_cur_len(EmuEngine* e) { return e ? e->cur_len : -1; }
 
+__global__ void gather_rows_int_kernel(int* start, int* posoff, const int* __restrict__ src, int n) {
+  __shared__ int a[emu::kLlmMaxRows], b[emu::kLlmMaxRows];
+  if (threadIdx.x < n) {
+    a[threadIdx.x] = start[src[threadIdx.x]];
+    b[threadIdx.x] = posoff[src[threadIdx.x]];
+  }
+  __syncthreads();
+  if (threadIdx.x < n) {
+    start[threadIdx.x] = a[threadIdx.x];
+    posoff[threadIdx.x] = b[threadIdx.x];
+  }
+}
+
+extern "C" int emu_llm_expand(EmuEngine* e, const int32_t* src_idx, int new_B, emu_stream_t stream) {
+  if (!e || !src_idx || new_B < 1) return EMU_ERR_INVALID;
+  const EmuConfig& c = e->cfg;
+  if (new_B > c.llm_max_batch) return e->fail(EMU_ERR_INVALID, "expanded batch exceeds llm_max_batch");
+  if (e->cur_len < 1) return e->fail(EMU_ERR_STATE, "expand before prefill");
+  cudaStream_t st = (cudaStream_t)stream;
+  EMU_TRY(kv_reorder(e->kv, c.llm_max_batch, src_idx, new_B, (long)c.llm_layers * 2, e->cur_len, e->Hl, c.llm_head_dim,
+                     c.llm_max_seq, st));
+  gather_rows_int_kernel<<<1, 32, 0, st>>>(e->d_start, e->d_posoff, src_idx, new_B);
+  count_launch(2);
+  e->cache_B = new_B;
+  return cudaGetLastError() == cudaSuccess ? EMU_OK : e->fail(EMU_ERR_CUDA, "cache expand failed");
+}
+
 extern "C" int emu_llm_embed(EmuEngine* e, const int32_t* ids, int n, void* out, emu_stream_t s) {
   if (!e || !ids || !out || n < 1) return EMU_ERR_INVALID;
   if (!e->embed) return e->fail(EMU_ERR_STATE, "embed_tokens missing");

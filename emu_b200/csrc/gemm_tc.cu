@@ -141,17 +141,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);  // one tcgen05.commit arrival from every CTA that reads the multicast stage
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
-      mbar_init(&res_full[i], 1);
-    }
     if (p.staged) tma_prefetch_desc(&tmC);
     if (p.res_smem) tma_prefetch_desc(&tmR);
+  }
+  if (threadIdx.x < kStages) {  // barrier inits spread over threads (one thread walking ~22 of them costs ~0.3 us per launch)
+    mbar_init(&full_bar[threadIdx.x], 1);
+    mbar_init(&empty_bar[threadIdx.x], CL);  // one tcgen05.commit arrival from every CTA that reads the multicast stage
+    mbar_fence_init();
+  } else if (threadIdx.x >= 32 && threadIdx.x < 34) {
+    const int i = threadIdx.x - 32;
+    mbar_init(&tmem_full[i], 1);
+    mbar_init(&tmem_empty[i], 8);
+    mbar_init(&res_full[i], 1);
     mbar_fence_init();
   }
   if (p.pdl) pdl_launch_dependents();  // the next kernel of the chain may start its own prologue now

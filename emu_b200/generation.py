@@ -101,10 +101,13 @@ def beam_search(engine, inputs_embeds, attention_mask, num_beams, max_new_tokens
         raise ValueError("batch x num_beams = %d exceeds the engine's llm_max_batch = %d" % (Bt * nb, engine.cfg.llm_max_batch))
     V = engine.cfg.llm_vocab
     max_length = max_new_tokens
-    emb = inputs_embeds.repeat_interleave(nb, dim=0)
-    mask = attention_mask.repeat_interleave(nb, dim=0) if attention_mask is not None else None
+    # HF expands the inputs to batch x beams and prefills num_beams identical copies of every prompt; here each prompt is
+    # prefilled ONCE and its cache row is then mapped to num_beams rows (same cache contents, 1 / num_beams of the work)
     engine.llm_reset()
-    _, logits = engine.llm_prefill(emb, mask, hf_positions=True, want_logits=True)
+    _, logits = engine.llm_prefill(inputs_embeds, attention_mask, hf_positions=True, want_logits=True)
+    if nb > 1:
+        engine.llm_expand(torch.arange(Bt * nb, device=dev, dtype=torch.int32) // nb, Bt * nb)
+        logits = logits.repeat_interleave(nb, dim=0).contiguous()
     logits_buf = torch.empty_like(logits)
     st = engine.beam_state(Bt, nb, max_length, pad_token_id, dev)
     keep = 2 * nb

@@ -103,6 +103,10 @@ int emu_llm_prefill(EmuEngine* e, const void* inputs_embeds, const int32_t* atte
 int emu_llm_decode(EmuEngine* e, const int32_t* token_ids, const void* embeds, const int32_t* beam_src_idx, int B,
                    float* logits, void* hidden, int32_t* next_ids, int ban_id, emu_stream_t s);
 int emu_llm_cur_len(EmuEngine* e);
+/* Re-map the cached sequences: row b of the new cache (new_B rows) = row src_idx[b] (device int32) of the current one.  Beam
+ * search prefills each prompt ONCE and then expands its cache row to num_beams rows (HF expands the inputs and prefills
+ * num_beams identical copies — same result, num_beams x the prompt work).  new_B <= llm_max_batch. */
+int emu_llm_expand(EmuEngine* e, const int32_t* src_idx, int new_B, emu_stream_t s);
 /* y[M,out] = x[M,in] W^T for the small projections: which = 0 project_up, 1 project_down, 2 stu_regress_head */
 int emu_project(EmuEngine* e, int which, const void* x, int M, void* y, emu_stream_t s);
 

@@ -35,6 +35,10 @@ class OracleEngine:
         self.hf = hf_positions
         return (h if want_hidden else None), O.lm_logits(self.sd, h[:, -1]).float()
 
+    def llm_expand(self, src_idx, new_B):
+        self.cache.reorder(src_idx.long())
+        self.mask = self.mask.index_select(0, src_idx.long())
+
     def llm_decode(self, token_ids=None, embeds=None, beam_src=None, logits=None, hidden=None, next_ids=None,
                    ban_id=-1, B=None):
         if beam_src is not None:
