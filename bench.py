@@ -807,6 +807,58 @@ def run_c4(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: batched text->image, 32 prompts, 50 steps, 1024x1024, UNet over the box.  Independent samples shard
+# trivially: every rank keeps the whole UNet (5 GB) and denoises 32 / N prompts with its cond / uncond pairs
+# together (CFG combine stays local) — no collective in the loop, final latents stay where the VAE decode would run.
+# ------------------------------------------------------------------------------------------------
+def run_c5(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    prompts = 32
+    per = (prompts + world - 1) // world
+    mine = max(0, min(per, prompts - rank * per))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    eng, _ = make_unet_engine()
+    r = run_denoise(eng=eng, sync=barrier, batch=max(mine, 1), latent_seed=rank, warm_loops=1, timed_loops=max(1, args.steps // 2))
+    eng.close()
+    ms_loop = r["ms_per_step"]
+    if world > 1:
+        t = torch.tensor([ms_loop], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_loop = float(t.item())
+    bf16_peak = 1480.4
+    try:
+        bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        pass
+    if rank == 0:
+        ach = prompts * 2 * UNET_FLOP_PER_SAMPLE_STEP / (ms_loop / 1000.0) / 1e12
+        emit({"metric": "emu2gen_c5_image_steps_per_s", "value": prompts * 1000.0 / ms_loop, "unit": "image-steps/s",
+              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_loop, "higher_is_better": True,
+              "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+              "config": {"workload": "Emu2-Gen batched text->image (BASELINE configs[4]): 32 prompts, 50 Euler steps, 1024x1024, "
+                                     "guidance 3 (UNet batch 64), %d prompts per GPU with their cond/uncond pairs together, "
+                                     "weights replicated, no collective in the loop" % per, "parallelism": "dp%d" % world,
+                         "global_batch": prompts},
+              "e2e": {"value": prompts * 1000.0 / ms_loop, "unit": "image-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+              "gpu_launches": int(r["launches_per_step"] * 50), "time_for_50_steps_s": ms_loop * 50 / 1000.0,
+              "latents_sha1_rank0": r["latents_sha1"], "finite": r["finite"],
+              "roofline": {"bound": "tensor", "achieved": ach, "peak": bf16_peak * world, "unit": "TFLOP/s", "frac": ach / (bf16_peak * world),
+                           "traffic": None}})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -837,9 +889,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-denoise", action="store_true", help="skip the Emu2-Gen denoise-loop measurement")
     ap.add_argument("--no-beam", action="store_true", help="skip the secondary 5-beam measurement")
-    ap.add_argument("--config", default="c2", choices=["c2", "c4"],
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
                     help="c2 = BASELINE configs[1] (the headline, default); c4 = configs[3]: 8-shot interleaved prompts "
-                         "(seq ~4k), batch 4, 5 beams, LLaMA-33B tensor parallel over --gpus (needs >= 2 GPUs for the KV cache)")
+                         "(seq ~4k), batch 4, 5 beams, LLaMA-33B tensor parallel over --gpus (needs >= 2 GPUs for the KV cache); "
+                         "c5 = configs[4]: 32 prompts x 50 denoise steps at 1024x1024, the prompt batch sharded over --gpus")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -848,6 +901,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
     if args.config == "c4":
         run_c4(args)
+        return
+    if args.config == "c5":
+        run_c5(args)
         return
     run_cuda(args)
 

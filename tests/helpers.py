@@ -57,6 +57,25 @@ def make_emu2_state_dict(vision=TINY_VISION, llama=TINY_LLAMA, vocab=VOCAB, seed
     return {k: v.to(dtype) for k, v in sd.items()}
 
 
+PARITY_RATIO = 1.5   # engine error vs the fp32 reference, in units of what bf16 storage costs the reference itself
+PARITY_FLOOR = 2e-3   # half a bf16 ulp of the largest element: below this the two rounding-noise samples are not comparable
+
+
+def bf16_state_dict(sd):
+    return {k: v.to(torch.bfloat16) for k, v in sd.items()}
+
+
+def assert_bf16_parity(name, out, ref32, ref16, ratio=PARITY_RATIO, floor=PARITY_FLOOR):
+    """The parity bound used by every model-level GPU test: the engine keeps activations in bf16 exactly
+    where the reference's own bf16 run rounds, so its distance from the fp32 reference must not exceed `ratio` x the distance
+    of the CPU oracle run in the same dtype policy (ref16) — no hard-coded budget.  Returns (engine error, bf16-oracle error)."""
+    from oracle import emu_oracle as O
+    e_eng, e_bf = O.rel_err(out, ref32), O.rel_err(ref16, ref32)
+    print("\n[parity] %-34s engine-vs-fp32 %.3e | bf16-oracle-vs-fp32 %.3e | ratio %.2f" % (name, e_eng, e_bf, e_eng / max(e_bf, 1e-12)))
+    assert e_eng <= max(ratio * e_bf, floor), (name, e_eng, e_bf)
+    return e_eng, e_bf
+
+
 class StubTokenizer:
     """Just enough of the HF tokenizer surface for EmuModel when texts are pre-tokenised (GPU box has no
     tokenizer.model: the reference's file is not redistributed; golden fixtures carry the real ids)."""

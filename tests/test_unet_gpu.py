@@ -57,8 +57,8 @@ def test_unet_forward(setup, hw):
     ref32 = D.unet_forward(sd, TINY_UNET, x.bfloat16().float(), 981.0, ctx.bfloat16().float(), te.bfloat16().float(), tid)
     ref16 = D.unet_forward(bsd, TINY_UNET, x.bfloat16(), 981.0, ctx.bfloat16(), te.bfloat16(), tid).float()
     out = eng.unet_forward(x.cuda(), 981.0, ctx.cuda(), te.cuda(), tid.cuda()).float().cpu()
-    budget = max(2.0 * O.rel_err(ref16, ref32), 2e-2)  # what bf16 storage costs the oracle itself
-    assert O.rel_err(out, ref32) < budget, (O.rel_err(out, ref32), O.rel_err(ref16, ref32))
+    from helpers import assert_bf16_parity
+    assert_bf16_parity("tiny unet forward %dx%d" % hw, out, ref32, ref16)
 
 
 def test_denoise_loop(setup):
@@ -71,11 +71,16 @@ def test_denoise_loop(setup):
     te = ctx.mean(1)
     ref = D.denoise_loop(lambda x, t, c, e, i: D.unet_forward(sd, TINY_UNET, x, t, c, e, i), lat0.clone(), ctx, te, tid,
                          steps, guidance)
+    bsd = {k: v.to(torch.bfloat16) for k, v in sd.items()}
+    ref16 = D.denoise_loop(lambda x, t, c, e, i: D.unet_forward(bsd, TINY_UNET, x.to(torch.bfloat16), t, c.to(torch.bfloat16),
+                                                                 e.to(torch.bfloat16), i).float(),
+                           lat0.clone(), ctx, te, tid, steps, guidance)
     lat = lat0.clone().cuda().contiguous()
     ctx_d, te_d, tid_d = ctx.to(torch.bfloat16).cuda(), te.to(torch.bfloat16).cuda(), tid.to(torch.int32).cuda()
     for i in range(steps):
         eng.denoise_step(lat, float(sig[i]), float(sig[i + 1]), float(ts[i]), guidance, ctx_d, te_d, tid_d)
-    assert O.rel_err(lat.cpu(), ref) < 3e-2
+    from helpers import assert_bf16_parity
+    assert_bf16_parity("tiny denoise loop (5 Euler steps)", lat.cpu(), ref, ref16)
 
 
 def test_denoise_graph_matches_eager(setup):
@@ -129,12 +134,12 @@ def test_sd15_unet_forward(sd15):
 
 
 def test_sd15_pndm_loop(sd15):
-    """6 PLMS steps (7 UNet evaluations, graph replays from the 3rd on) under CFG 7.5 vs the literal oracle loop"""
+    """4 PLMS steps (5 UNet evaluations, graph replays from the 3rd on) under CFG 7.5 vs the literal oracle loop"""
     from emu_b200.emu1.scheduler import PNDMScheduler
     sd, eng, ctx = sd15
-    steps, guidance = 6, 7.5
+    steps, guidance = 4, 7.5
     g = torch.Generator().manual_seed(17)
-    lat0 = torch.randn(1, 4, 32, 32, generator=g).to(torch.bfloat16).float()
+    lat0 = torch.randn(1, 4, 16, 16, generator=g).to(torch.bfloat16).float()
     bsd = {k: v.to(torch.bfloat16) for k, v in sd.items()}
     with torch.no_grad():
         ref32 = D.pndm_denoise_loop(lambda x, t, c: D.unet_forward(sd, SD15, x, t, c), lat0.clone(), ctx.float(), steps, guidance)
@@ -149,4 +154,4 @@ def test_sd15_pndm_loop(sd15):
         eng.denoise_step_multistep(lat, state, sch.step_coefficients(i), float(t), guidance, ctx_d)
     e_eng, e_bf = O.rel_err(lat.cpu(), ref32), O.rel_err(ref16, ref32)
     print("\n[sd15] PNDM loop: engine-vs-fp32 %.3e | bf16-oracle-vs-fp32 %.3e | ratio %.2f" % (e_eng, e_bf, e_eng / e_bf))
-    assert e_eng <= max(1.5 * e_bf, 1e-2), (e_eng, e_bf)
+    assert e_eng <= max(1.5 * e_bf, 2e-3), (e_eng, e_bf)
