@@ -138,54 +138,104 @@ def ncu_traffic():
     return None, None
 
 
-def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, ctx=75, threads=None, budget_s=25.0):
-    """Time `tokens` single-token decode steps of `layers_sampled` real-shape LLaMA layers + lm_head in bf16 on the
-    host cores with the oracle (oracle/emu_oracle.llama_forward, KV cache), extrapolate to all layers -> tok/s."""
+def _cpu_state(lc, vc, vocab, layers_sampled, g):
+    """Random-init real-shape weights of `layers_sampled` LLaMA layers + lm_head and ONE EVA-CLIP block (bf16, host)."""
+    H, F = lc["hidden_size"], lc["intermediate_size"]
+    key = (H, F, vocab, layers_sampled, vc.width)
+    if key in _CPU_SD_CACHE:
+        return _CPU_SD_CACHE[key]
+    sd = {}
+    rn = lambda *sh: (torch.randn(*sh, generator=g) * 0.02).to(torch.bfloat16)
+    for l in range(layers_sampled):
+        p = f"decoder.lm.model.layers.{l}."
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            sd[p + f"self_attn.{n}.weight"] = rn(H, H)
+        sd[p + "mlp.gate_proj.weight"] = rn(F, H)
+        sd[p + "mlp.up_proj.weight"] = rn(F, H)
+        sd[p + "mlp.down_proj.weight"] = rn(H, F)
+        sd[p + "input_layernorm.weight"] = torch.ones(H, dtype=torch.bfloat16)
+        sd[p + "post_attention_layernorm.weight"] = torch.ones(H, dtype=torch.bfloat16)
+    sd["decoder.lm.model.norm.weight"] = torch.ones(H, dtype=torch.bfloat16)
+    sd["decoder.lm.lm_head.weight"] = rn(vocab, H)
+    W, M = vc.width, int(vc.width * vc.mlp_ratio)
+    v = "visual.blocks.0."
+    sd[v + "attn.qkv.weight"] = rn(3 * W, W)
+    sd[v + "attn.q_bias"] = rn(W)
+    sd[v + "attn.v_bias"] = rn(W)
+    sd[v + "attn.proj.weight"] = rn(W, W)
+    sd[v + "attn.proj.bias"] = rn(W)
+    sd[v + "mlp.fc1.weight"] = rn(M, W)
+    sd[v + "mlp.fc1.bias"] = rn(M)
+    sd[v + "mlp.fc2.weight"] = rn(W, M)
+    sd[v + "mlp.fc2.bias"] = rn(W)
+    for n in ("norm1", "norm2"):
+        sd[v + n + ".weight"] = torch.ones(W, dtype=torch.bfloat16)
+        sd[v + n + ".bias"] = torch.zeros(W, dtype=torch.bfloat16)
+    _CPU_SD_CACHE[key] = sd
+    return sd
+
+
+def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=8, ctx=75, threads=None, budget_s=25.0, vc=None):
+    """The reference's CPU path for the headline workload, on a bounded sample, via the oracle (oracle/emu_oracle.py):
+    one real-shape EVA-CLIP block over the 1025 image tokens (x vit layers), the 75-token prompt through `layers_sampled`
+    real-shape LLaMA layers (x layers / sampled), then `tokens` single-token decode steps with the KV cache + lm_head
+    (per-layer time x layers).  Returns whole-job tok/s = new_tokens / (vit + prefill + new_tokens * per_token)."""
     from oracle import emu_oracle as O
+    import torch.nn.functional as Fn
     global _CPU_BEST_THREADS
+    if vc is None:
+        vc = emu2_cfgs(False)[0] if lc["hidden_size"] > 1024 else emu2_cfgs(True)[0]
     probe = threads is None and _CPU_BEST_THREADS is None
     threads = threads or _CPU_BEST_THREADS or os.cpu_count()
     torch.set_num_threads(threads)
     H, F, nh = lc["hidden_size"], lc["intermediate_size"], lc["num_attention_heads"]
     g = torch.Generator().manual_seed(0)
-    key = (H, F, nh, vocab, layers_sampled)
-    sd = _CPU_SD_CACHE.get(key, {})
-    for l in range(layers_sampled if not sd else 0):
-        p = f"decoder.lm.model.layers.{l}."
-        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
-            sd[p + f"self_attn.{n}.weight"] = (torch.randn(H, H, generator=g) * 0.02).to(torch.bfloat16)
-        sd[p + "mlp.gate_proj.weight"] = (torch.randn(F, H, generator=g) * 0.02).to(torch.bfloat16)
-        sd[p + "mlp.up_proj.weight"] = (torch.randn(F, H, generator=g) * 0.02).to(torch.bfloat16)
-        sd[p + "mlp.down_proj.weight"] = (torch.randn(H, F, generator=g) * 0.02).to(torch.bfloat16)
-        sd[p + "input_layernorm.weight"] = torch.ones(H, dtype=torch.bfloat16)
-        sd[p + "post_attention_layernorm.weight"] = torch.ones(H, dtype=torch.bfloat16)
-    if key not in _CPU_SD_CACHE:
-        sd["decoder.lm.model.norm.weight"] = torch.ones(H, dtype=torch.bfloat16)
-        sd["decoder.lm.lm_head.weight"] = (torch.randn(vocab, H, generator=g) * 0.02).to(torch.bfloat16)
-        _CPU_SD_CACHE[key] = sd
+    sd = _cpu_state(lc, vc, vocab, layers_sampled, g)
     cache = O.KVCache(layers_sampled)
     with torch.no_grad():
-        x = (torch.randn(1, ctx, H, generator=g) * 0.02).to(torch.bfloat16)
-        mask = torch.ones(1, ctx, dtype=torch.long)
-        O.llama_forward(sd, x, mask, layers=layers_sampled, heads=nh, cache=cache)  # prefill (untimed)
         if probe:
             # torch's CPU bf16 matrix-vector kernels do not scale to every thread count: give the reference its best
-            # setting (all cores, half, a quarter ...) from a one-layer probe, once per process
+            # setting (all cores, half, a quarter ...) from a one-layer decode probe, once per process
             best = None
             e = (torch.randn(1, 1, H, generator=g) * 0.02).to(torch.bfloat16)
             w = sd["decoder.lm.model.layers.0.mlp.gate_proj.weight"]
             cands = sorted({max(1, os.cpu_count() // d) for d in (1, 2, 4, 8, 16)}, reverse=True)
             for t in cands:
                 torch.set_num_threads(t)
-                torch.nn.functional.linear(e, w)
+                Fn.linear(e, w)
                 t0 = time.perf_counter()
                 for _ in range(3):
-                    torch.nn.functional.linear(e, w)
+                    Fn.linear(e, w)
                 dt = time.perf_counter() - t0
                 if best is None or dt < best[0]:
                     best = (dt, t)
             threads = _CPU_BEST_THREADS = best[1]
-            torch.set_num_threads(threads)
+        # ---- ViT: one post-norm block (attention + MLP) over the image tokens, all host cores ----
+        torch.set_num_threads(os.cpu_count())
+        n_tok = (vc.image_size // vc.patch_size) ** 2 + 1
+        W = vc.width
+        xv = (torch.randn(1, n_tok, W, generator=g) * 0.5).to(torch.bfloat16)
+        pre = "visual.blocks.0."
+        heads = W // vc.head_width
+
+        def vit_block(x):
+            n1 = lambda t: Fn.layer_norm(t, (W,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-6)
+            n2 = lambda t: Fn.layer_norm(t, (W,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-6)
+            x = x + n1(O.vit_attention(x, sd, pre, heads))
+            return x + n2(O.vit_mlp(x, sd, pre))
+        vit_block(xv)
+        t0 = time.perf_counter()
+        vit_block(xv)
+        vit_s = (time.perf_counter() - t0) * vc.layers
+        # ---- prefill of the prompt (timed on its second run) ----
+        x = (torch.randn(1, ctx, H, generator=g) * 0.02).to(torch.bfloat16)
+        mask = torch.ones(1, ctx, dtype=torch.long)
+        O.llama_forward(sd, x, mask, layers=layers_sampled, heads=nh, cache=O.KVCache(layers_sampled))
+        t0 = time.perf_counter()
+        O.llama_forward(sd, x, mask, layers=layers_sampled, heads=nh, cache=cache)
+        prefill_s = (time.perf_counter() - t0) * lc["num_hidden_layers"] / layers_sampled
+        # ---- decode steps ----
+        torch.set_num_threads(threads)
         per_tok = []
         t_start = time.time()
         for i in range(tokens + 1):
@@ -203,11 +253,15 @@ def cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, ctx=75, threads=Non
                 break
     layer_s = sum(a for a, _ in per_tok) / len(per_tok)
     head_s = sum(b for _, b in per_tok) / len(per_tok)
-    tok_s = 1.0 / (layer_s * lc["num_hidden_layers"] + head_s)
-    sample = ("%d real-shape LLaMA-33B decoder layers (h=%d, ffn=%d, %d heads) + lm_head, bf16, %d decode steps at "
-              "ctx %d via oracle/emu_oracle.py, per-layer time extrapolated x%d layers (ViT/prefill excluded); torch threads = %d of %d host "
-              "cores (fastest of a thread-count probe)" %
-              (layers_sampled, H, F, nh, len(per_tok), ctx, lc["num_hidden_layers"], threads, os.cpu_count()))
+    tok_step_s = layer_s * lc["num_hidden_layers"] + head_s
+    tok_s = NEW_TOKENS / (vit_s + prefill_s + NEW_TOKENS * tok_step_s)
+    sample = ("whole job = ViT + prefill + %d decode steps, each extrapolated from a real-shape sample via oracle/emu_oracle.py: "
+              "1 EVA-CLIP block (width %d, %d tokens) x%d = %.1f s; the %d-token prompt through %d LLaMA-33B layers (h=%d, ffn=%d, "
+              "%d heads) x%d = %.1f s; %d timed single-token decode steps through the same layers + lm_head = %.3f s/token "
+              "(decode-only %.2f tok/s); bf16; torch threads = %d of %d host cores for decode (fastest of a thread-count probe), "
+              "all cores for ViT / prefill" %
+              (NEW_TOKENS, W, n_tok, vc.layers, vit_s, ctx, layers_sampled, H, F, nh, lc["num_hidden_layers"] // layers_sampled,
+               prefill_s, len(per_tok), tok_step_s, 1.0 / tok_step_s, threads, os.cpu_count()))
     return tok_s, threads, sample
 
 
@@ -221,7 +275,7 @@ def run_reference(args):
     threads = os.cpu_count()
     sample = ""
     for i in range(args.warmup + args.steps):
-        v, threads, sample = cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=2, budget_s=20.0)
+        v, threads, sample = cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=8, budget_s=20.0, vc=vc)
         if i >= args.warmup:
             vals.append(v)
     val = sum(vals) / len(vals)
@@ -631,7 +685,7 @@ def run_cuda(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, threads, sample = cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=3, budget_s=25.0)
+            v, threads, sample = cpu_decode_sample(lc, vocab, layers_sampled=2, tokens=8, budget_s=25.0, vc=vc)
             cpu = {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample}
         except Exception as ex:  # the CPU baseline must never take the GPU result down with it
             cpu = {"value": None, "unit": "tok/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % ex}

@@ -21,7 +21,10 @@ template <int D>
 __global__ void __launch_bounds__(kDecThreads) attn_decode_kernel(
     const bf16* __restrict__ q, const bf16* __restrict__ k_cache, const bf16* __restrict__ v_cache, int H, int t_max,
     const int* __restrict__ pos, const int* __restrict__ start, float scale, bf16* out, float* ws_o, float* ws_ml,
-    int* counters, int nsplit, int pdl) {
+    int* counters, int nsplit, int pdl, const int* __restrict__ indir) {
+  // indir (optional, [rows][t_max]): cache row that holds token t of sequence b — beam search re-parents sequences by
+  // rewriting this table instead of moving the cache (HF's `_reorder_cache` moves it; at 4k tokens x 20 rows that is
+  // 2x the whole cache per step).
   constexpr int EPL = D / 8;  // elements per lane (8 lanes per token)
   constexpr int VPL = EPL / 8;  // uint4 per lane
   extern __shared__ __align__(16) float sm[];
@@ -47,8 +50,10 @@ __global__ void __launch_bounds__(kDecThreads) attn_decode_kernel(
   for (int i = tid; i < D; i += kDecThreads) qs[i] = __bfloat162float(q[((long)b * H + h) * D + i]) * scale;
   __syncthreads();
 
-  const bf16* kb = k_cache + ((long)b * H + h) * t_max * D;
-  const bf16* vb = v_cache + ((long)b * H + h) * t_max * D;
+  const long row_stride = (long)H * t_max * D;
+  const bf16* kb = k_cache + (long)h * t_max * D;
+  const bf16* vb = v_cache + (long)h * t_max * D;
+  const int* ind = indir ? indir + (long)b * t_max : nullptr;
 
   // ---- phase 1: scores ----
   const int part = lane & 7, tig = lane >> 3;  // 8 lanes per token, 4 tokens per warp pass
@@ -61,7 +66,8 @@ __global__ void __launch_bounds__(kDecThreads) attn_decode_kernel(
     float s = 0.f;
     const bool ok = t < t1;
     if (ok) {
-      const uint4* kr = reinterpret_cast<const uint4*>(kb + (long)t * D + part * EPL);
+      const int row = ind ? __ldg(ind + t) : b;
+      const uint4* kr = reinterpret_cast<const uint4*>(kb + row * row_stride + (long)t * D + part * EPL);
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
         const uint4 kv = ldg_stream(kr + v);
@@ -97,7 +103,8 @@ __global__ void __launch_bounds__(kDecThreads) attn_decode_kernel(
   for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
   for (int t = t0 + tl; t < t1; t += 16) {
     const float p = sc[t - t0];
-    const uint4* vr = reinterpret_cast<const uint4*>(vb + (long)t * D + dpart * EPL);
+    const int row = ind ? __ldg(ind + t) : b;
+    const uint4* vr = reinterpret_cast<const uint4*>(vb + row * row_stride + (long)t * D + dpart * EPL);
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       const uint4 vv = ldg_stream(vr + v);
@@ -155,7 +162,7 @@ size_t attn_decode_workspace_bytes(int B, int H, int D) { return (size_t)B * H *
 
 int attn_decode(const bf16* q, const bf16* k_cache, const bf16* v_cache, int B, int H, int D, int t_max,
                 const int* pos, const int* start, float scale, bf16* out, float* workspace, int* counters,
-                int max_len_hint, int pdl, cudaStream_t st) {
+                int max_len_hint, int pdl, cudaStream_t st, const int* indir) {
   if (D != 64 && D != 128) return EMU_ERR_UNSUPPORTED;
   int nsplit = (2 * kNumSMs + H * B - 1) / (H * B);
   const int by_len = (max_len_hint + 63) / 64;
@@ -186,7 +193,7 @@ int attn_decode(const bf16* q, const bf16* k_cache, const bf16* v_cache, int B, 
       mx = smem;
     }
     e = cudaLaunchKernelEx(&cfg, attn_decode_kernel<128>, q, k_cache, v_cache, H, t_max, pos, start, scale, out, ws_o,
-                           ws_ml, counters, nsplit, pdl);
+                           ws_ml, counters, nsplit, pdl, indir);
   } else {
     static size_t mx = 48 * 1024;
     if (smem > mx) {
@@ -195,7 +202,7 @@ int attn_decode(const bf16* q, const bf16* k_cache, const bf16* v_cache, int B, 
       mx = smem;
     }
     e = cudaLaunchKernelEx(&cfg, attn_decode_kernel<64>, q, k_cache, v_cache, H, t_max, pos, start, scale, out, ws_o,
-                           ws_ml, counters, nsplit, pdl);
+                           ws_ml, counters, nsplit, pdl, indir);
   }
   return e == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }

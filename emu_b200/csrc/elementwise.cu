@@ -393,6 +393,33 @@ int kv_reorder(bf16* cache, int Bcap, const int* src_idx, int B, long outer, int
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
+__global__ void kv_indir_update_kernel(int* indir, const int* __restrict__ src_idx, int B, int t_max, int n_tok) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tok) return;
+  int vals[32];
+#pragma unroll
+  for (int b = 0; b < 32; ++b)
+    if (b < B) vals[b] = indir[(long)src_idx[b] * t_max + t];
+#pragma unroll
+  for (int b = 0; b < 32; ++b)
+    if (b < B) indir[(long)b * t_max + t] = vals[b];
+}
+int kv_indir_update(int* indir, const int* src_idx, int B, int t_max, int n_tok, cudaStream_t st) {
+  if (B > 32) return EMU_ERR_INVALID;
+  if (n_tok <= 0) return EMU_OK;
+  kv_indir_update_kernel<<<(n_tok + 127) / 128, 128, 0, st>>>(indir, src_idx, B, t_max, n_tok);
+  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+}
+__global__ void kv_indir_identity_kernel(int* indir, int rows, int t_max) {
+  const long n = (long)rows * t_max;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    indir[i] = (int)(i / t_max);
+}
+int kv_indir_identity(int* indir, int rows, int t_max, cudaStream_t st) {
+  kv_indir_identity_kernel<<<kNumSMs, 256, 0, st>>>(indir, rows, t_max);
+  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+}
+
 __global__ void add_rows_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* out, long n) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(__bfloat162float(a[i]) + __bfloat162float(b[i]));

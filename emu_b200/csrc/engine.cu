@@ -312,18 +312,24 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
     e->dec_tmp = (bf16*)e->dmalloc((size_t)Bm * c.llm_hidden * 2);
     e->dec_attn_ws = (float*)e->dmalloc(attn_decode_workspace_bytes(Bm, e->Hl, c.llm_head_dim));
     e->dec_counters = (int*)e->dmalloc((size_t)Bm * e->Hl * sizeof(int));
+    e->kv_indir = (int*)e->dmalloc((size_t)Bm * c.llm_max_seq * sizeof(int));
+    {
+      const char* kc = getenv("EMU_KV_COPY");
+      e->kv_copy = kc && kc[0] == '1';
+    }
     e->dec_logits_local = (float*)e->dmalloc((size_t)Bm * c.llm_vocab * sizeof(float));
     e->dec_logits_shard = (float*)e->dmalloc(((size_t)Bm * e->Vl + 4) * sizeof(float));
     e->dec_part = (float*)e->dmalloc((size_t)Bm * c.llm_hidden * sizeof(float));
     e->dec_logits_gather = (float*)e->dmalloc((size_t)Bm * e->Vl * tp_size * sizeof(float));
     if (!e->rope_cos || !e->rope_sin || !e->kv || !e->d_pos || !e->dec_h || !e->dec_q || !e->dec_attn || !e->dec_act ||
-        !e->dec_tmp || !e->dec_attn_ws || !e->dec_counters || !e->dec_logits_local) {
+        !e->dec_tmp || !e->dec_attn_ws || !e->dec_counters || !e->dec_logits_local || !e->kv_indir) {
       emu_engine_destroy(e);
       return EMU_ERR_NOMEM;
     }
     rope_table_kernel<<<2 * kNumSMs, 256>>>(e->rope_cos, e->rope_sin, max_pos, half, c.llm_rope_theta);
     cudaMemset(e->dec_counters, 0, (size_t)Bm * e->Hl * sizeof(int));
     cudaMemset(e->d_pos, 0, 3 * kLlmMaxRows * sizeof(int));
+    kv_indir_identity(e->kv_indir, Bm, c.llm_max_seq, 0);
   }
   if (c.vit_layers > 0) {
     if (c.vit_width % c.vit_heads || c.vit_image % c.vit_patch || c.vit_width % 8) {
@@ -710,6 +716,10 @@ extern "C" int emu_llm_reset(EmuEngine* e, emu_stream_t s) {
   e->cur_len = 0;
   e->cache_B = 0;
   if (e->d_pos && cudaMemsetAsync(e->d_pos, 0, 3 * kLlmMaxRows * sizeof(int), (cudaStream_t)s) != cudaSuccess) return EMU_ERR_CUDA;
+  if (e->kv_indir && e->kv_indir_dirty) {
+    EMU_TRY(kv_indir_identity(e->kv_indir, e->cfg.llm_max_batch, e->cfg.llm_max_seq, (cudaStream_t)s));
+    e->kv_indir_dirty = false;
+  }
   return EMU_OK;
 }
 extern "C" int emu_llm_cur_len(EmuEngine* e) { return e ? e->cur_len : -1; }
@@ -727,14 +737,24 @@ __global__ void gather_rows_int_kernel(int* start, int* posoff, const int* __res
   }
 }
 
+// re-parent the cached sequences: row b continues the sequence row src[b] held.  Default: rewrite the row table the
+// decode attention reads through (a few hundred KB); EMU_KV_COPY=1 moves the cache itself like HF does.
+static int kv_reparent(EmuEngine* e, const int32_t* src_idx, int B, cudaStream_t st) {
+  const EmuConfig& c = e->cfg;
+  if (e->kv_copy)
+    return kv_reorder(e->kv, c.llm_max_batch, src_idx, B, (long)c.llm_layers * 2, e->cur_len, e->Hl, c.llm_head_dim,
+                      c.llm_max_seq, st);
+  e->kv_indir_dirty = true;
+  return kv_indir_update(e->kv_indir, src_idx, B, c.llm_max_seq, e->cur_len, st);
+}
+
 extern "C" int emu_llm_expand(EmuEngine* e, const int32_t* src_idx, int new_B, emu_stream_t stream) {
   if (!e || !src_idx || new_B < 1) return EMU_ERR_INVALID;
   const EmuConfig& c = e->cfg;
   if (new_B > c.llm_max_batch) return e->fail(EMU_ERR_INVALID, "expanded batch exceeds llm_max_batch");
   if (e->cur_len < 1) return e->fail(EMU_ERR_STATE, "expand before prefill");
   cudaStream_t st = (cudaStream_t)stream;
-  EMU_TRY(kv_reorder(e->kv, c.llm_max_batch, src_idx, new_B, (long)c.llm_layers * 2, e->cur_len, e->Hl, c.llm_head_dim,
-                     c.llm_max_seq, st));
+  EMU_TRY(kv_reparent(e, src_idx, new_B, st));
   gather_rows_int_kernel<<<1, 32, 0, st>>>(e->d_start, e->d_posoff, src_idx, new_B);
   count_launch(2);
   e->cache_B = new_B;
@@ -776,6 +796,8 @@ extern "C" int emu_llm_prefill(EmuEngine* e, const void* inputs_embeds, const in
   if (B > c.llm_max_batch) return e->fail(EMU_ERR_INVALID, "batch exceeds llm_max_batch");
   if (e->cur_len + N > c.llm_max_seq) return e->fail(EMU_ERR_INVALID, "sequence exceeds llm_max_seq");
   if (e->cur_len > 0 && B != e->cache_B) return e->fail(EMU_ERR_STATE, "batch differs from cached batch");
+  if (e->cur_len > 0 && e->kv_indir_dirty)
+    return e->fail(EMU_ERR_STATE, "a further prompt chunk after a beam re-parent needs EMU_KV_COPY=1 (the prefill attention reads rows directly)");
   const int Hd = c.llm_hidden, D = c.llm_head_dim, Hl = e->Hl, Fl = e->Fl;
   const long M = (long)B * N;
   const int pos0 = e->cur_len;
@@ -966,7 +988,7 @@ static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const v
                           cudaMemcpyDeviceToDevice, st) != cudaSuccess)
       return e->fail(EMU_ERR_CUDA, "q gather failed");
     EMU_TRY(attn_decode(e->dec_q, kc, vc, B, Hl, D, c.llm_max_seq, e->d_pos, e->d_start, scale, e->dec_attn, e->dec_attn_ws,
-                        e->dec_counters, c.llm_max_seq, 0, st));
+                        e->dec_counters, c.llm_max_seq, 0, st, e->kv_indir));
     GemmEpilogue eo;
     if (e->tp_size == 1) {
       eo.C = h; eo.ldc = Hd; eo.residual = h; eo.ldr = Hd;
@@ -1058,7 +1080,7 @@ static int decode_step_body(EmuEngine* e, const int32_t* token_ids, const void* 
     q.k_cache = kc; q.v_cache = vc; q.t_max = c.llm_max_seq; q.pdl = (l > 0 || token_ids) ? pdl : 0;
     EMU_TRY(gemv_bf16(q, st));
     EMU_TRY(attn_decode(e->dec_q, kc, vc, B, Hl, D, c.llm_max_seq, e->d_pos, e->d_start, scale, e->dec_attn,
-                        e->dec_attn_ws, e->dec_counters, c.llm_max_seq, pdl, st));
+                        e->dec_attn_ws, e->dec_counters, c.llm_max_seq, pdl, st, e->kv_indir));
     GemvArgs o;
     o.W = L.wo; o.N = Hd; o.K = Hl * D; o.x = e->dec_attn; o.ldx = Hl * D; o.B = B; o.pdl = pdl;
     if (e->tp_size == 1) {
@@ -1132,8 +1154,7 @@ extern "C" int emu_llm_decode(EmuEngine* e, const int32_t* token_ids, const void
   if (B != e->cache_B) return e->fail(EMU_ERR_STATE, "batch differs from cached batch");
   if (e->cur_len + 1 > c.llm_max_seq) return e->fail(EMU_ERR_INVALID, "KV cache full");
   if (beam_src_idx) {
-    EMU_TRY(kv_reorder(e->kv, c.llm_max_batch, beam_src_idx, B, (long)c.llm_layers * 2, e->cur_len, e->Hl, c.llm_head_dim,
-                       c.llm_max_seq, st));
+    EMU_TRY(kv_reparent(e, beam_src_idx, B, st));
     count_launch();
   }
   int nl = 0;

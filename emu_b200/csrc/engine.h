@@ -73,6 +73,9 @@ struct EmuEngine {
   emu::bf16 *dec_h = nullptr, *dec_q = nullptr, *dec_attn = nullptr, *dec_act = nullptr, *dec_tmp = nullptr;
   emu::bf16 *dec_xn = nullptr, *dec_qkv = nullptr;  // wide decode (> 8 cache rows) only
   float* dec_attn_ws = nullptr;
+  int* kv_indir = nullptr;     // [llm_max_batch][llm_max_seq]: cache row holding token t of sequence b (beam re-parenting)
+  bool kv_indir_dirty = false;  // table differs from identity
+  bool kv_copy = false;         // EMU_KV_COPY=1: move the cache on a re-parent (HF `_reorder_cache`) instead
   int* dec_counters = nullptr;
   float* dec_logits_local = nullptr;
   float *dec_logits_shard = nullptr, *dec_logits_gather = nullptr;

@@ -861,8 +861,15 @@ static int pick_bn(int M, int N, int K, const GemmEpilogue& e) {
   for (int bn : cand) {
     const long tiles = tm * ((N + bn - 1) / bn);
     const long waves = (tiles + kNumSMs - 1) / kNumSMs;
-    const double mma = 2.0 * bn, l2 = (128.0 + bn) * 128.0 / 75.0;
-    const double ml = (double)kb * (mma > l2 ? mma : l2) + 1500.0;  // + pipeline fill
+    const double a_rows = M < 128 ? (double)M : 128.0;  // rows past M are zero-filled by TMA, not fetched
+    const double mma = 2.0 * bn, l2 = (a_rows + bn) * 128.0 / 75.0;
+    double per_kb = mma > l2 ? mma : l2;
+    if (tm == 1) {  // one row of tiles: every weight byte comes from HBM exactly once, shared by the busy SMs (~3370 B/clk)
+      const double active = tiles < kNumSMs ? (double)tiles : (double)kNumSMs;
+      const double hbm = bn * 128.0 * active / 3370.0;
+      if (hbm > per_kb) per_kb = hbm;
+    }
+    const double ml = (double)kb * per_kb + 1500.0;  // + pipeline fill
     const bool staged = !env_no_stage() && can_stage(e, N, bn);
     double per_col = staged ? (act ? 20.0 : 6.0) : (act ? 60.0 : (e.residual ? 47.0 : 21.0));
     const double epi = per_col * bn + 400.0;

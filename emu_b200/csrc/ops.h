@@ -88,7 +88,8 @@ int gemv_init();  // allocate the stream-K workspace (must run once outside stre
 // decode: one query token per sequence against the KV cache (slots [start[b], pos[b]] inclusive)
 int attn_decode(const bf16* q /*[B, H*D] pair-interleaved like k*/, const bf16* k_cache, const bf16* v_cache,
                 int B, int H, int D, int t_max, const int* pos, const int* start, float scale, bf16* out /*[B,H*D]*/,
-                float* workspace, int* counters, int max_len_hint, int pdl, cudaStream_t st);
+                float* workspace, int* counters, int max_len_hint, int pdl, cudaStream_t st,
+                const int* indir = nullptr /*[rows][t_max] cache row holding token t of sequence b; null = own row*/);
 size_t attn_decode_workspace_bytes(int B, int H, int D);
 // prefill / encoder attention (flash style, mma.sync): q,k,v given as strided [B, N, H, D] views
 struct AttnArgs {
@@ -148,6 +149,9 @@ int vit_pool(const bf16* x /*[B,1+G*G,dim]*/, bf16* out /*[B,n_query,dim]*/, int
              cudaStream_t st);
 int kv_reorder(bf16* cache /*[outer][Bcap][H][t_max][D]*/, int Bcap, const int* src_idx, int B, long outer,
                int n_used_tokens, int H, int D, int t_max, cudaStream_t st);
+// beam re-parenting without moving the cache: indir[b][t] <- indir[src[b]][t] for t < n_tok (in place, column-wise)
+int kv_indir_update(int* indir /*[rows][t_max]*/, const int* src_idx, int B, int t_max, int n_tok, cudaStream_t st);
+int kv_indir_identity(int* indir, int rows, int t_max, cudaStream_t st);
 int add_rows(const bf16* a, const bf16* b, bf16* out, long n, cudaStream_t st);
 
 }  // namespace emu

@@ -274,3 +274,41 @@ def test_beam_search_batch4_x_5_beams(wide_model, gold):
     assert all(torch.equal(out4[i], out4[0]) for i in range(4))      # identical prompts -> identical hypotheses
     n = min(out4.shape[1], out1.shape[1])
     assert n >= 1 and out4.shape[1] == out1.shape[1] or True          # lengths may differ at a near tie; both are valid beams
+
+
+def test_beam_reparent_table_equals_cache_copy(cuda, sd, gold):
+    """Beam re-parenting rewrites the row table the decode attention reads through; EMU_KV_COPY=1 moves the cache like
+    HF's `_reorder_cache`.  Both must give bit-identical logits over expand + permuted steps (narrow and wide paths)."""
+    from emu_b200.emu2.conf import CLIPVisionCfg, TextDecoderCfg
+    from emu_b200.emu2.emu import EmuModel
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(100, 30000, (2, 7), generator=g).cuda()
+    mask = torch.ones(2, 7, dtype=torch.long)
+    mask[1, :2] = 0
+    mask = mask.cuda()
+    res = {}
+    for mode in ("0", "1"):
+        os.environ["EMU_KV_COPY"] = mode
+        try:
+            m = EmuModel(CLIPVisionCfg(**TINY_VISION), TextDecoderCfg(), tokenizer=StubTokenizer(), llama_config=TINY_LLAMA,
+                         max_batch=12, max_seq=64)
+        finally:
+            os.environ.pop("EMU_KV_COPY", None)
+        m.load_state_dict(sd)
+        eng = m.engine
+        outs = []
+        for nb in (3, 6):                                  # 6 rows: narrow path; 12 rows: wide path
+            eng.llm_reset()
+            eng.llm_prefill(eng.llm_embed(ids), mask, hf_positions=True, want_logits=True)
+            B = 2 * nb
+            eng.llm_expand(torch.arange(B, dtype=torch.int32, device="cuda") // nb, B)
+            gg = torch.Generator().manual_seed(17)
+            buf = torch.empty(B, TINY_LLAMA["vocab_size"], dtype=torch.float32, device="cuda")
+            for step in range(4):
+                tok = torch.randint(100, 30000, (B,), generator=gg).to(torch.int32).cuda()
+                src = (torch.arange(B) // nb) * nb + torch.randint(0, nb, (B,), generator=gg)
+                eng.llm_decode(token_ids=tok, logits=buf, B=B, beam_src=src.to(torch.int32).cuda() if step else None)
+                outs.append(buf.clone())
+        res[mode] = outs
+    for a, b in zip(res["0"], res["1"]):
+        assert torch.equal(a, b)
