@@ -60,7 +60,7 @@ SYMBOLS = [
     "emu_beam_topk", "emu_beam_step", "emu_sample_tokens", "emu_image_to_uint8", "emu_preprocess_image", "emu_engine_create", "emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_tp_head_range", "emu_engine_load_tensor",
     "emu_vit_forward", "emu_llm_reset", "emu_llm_embed", "emu_llm_prefill", "emu_llm_decode", "emu_llm_cur_len", "emu_llm_expand",
     "emu_project", "emu_cformer_forward", "emu_unet_configure", "emu_unet_forward", "emu_denoise_step",
-    "emu_denoise_step_multistep", "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
+    "emu_denoise_step_multistep", "emu_vae_configure", "emu_vae_decode", "emu_op_gemm", "emu_op_gemm_skinny", "emu_op_conv3x3", "emu_op_gemv", "emu_op_gemv_rope_qkv",
     "emu_op_attn_prefill", "emu_op_attn_decode", "emu_op_rmsnorm", "emu_op_layernorm", "emu_launch_count",
     "emu_debug_gemm_phases", "emu_debug_gemv_phases",
     "emu_version",
@@ -199,6 +199,14 @@ class Engine:
                    ban_id=-1, B=None):
         if B is None:
             B = token_ids.shape[0] if token_ids is not None else embeds.shape[0]
+        # the C entry point takes bare pointers: a short buffer would be written past its end
+        c = self.cfg
+        for name, t, need, dt in (("logits", logits, B * c.llm_vocab, torch.float32), ("hidden", hidden, B * c.llm_hidden, torch.bfloat16),
+                                  ("next_ids", next_ids, B, torch.int32), ("token_ids", token_ids, B, torch.int32),
+                                  ("beam_src", beam_src, B, torch.int32), ("embeds", embeds, B * c.llm_hidden, torch.bfloat16)):
+            if t is not None and (t.dtype != dt or t.numel() < need or not t.is_contiguous()):
+                raise ValueError(f"llm_decode: {name} must be a contiguous {dt} tensor of at least {need} elements, got "
+                                 f"{tuple(t.shape)} {t.dtype}")
         check(self.lib.emu_llm_decode(self.h, _ptr(token_ids), _ptr(embeds), _ptr(beam_src), B, _ptr(logits),
                                       _ptr(hidden), _ptr(next_ids), ban_id, _stream()), self.h)
 
@@ -311,6 +319,20 @@ def op_gemm(A, W, bias=None, residual=None, epi=EPI_NONE, out_fp32=False, force_
                          residual.stride(0) if residual is not None else 0, epi, _ptr(Cm), n_out,
                          1 if out_fp32 else 0, force_bn, _stream())
     check(rc)
+    return Cm
+
+
+def op_gemm_skinny(X, W, residual=None, epi=EPI_NONE, out_fp32=False):
+    """X [B <= 32, K] . W [N, K]^T through the wide-decode projection kernel (gemm_skinny.cu)"""
+    require_cuda()
+    lib = load()
+    B, K = X.shape
+    N = W.shape[0]
+    n_out = N // 2 if epi == EPI_SWIGLU else N
+    Cm = torch.empty(B, n_out, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=X.device)
+    check(lib.emu_op_gemm_skinny(_ptr(X), X.stride(0), _ptr(W), W.stride(0), B, N, K, _ptr(residual),
+                                 residual.stride(0) if residual is not None else 0, epi, _ptr(Cm), n_out, 1 if out_fp32 else 0,
+                                 _stream()))
     return Cm
 
 

@@ -16,6 +16,23 @@ extern "C" int emu_op_gemm(const void* A, int lda, const void* W, int ldw, int M
   return gemm_bf16((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, e, (cudaStream_t)s);
 }
 
+// the wide-decode projection kernel (weights as the 128-row MMA operand, K-split partial sums), stand-alone
+extern "C" int emu_op_gemm_skinny(const void* X, int ldx, const void* W, int ldw, int B, int N, int K, const void* residual,
+                                  int ldr, int epi_mode, void* C, int ldc, int out_fp32, emu_stream_t s) {
+  if (!X || !W || !C) return EMU_ERR_INVALID;
+  static float* ws = nullptr;
+  static int* counters = nullptr;
+  if (!ws) {
+    if (cudaMalloc((void**)&ws, gemm_skinny_workspace_bytes()) != cudaSuccess) return EMU_ERR_NOMEM;
+    if (cudaMalloc((void**)&counters, kSkinnyMaxTiles * sizeof(int)) != cudaSuccess) return EMU_ERR_NOMEM;
+    if (cudaMemset(counters, 0, kSkinnyMaxTiles * sizeof(int)) != cudaSuccess) return EMU_ERR_CUDA;
+  }
+  GemmEpilogue e;
+  e.C = C; e.ldc = ldc; e.residual = (const bf16*)residual; e.ldr = ldr; e.mode = epi_mode; e.out_fp32 = out_fp32;
+  count_launch();
+  return gemm_skinny_bf16((const bf16*)X, ldx, (const bf16*)W, ldw, B, N, K, e, ws, counters, (cudaStream_t)s);
+}
+
 extern "C" int emu_debug_gemm_phases(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const void* bias,
                                      const void* residual, int ldr, int epi_mode, void* C, int ldc, int force_bn,
                                      unsigned long long* stamps /*[148][8] device*/, emu_stream_t s) {

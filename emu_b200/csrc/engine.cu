@@ -299,10 +299,15 @@ extern "C" int emu_engine_create(const EmuConfig* cfg, int tp_rank, int tp_size,
     if (c.llm_max_batch > 8) {  // wide decode (more than 8 cache rows: the C4 workload, 4 prompts x 5 beams) runs on the GEMM path
       e->dec_xn = (bf16*)e->dmalloc((size_t)c.llm_max_batch * c.llm_hidden * 2);
       e->dec_qkv = (bf16*)e->dmalloc((size_t)c.llm_max_batch * 3 * e->Hl * c.llm_head_dim * 2);
-      if (!e->dec_xn || !e->dec_qkv) {
+      e->sk_ws = (float*)e->dmalloc(gemm_skinny_workspace_bytes());
+      e->sk_counters = (int*)e->dmalloc(kSkinnyMaxTiles * sizeof(int));
+      if (!e->dec_xn || !e->dec_qkv || !e->sk_ws || !e->sk_counters || gemm_skinny_init() != EMU_OK) {
         emu_engine_destroy(e);
         return EMU_ERR_NOMEM;
       }
+      cudaMemset(e->sk_counters, 0, kSkinnyMaxTiles * sizeof(int));
+      const char* wsk = getenv("EMU_WIDE_SKINNY");
+      e->wide_skinny = !(wsk && wsk[0] == '0');
     }
     const int Bm = c.llm_max_batch;
     e->dec_h = (bf16*)e->dmalloc((size_t)Bm * c.llm_hidden * 2);
@@ -959,6 +964,17 @@ static int row_parallel_tail(EmuEngine* e, GemvArgs& g, bf16* h, int B, int Hd, 
 // HBM-bound), RoPE + cache append as in prefill but at the device-side slot, the split-KV decode attention over the cache,
 // NCCL all-reduce on the row-parallel outputs under tensor parallelism.  Same arithmetic / rounding points as the narrow
 // path; captured into the same CUDA-graph cache.
+// a projection of the wide decode step: weights as the 128-row MMA operand (gemm_skinny.cu); shapes or epilogues that kernel
+// does not take go to the general GEMM
+static int wide_gemm(EmuEngine* e, const bf16* X, int ldx, const bf16* W, int ldw, int B, int N, int K, const GemmEpilogue& ep,
+                     cudaStream_t st) {
+  if (e->wide_skinny && e->sk_ws) {
+    const int rc = gemm_skinny_bf16(X, ldx, W, ldw, B, N, K, ep, e->sk_ws, e->sk_counters, st);
+    if (rc != EMU_ERR_UNSUPPORTED) return rc;
+  }
+  return gemm_bf16(X, ldx, W, ldw, B, N, K, ep, st);
+}
+
 static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const void* embeds, int B, float* logits,
                                  void* hidden, int32_t* next_ids, int ban_id, cudaStream_t st, int* n_launch) {
   const EmuConfig& c = e->cfg;
@@ -982,7 +998,7 @@ static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const v
     EMU_TRY(rmsnorm(h, L.ln1, xn, B, Hd, c.llm_rms_eps, 0, st));
     GemmEpilogue ep;
     ep.C = qkv; ep.ldc = 3 * Hl * D;
-    EMU_TRY(gemm_bf16(xn, Hd, L.wqkv, Hd, B, 3 * Hl * D, Hd, ep, st));
+    EMU_TRY(wide_gemm(e, xn, Hd, L.wqkv, Hd, B, 3 * Hl * D, Hd, ep, st));
     EMU_TRY(rope_kv_write(qkv, B, 1, Hl, D, e->rope_cos, e->rope_sin, e->d_posoff, 0, kc, vc, c.llm_max_seq, st, e->d_pos));
     if (cudaMemcpy2DAsync(e->dec_q, (size_t)Hl * D * 2, qkv, (size_t)3 * Hl * D * 2, (size_t)Hl * D * 2, B,
                           cudaMemcpyDeviceToDevice, st) != cudaSuccess)
@@ -992,10 +1008,10 @@ static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const v
     GemmEpilogue eo;
     if (e->tp_size == 1) {
       eo.C = h; eo.ldc = Hd; eo.residual = h; eo.ldr = Hd;
-      EMU_TRY(gemm_bf16(e->dec_attn, Hl * D, L.wo, Hl * D, B, Hd, Hl * D, eo, st));
+      EMU_TRY(wide_gemm(e, e->dec_attn, Hl * D, L.wo, Hl * D, B, Hd, Hl * D, eo, st));
     } else {
       eo.C = e->dec_tmp; eo.ldc = Hd;
-      EMU_TRY(gemm_bf16(e->dec_attn, Hl * D, L.wo, Hl * D, B, Hd, Hl * D, eo, st));
+      EMU_TRY(wide_gemm(e, e->dec_attn, Hl * D, L.wo, Hl * D, B, Hd, Hl * D, eo, st));
       EMU_TRY(nccl_allreduce_bf16(e, e->dec_tmp, (size_t)B * Hd, st));
       EMU_TRY(add_rows(h, e->dec_tmp, h, (long)B * Hd, st));
       nl += 2;
@@ -1003,14 +1019,14 @@ static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const v
     EMU_TRY(rmsnorm(h, L.ln2, xn, B, Hd, c.llm_rms_eps, 0, st));
     GemmEpilogue eg;
     eg.C = e->dec_act; eg.ldc = Fl; eg.mode = EPI_SWIGLU;
-    EMU_TRY(gemm_bf16(xn, Hd, L.wgu, Hd, B, 2 * Fl, Hd, eg, st));
+    EMU_TRY(wide_gemm(e, xn, Hd, L.wgu, Hd, B, 2 * Fl, Hd, eg, st));
     GemmEpilogue ed;
     if (e->tp_size == 1) {
       ed.C = h; ed.ldc = Hd; ed.residual = h; ed.ldr = Hd;
-      EMU_TRY(gemm_bf16(e->dec_act, Fl, L.wdown, Fl, B, Hd, Fl, ed, st));
+      EMU_TRY(wide_gemm(e, e->dec_act, Fl, L.wdown, Fl, B, Hd, Fl, ed, st));
     } else {
       ed.C = e->dec_tmp; ed.ldc = Hd;
-      EMU_TRY(gemm_bf16(e->dec_act, Fl, L.wdown, Fl, B, Hd, Fl, ed, st));
+      EMU_TRY(wide_gemm(e, e->dec_act, Fl, L.wdown, Fl, B, Hd, Fl, ed, st));
       EMU_TRY(nccl_allreduce_bf16(e, e->dec_tmp, (size_t)B * Hd, st));
       EMU_TRY(add_rows(h, e->dec_tmp, h, (long)B * Hd, st));
       nl += 2;
@@ -1028,10 +1044,10 @@ static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const v
     el.out_fp32 = 1;
     if (e->tp_size == 1) {
       el.C = lg; el.ldc = c.llm_vocab;
-      EMU_TRY(gemm_bf16(xn, Hd, e->lm_head, Hd, B, e->Vl, Hd, el, st));
+      EMU_TRY(wide_gemm(e, xn, Hd, e->lm_head, Hd, B, e->Vl, Hd, el, st));
     } else {
       el.C = e->dec_logits_shard; el.ldc = e->Vl;
-      EMU_TRY(gemm_bf16(xn, Hd, e->lm_head, Hd, B, e->Vl, Hd, el, st));
+      EMU_TRY(wide_gemm(e, xn, Hd, e->lm_head, Hd, B, e->Vl, Hd, el, st));
       EMU_TRY(gather_logits(e, e->dec_logits_shard, e->dec_logits_gather, lg, B, st));
       nl += 2;
     }

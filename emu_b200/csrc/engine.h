@@ -73,6 +73,9 @@ struct EmuEngine {
   emu::bf16 *dec_h = nullptr, *dec_q = nullptr, *dec_attn = nullptr, *dec_act = nullptr, *dec_tmp = nullptr;
   emu::bf16 *dec_xn = nullptr, *dec_qkv = nullptr;  // wide decode (> 8 cache rows) only
   float* dec_attn_ws = nullptr;
+  float* sk_ws = nullptr;      // gemm_skinny K-split partial sums (wide decode)
+  int* sk_counters = nullptr;
+  bool wide_skinny = true;     // EMU_WIDE_SKINNY=0: wide decode projections on gemm_tc instead
   int* kv_indir = nullptr;     // [llm_max_batch][llm_max_seq]: cache row holding token t of sequence b (beam re-parenting)
   bool kv_indir_dirty = false;  // table differs from identity
   bool kv_copy = false;         // EMU_KV_COPY=1: move the cache on a re-parent (HF `_reorder_cache`) instead

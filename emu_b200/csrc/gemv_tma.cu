@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_con
   __shared__ float s_rstd[8];
   __shared__ int s_last;
   __shared__ GemvTmaParams s_params;
+  __shared__ __align__(8) uint64_t s_xbar;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // diagnostics: {globaltimer at entry; clock64 at entry, barriers ready, dependency resolved, x staged, first weight chunk
@@ -92,6 +93,9 @@ __global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_con
     mbar_init(&full_bar[threadIdx.x], 1);
     mbar_init(&empty_bar[threadIdx.x], kTW);
     mbar_fence_init();
+  } else if (threadIdx.x == 32) {
+    mbar_init(&s_xbar, 1);
+    mbar_fence_init();
   }
   __syncthreads();
   if (dbg && threadIdx.x == 0) dbg[2] = clk();
@@ -108,13 +112,15 @@ __global__ void __launch_bounds__(kTThreads, 2) gemv_tma_kernel(const __grid_con
   if (p.a.pdl) pdl_wait();
   if (dbg && threadIdx.x == 0) dbg[3] = clk();
   const int xsc = (p.xsc > 0 && p.xsc < p.cpt) ? p.xsc : p.cpt;
-  tma_stage_x(p, xs, s_ss, s_rstd, (int)(c0 % p.cpt) / xsc, &pre);
+  uint32_t xphase = 0;
+  if (p.xbulk) tma_stage_x_bulk(p, xs, s_ss, s_rstd, (int)(c0 % p.cpt) / xsc, &pre, &s_xbar, xphase);
+  else tma_stage_x(p, xs, s_ss, s_rstd, (int)(c0 % p.cpt) / xsc, &pre);
   if (dbg && threadIdx.x == 0) {
     dbg[4] = clk();
     if (c0 < c1) mbar_wait(&full_bar[0], 0);  // (diagnostic only) when did the first chunk land?
     dbg[5] = clk();
   }
-  tma_consume(&s_params, c0, c1, ring, full_bar, empty_bar, red, fin, xs, &s_last, stage, phase, s_rstd);
+  tma_consume(&s_params, c0, c1, ring, full_bar, empty_bar, red, fin, xs, &s_last, stage, phase, s_rstd, &s_xbar, &xphase);
   if (dbg && threadIdx.x == 0) dbg[6] = clk();
   if (p.a.ll_n > 0 && p.a.ll_h != nullptr && (int)blockIdx.x < p.a.ll_red) gemv_tail_reduce(p.a);
   if (dbg && threadIdx.x == 0) dbg[7] = clk();
@@ -163,6 +169,15 @@ int gemv_tma_bf16(const GemvArgs& a, cudaStream_t st) {
       p.xsc = xsc;
       p.ldxs = xsc * kTCols + 8;
     }
+  }
+  {
+    static int env_bulk = -1;
+    if (env_bulk < 0) {
+      const char* v = getenv("EMU_GEMV_XBULK");
+      env_bulk = v ? atoi(v) : 1;
+    }
+    // bulk row copies need 16-byte aligned rows; the in-place norm needs the whole row in shared memory
+    p.xbulk = env_bulk && (a.ldx % 8 == 0) && !(reinterpret_cast<uintptr_t>(a.x) & 15) && (a.norm_w == nullptr || p.xsc == 0);
   }
   p.total = (long)groups * p.cpt;
   p.ws = g_tws;

@@ -26,6 +26,7 @@ struct GemvTmaParams {
   int cpt;       // chunks per row group
   int xsc;       // chunks of x staged in shared memory at a time (0 or >= cpt: the whole row; smaller: K segments that
                  //   are re-staged as the chunk stream crosses them — batch x K too large for shared memory, e.g. 5 x 17920)
+  int xbulk;     // x reaches shared memory by cp.async.bulk row copies (aligned rows; normalised in place afterwards)
   int nstages;   // ring depth actually used (<= kTStages)
   int geff;      // number of CTAs that share this matrix's chunks (<= gridDim.x); CTAs >= geff get none
   long total;    // total chunks
@@ -263,11 +264,115 @@ static __device__ __forceinline__ void tma_stage_x(const GemvTmaParams& p, bf16*
   tma_stage_x_seg(p, xs, s_rstd, seg, pre);
 }
 
+// ---- bulk-copy staging: every batch row of the segment flies at once (one latency, no registers) ----
+// The per-row load loops above pay one L2 round trip per batch row and pass (sum of squares, then the copy): ~10 us per
+// GEMV at 5 beams.  Here thread 0 issues one cp.async.bulk per row, all 256 consumers wait on one mbarrier, and the
+// RMSNorm (whole-row staging only) is applied in place from shared memory.
+static __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+static __device__ __forceinline__ void tma_stage_x_bulk(const GemvTmaParams& p, bf16* xs, float (*s_ss)[8], float* s_rstd,
+                                                        int seg, const XPre* pre, uint64_t* xbar, uint32_t& xphase) {
+  const GemvArgs& a = p.a;
+  const int K = a.K, B = a.B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xsc = (p.xsc > 0 && p.xsc < p.cpt) ? p.xsc : p.cpt;
+  const int col0 = seg * xsc * kTCols;
+  const int ncols_pad = min(xsc, p.cpt - seg * xsc) * kTCols;
+  const int ncols = min(ncols_pad, K - col0);
+  if (threadIdx.x == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier reads of xs are ordered before the async writes
+    mbar_expect_tx(xbar, (uint32_t)B * (uint32_t)ncols * 2u);
+    for (int b = 0; b < B; ++b) bulk_g2s(xs + (long)b * p.ldxs, a.x + (long)b * a.ldx + col0, (uint32_t)ncols * 2u, xbar);
+  }
+  const int padv = (ncols_pad - ncols) >> 3;  // zero the columns past K (generic writes, disjoint from the copies)
+  for (int i = threadIdx.x; i < B * padv; i += 256) {
+    const int b = i / padv, j = i - b * padv;
+    reinterpret_cast<uint4*>(xs + (long)b * p.ldxs + ncols)[j] = make_uint4(0, 0, 0, 0);
+  }
+  mbar_wait(xbar, xphase);
+  xphase ^= 1;
+  if (a.norm_w != nullptr) {  // whole row staged (host guarantees it): LlamaRMSNorm in place
+    const int vec_per_row = K >> 3;
+    float ss[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) ss[b] = 0.f;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      if (b < B) {
+        const uint4* row = reinterpret_cast<const uint4*>(xs + (long)b * p.ldxs);
+        float s = 0.f;
+        for (int i = threadIdx.x; i < vec_per_row; i += 256) {
+          const uint4 v = row[i];
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float lo = bf16_lo(w4[q]), hi = bf16_hi(w4[q]);
+            s += lo * lo + hi * hi;
+          }
+        }
+        ss[b] = warp_sum(s);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int b = 0; b < 8; ++b) s_ss[warp][b] = ss[b];
+    }
+    consumer_bar();
+    if (threadIdx.x < 8) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kTW; ++w) tot += s_ss[w][threadIdx.x];
+      s_rstd[threadIdx.x] = rsqrtf(tot / (float)K + a.norm_eps);
+    }
+    consumer_bar();
+    const uint4* wsrc = reinterpret_cast<const uint4*>(a.norm_w);
+    const bool use_pre = pre != nullptr && pre->have;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = (int)threadIdx.x + 256 * j;
+      if (i >= vec_per_row) break;
+      const uint4 w = use_pre ? pre->w[j] : __ldg(wsrc + i);
+      const uint32_t w4[4] = {w.x, w.y, w.z, w.w};
+      for (int b = 0; b < B; ++b) {
+        uint4* row = reinterpret_cast<uint4*>(xs + (long)b * p.ldxs);
+        const float rstd = s_rstd[b];
+        const uint4 v = row[i];
+        const uint32_t v4[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
+          o4[q] = pack_bf16(round_bf16(bf16_lo(v4[q]) * rstd) * bf16_lo(w4[q]), round_bf16(bf16_hi(v4[q]) * rstd) * bf16_hi(w4[q]));
+        row[i] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+    for (int i = (int)threadIdx.x + 1024; i < vec_per_row; i += 256) {  // K > 8192
+      const uint4 w = __ldg(wsrc + i);
+      const uint32_t w4[4] = {w.x, w.y, w.z, w.w};
+      for (int b = 0; b < B; ++b) {
+        uint4* row = reinterpret_cast<uint4*>(xs + (long)b * p.ldxs);
+        const float rstd = s_rstd[b];
+        const uint4 v = row[i];
+        const uint32_t v4[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          o4[q] = pack_bf16(round_bf16(bf16_lo(v4[q]) * rstd) * bf16_lo(w4[q]), round_bf16(bf16_hi(v4[q]) * rstd) * bf16_hi(w4[q]));
+        row[i] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+  }
+  consumer_bar();
+}
+
 // ---- consumers: pull this CTA's chunks [c0, c1) out of the ring, mma them against xs, finish row groups ----
 static __device__ __forceinline__ void tma_consume(const GemvTmaParams* sp, long c0, long c1, uint8_t* ring,
                                                    uint64_t* full_bar, uint64_t* empty_bar, float* red, float* fin,
                                                    bf16* xs, int* s_last, int& stage, uint32_t& phase,
-                                                   const float* s_rstd = nullptr) {
+                                                   const float* s_rstd = nullptr, uint64_t* xbar = nullptr,
+                                                   uint32_t* xphase = nullptr) {
   const GemvTmaParams& p = *sp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -302,7 +407,8 @@ static __device__ __forceinline__ void tma_consume(const GemvTmaParams* sp, long
     }
     if (restage) {  // all 8 consumer warps take this branch together (same chunk stream)
       consumer_bar();
-      tma_stage_x_seg(p, xs, s_rstd, cur_seg);
+      if (p.xbulk) tma_stage_x_bulk(p, xs, nullptr, nullptr, cur_seg, nullptr, xbar, *xphase);  // segmented => no norm
+      else tma_stage_x_seg(p, xs, s_rstd, cur_seg);
     }
     mbar_wait(&full_bar[stage], phase);
     const uint32_t tbase = smem_u32(ring + stage * kTStageBytes + tile_j * (kTRows * 128));

@@ -234,9 +234,102 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamStepArgs a) {
   }
 }
 
-// top-`keep` of each group of n contiguous values (n = beams * V), largest first, ties to the lower index.
+// top-`keep` of each group of n contiguous values (n = beams * V), largest first, ties to the lower index, NaN never
+// selected, every index at most once (like torch.topk).  Two levels in ONE launch: the group is cut into slices, one CTA per
+// slice keeps the slice in shared memory as order-preserving 64-bit items {key(value), ~index} and extracts its own top-keep
+// by repeated block-max; the CTA that finishes a group last merges the per-slice candidates the same way.  (Round 1 walked
+// the whole group `keep` times with one CTA: 10 dependent passes over 5 x 32k floats, ~0.4 ms of every beam step.)
+constexpr int kTopkThreads = 256;
+constexpr int kTopkMaxKeep = 32;
+constexpr int kTopkMaxParts = 2 * 148;
+constexpr int kTopkSlice = 4096;  // values per slice (shared-memory items: 32 KB)
+
+__device__ __forceinline__ uint32_t topk_key(float x) {  // monotone map; 0 is reserved for "nothing" (NaN, taken, padding)
+  if (x != x) return 0u;
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // -inf -> 0x007fffff > 0
+}
+
+// block-wide argmax over `items[0..cnt)`, `rounds` times; winner r goes to out[r] (0 when nothing is left) and is cleared
+__device__ __forceinline__ void topk_rounds(unsigned long long* items, int cnt, int rounds, unsigned long long* out,
+                                            unsigned long long* s_w /*[8]*/, bool local_index, unsigned base) {
+  for (int r = 0; r < rounds; ++r) {
+    unsigned long long best = 0ull;
+    for (int i = threadIdx.x; i < cnt; i += kTopkThreads) {
+      const unsigned long long v = items[i];
+      best = v > best ? v : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ov = __shfl_xor_sync(0xffffffffu, best, o);
+      best = ov > best ? ov : best;
+    }
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = best;
+    __syncthreads();
+    best = s_w[0];
+#pragma unroll
+    for (int w = 1; w < kTopkThreads / 32; ++w) best = s_w[w] > best ? s_w[w] : best;
+    if (threadIdx.x == 0) out[r] = best;
+    if (best != 0ull) {
+      // clear the winner: its slot is known from the index (slice level) or found by value (merge level: items are unique)
+      if (local_index) {
+        if (threadIdx.x == 0) items[(0xffffffffu - (unsigned)(best & 0xffffffffull)) - base] = 0ull;
+      } else {
+        for (int i = threadIdx.x; i < cnt; i += kTopkThreads)
+          if (items[i] == best) items[i] = 0ull;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kTopkThreads) topk_group_kernel(const float* __restrict__ x, long n, int keep, int parts,
+                                                                  unsigned long long* cand /*[groups][parts][keep]*/,
+                                                                  int* counters /*[groups]*/, float* out_val, int* out_idx) {
+  __shared__ unsigned long long items[kTopkSlice];
+  __shared__ unsigned long long s_w[kTopkThreads / 32];
+  __shared__ unsigned long long s_out[kTopkMaxKeep];
+  __shared__ int s_last;
+  const int grp = blockIdx.y, part = blockIdx.x;
+  const float* g = x + (long)grp * n;
+  const long per = (n + parts - 1) / parts;
+  const long lo = (long)part * per;
+  const int cnt = (int)max(0L, min(per, n - lo));
+  for (int i = threadIdx.x; i < cnt; i += kTopkThreads) {
+    const uint32_t k = topk_key(__ldcg(g + lo + i));
+    items[i] = k ? (((unsigned long long)k << 32) | (unsigned long long)(0xffffffffu - (unsigned)(lo + i))) : 0ull;
+  }
+  __syncthreads();
+  topk_rounds(items, cnt, keep, s_out, s_w, true, (unsigned)lo);
+  unsigned long long* mine = cand + ((long)grp * parts + part) * keep;
+  if (threadIdx.x < keep) mine[threadIdx.x] = s_out[threadIdx.x];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(&counters[grp], 1);
+    s_last = prev == parts - 1;
+    if (s_last) counters[grp] = 0;  // self-reset for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // merge: parts * keep candidates (<= 2048 by construction of `parts`)
+  const int total = parts * keep;
+  const unsigned long long* all = cand + (long)grp * parts * keep;
+  for (int i = threadIdx.x; i < total; i += kTopkThreads) items[i] = __ldcg(all + i);
+  __syncthreads();
+  topk_rounds(items, total, keep, s_out, s_w, false, 0u);
+  if (threadIdx.x < keep) {
+    const unsigned long long w = s_out[threadIdx.x];
+    const unsigned idx = w ? 0xffffffffu - (unsigned)(w & 0xffffffffull) : 0u;
+    out_val[(long)grp * keep + threadIdx.x] = w ? __ldcg(g + idx) : -INFINITY;  // nothing left (NaN rows): -inf at index 0
+    out_idx[(long)grp * keep + threadIdx.x] = (int)idx;
+  }
+}
+
+// fallback for groups too large for the sliced kernel: one CTA walks the whole group `keep` times.
 // DESTRUCTIVE: every selected entry is overwritten with -inf (the buffer is the decode step's scratch logits).
-__global__ void __launch_bounds__(1024) topk_group_kernel(float* x, long n, int keep, float* out_val, int* out_idx) {
+__global__ void __launch_bounds__(1024) topk_group_walk_kernel(float* x, long n, int keep, float* out_val, int* out_idx) {
   __shared__ float sv[32];
   __shared__ long si[32];
   float* g = x + (long)blockIdx.x * n;
@@ -274,6 +367,31 @@ __global__ void __launch_bounds__(1024) topk_group_kernel(float* x, long n, int 
     }
     __syncthreads();
   }
+}
+
+static unsigned long long* g_topk_cand = nullptr;
+static int* g_topk_counters = nullptr;
+static int topk_groups(float* x, int groups, long n, int keep, float* out_val, int* out_idx, cudaStream_t st) {
+  auto walk = [&]() {
+    topk_group_walk_kernel<<<groups, 1024, 0, st>>>(x, n, keep, out_val, out_idx);
+    return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
+  };
+  if (keep > kTopkMaxKeep || groups > 64 || n >= 0xffffffffL) return walk();
+  if (!g_topk_cand) {  // first use (never under stream capture: the beam step is launched eagerly)
+    if (cudaMalloc((void**)&g_topk_cand, (size_t)64 * kTopkSlice * sizeof(unsigned long long)) != cudaSuccess) return EMU_ERR_NOMEM;
+    if (cudaMalloc((void**)&g_topk_counters, 64 * sizeof(int)) != cudaSuccess) return EMU_ERR_NOMEM;
+    if (cudaMemset(g_topk_counters, 0, 64 * sizeof(int)) != cudaSuccess) return EMU_ERR_CUDA;
+  }
+  // slices of <= kTopkSlice values, as many as keep the merge inside one slice buffer and fill the SMs across the groups
+  long parts = (n + kTopkSlice - 1) / kTopkSlice;
+  const long want = (2 * kNumSMs + groups - 1) / groups;
+  if (parts < want) parts = want;
+  if (parts > kTopkSlice / keep) parts = kTopkSlice / keep;
+  if (parts > kTopkMaxParts) parts = kTopkMaxParts;
+  if ((n + parts - 1) / parts > kTopkSlice) return walk();  // group too large for this kernel's slice buffer
+  topk_group_kernel<<<dim3((unsigned)parts, (unsigned)groups), kTopkThreads, 0, st>>>(x, n, keep, (int)parts, g_topk_cand,
+                                                                                     g_topk_counters, out_val, out_idx);
+  return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -480,8 +598,9 @@ extern "C" int emu_beam_topk(float* logits, const float* running_scores, int bat
     allowed_mask_kernel<<<2 * kNumSMs, 256, 0, st>>>(logits, allowed, (long)rows * vocab);
     ++nl;
   }
-  topk_group_kernel<<<batch, 1024, 0, st>>>(logits, (long)beams * vocab, keep, out_lp, out_idx);
+  const int rc = topk_groups(logits, batch, (long)beams * vocab, keep, out_lp, out_idx, st);
   count_launch(nl);
+  if (rc != EMU_OK) return rc;
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 

@@ -37,6 +37,16 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
 int conv3x3_bf16(const bf16* X_nhwc, int NB, int H, int W, int Cin, const bf16* Wk, int Cout, const GemmEpilogue& e,
                  cudaStream_t st);
 
+// ---- gemm_skinny.cu : tcgen05 GEMM with the WEIGHTS as the 128-row operand, activations B <= 32 rows (wide decode) ----
+// plain / +residual / EPI_SWIGLU epilogues, bf16 or fp32 output; K-split partial sums through `ws` (gemm_skinny_workspace_bytes())
+// and `counters` (kSkinnyMaxTiles ints, zeroed once).  EMU_ERR_UNSUPPORTED: shape / epilogue outside this kernel -> gemm_bf16.
+constexpr int kSkinnyMaxUnits = 1024;
+constexpr int kSkinnyMaxTiles = 4096;
+size_t gemm_skinny_workspace_bytes();
+int gemm_skinny_init();
+int gemm_skinny_bf16(const bf16* X, int ldx, const bf16* W, int ldw, int B, int N, int K, const GemmEpilogue& e, float* ws,
+                     int* counters, cudaStream_t st);
+
 // ---- gemv.cu : weight-streaming skinny GEMM for the decode loop (batch <= 8) ----
 struct GemvArgs {
   const bf16* W = nullptr;  // [N, K] row-major

@@ -164,6 +164,11 @@ int emu_vae_decode(EmuEngine* e, const void* latents_nchw /*bf16, already / scal
 int emu_op_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const void* bias,
                 const void* residual, int ldr, int epi_mode, void* C, int ldc, int out_fp32, int force_bn,
                 emu_stream_t s);
+/* C[B, N] = epilogue(X[B, K] . W[N, K]^T) for B <= 32 activation rows: the projection kernel of the decode step with more than
+   8 cache rows (num_beams x batch of `lm.generate`, Emu2/emu/emu.py:213-229).  epi_mode EPI_NONE (+ residual) or EPI_SWIGLU.
+   EMU_ERR_UNSUPPORTED for shapes / epilogues it does not take (use emu_op_gemm). */
+int emu_op_gemm_skinny(const void* X, int ldx, const void* W, int ldw, int B, int N, int K, const void* residual, int ldr,
+                       int epi_mode, void* C, int ldc, int out_fp32, emu_stream_t s);
 int emu_op_conv3x3(const void* x_nhwc, int NB, int H, int W, int Cin, const void* w_k /*[Cout, 9*Cin]*/, int Cout,
                    const void* bias, const void* residual, void* y_nhwc, emu_stream_t s);
 int emu_op_gemv(const void* W, int N, int K, const void* x, int ldx, int B, const void* norm_w, float eps,

@@ -303,7 +303,7 @@ def test_beam_reparent_table_equals_cache_copy(cuda, sd, gold):
             B = 2 * nb
             eng.llm_expand(torch.arange(B, dtype=torch.int32, device="cuda") // nb, B)
             gg = torch.Generator().manual_seed(17)
-            buf = torch.empty(B, TINY_LLAMA["vocab_size"], dtype=torch.float32, device="cuda")
+            buf = torch.empty(B, eng.cfg.llm_vocab, dtype=torch.float32, device="cuda")
             for step in range(4):
                 tok = torch.randint(100, 30000, (B,), generator=gg).to(torch.int32).cuda()
                 src = (torch.arange(B) // nb) * nb + torch.randint(0, nb, (B,), generator=gg)

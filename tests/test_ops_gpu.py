@@ -100,6 +100,38 @@ def test_gemm_epilogues(cuda):
                      bf(hb) * torch.nn.functional.gelu(bf(gb))) < TOL_BF16
 
 
+@pytest.mark.parametrize("B,N,K", [
+    (20, 6656, 2240), (5, 2688, 6656), (32, 4480, 1664), (1, 300, 72), (11, 768, 256), (20, 6656, 896), (13, 1000, 4104),
+])
+def test_gemm_skinny(cuda, B, N, K):
+    """The wide-decode projection kernel (weights as the 128-row MMA operand, K-split partial sums through the workspace):
+    plain fp32 / bf16, in-place residual (h = h + W a), SwiGLU with interleaved rows; TP-shard shapes of LLaMA-33B, ragged N / K,
+    1..32 activation rows.  Run twice: the split counters must reset themselves."""
+    from emu_b200 import _lib
+    X, W, r = _rand((B, K), 31), _rand((N, K), 32, 0.05), _rand((B, N), 33)
+    bf = lambda t: t.to(torch.bfloat16)
+    ref = O.op_linear(X, W)
+    Xc, Wc = X.cuda(), W.cuda()
+    for _ in range(2):
+        assert O.rel_err(_lib.op_gemm_skinny(Xc, Wc, out_fp32=True).cpu(), ref) < TOL_F32
+    assert O.rel_err(_lib.op_gemm_skinny(Xc, Wc).cpu(), ref) < TOL_BF16
+    want = bf(ref).float() + r.float()
+    assert O.rel_err(_lib.op_gemm_skinny(Xc, Wc, residual=r.cuda()).cpu(), want) < TOL_BF16
+    h = r.cuda().clone()
+    lib = _lib.load()
+    _lib.check(lib.emu_op_gemm_skinny(_lib._ptr(Xc), K, _lib._ptr(Wc), K, B, N, K, _lib._ptr(h), N, 0, _lib._ptr(h), N, 0,
+                                      _lib._stream()))
+    assert O.rel_err(h.cpu(), want) < TOL_BF16
+    if N % 2 == 0:
+        g, u = O.op_linear(X, W[0::2]), O.op_linear(X, W[1::2])
+        got = _lib.op_gemm_skinny(Xc, Wc, epi=_lib.EPI_SWIGLU).cpu()
+        assert O.rel_err(got, torch.nn.functional.silu(bf(g)) * bf(u)) < TOL_BF16
+    # same rounding points as the general GEMM: bf16 outputs agree to the last bit except where the fp32 sums differ by
+    # summation order right at a rounding boundary
+    a, b = _lib.op_gemm_skinny(Xc, Wc).float().cpu(), _lib.op_gemm(Xc, Wc).float().cpu()
+    assert O.rel_err(a, b) < 2e-3
+
+
 @pytest.mark.parametrize("NB,H,W,Cin,Cout", [(1, 16, 8, 64, 64), (2, 32, 32, 128, 320), (1, 64, 64, 8, 96),
                                               (1, 8, 128, 320, 32)])
 def test_conv3x3(cuda, NB, H, W, Cin, Cout):

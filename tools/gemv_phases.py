@@ -14,24 +14,27 @@ H, F = 6656, 17920
 
 def main():
     lib = _lib.load()
-    for tp in (1, 2, 8):
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 1       # batch rows (5 = the reference's default beam search)
+    tps = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 8]
+    print("batch rows = %d, EMU_GEMV_XBULK=%s" % (B, os.environ.get("EMU_GEMV_XBULK", "1")))
+    for tp in tps:
         Hl = (52 + tp - 1) // tp * 128
         Fl = F // tp
         shapes = [("qkv", 3 * Hl, H, True, 0), ("o", H, Hl, False, 0), ("gate_up", 2 * Fl, H, True, 2), ("down", H, Fl, False, 0)]
         layers = 6
         Ws = [[torch.randn(n, k, device="cuda", dtype=torch.bfloat16) * 0.02 for _, n, k, _, _ in shapes] for _ in range(layers)]
-        xh = torch.randn(1, H, device="cuda", dtype=torch.bfloat16)
-        xs = {H: xh, Hl: torch.randn(1, Hl, device="cuda", dtype=torch.bfloat16), Fl: torch.randn(1, Fl, device="cuda", dtype=torch.bfloat16)}
+        xh = torch.randn(B, H, device="cuda", dtype=torch.bfloat16)
+        xs = {H: xh, Hl: torch.randn(B, Hl, device="cuda", dtype=torch.bfloat16), Fl: torch.randn(B, Fl, device="cuda", dtype=torch.bfloat16)}
         nw = torch.ones(H, device="cuda", dtype=torch.bfloat16)
-        outs = {n: torch.empty(1, n, device="cuda", dtype=torch.bfloat16) for _, n, _, _, _ in shapes}
-        outs[Fl] = torch.empty(1, Fl, device="cuda", dtype=torch.bfloat16)
+        outs = {n: torch.empty(B, n, device="cuda", dtype=torch.bfloat16) for _, n, _, _, _ in shapes}
+        outs[Fl] = torch.empty(B, Fl, device="cuda", dtype=torch.bfloat16)
         stamps = [[torch.zeros(148, 8, dtype=torch.int64, device="cuda") for _ in shapes] for _ in range(layers)]
 
         def run():
             for l in range(layers):
                 for j, (name, n, k, norm, mode) in enumerate(shapes):
                     n_out = n // 2 if mode == 2 else n
-                    _lib.check(lib.emu_debug_gemv_phases(_lib._ptr(Ws[l][j]), n, k, _lib._ptr(xs[k]), k, 1,
+                    _lib.check(lib.emu_debug_gemv_phases(_lib._ptr(Ws[l][j]), n, k, _lib._ptr(xs[k]), k, B,
                                                          _lib._ptr(nw if norm else None), _lib.C.c_float(1e-6), mode, None, 0,
                                                          _lib._ptr(outs[n_out]), n_out, 1, _lib._ptr(stamps[l][j]),
                                                          _lib._stream()))
