@@ -195,12 +195,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           __threadfence();
           const float* base = p.ws + ((long)tile * p.splits * 32) * SKM + r;
 #pragma unroll
-          for (int b = 0; b < 32; ++b) {
-            if (b < B) {
-              float a = 0.f;
-              for (int s2 = 0; s2 < p.splits; ++s2) a += __ldcg(base + ((long)s2 * 32 + b) * SKM);  // split order: deterministic
-              f[b] = a;
-            }
+          for (int b = 0; b < 32; ++b) f[b] = 0.f;
+          for (int s2 = 0; s2 < p.splits; ++s2) {  // split order: deterministic.  All rows of one split are loaded before any
+            const float* src = base + (long)s2 * 32 * SKM;  // is added: one L2 round trip per split, not per value
+            float t[32];
+#pragma unroll
+            for (int b = 0; b < 32; ++b) t[b] = b < B ? __ldcg(src + b * SKM) : 0.f;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) f[b] += t[b];
           }
         }
         sk_named_bar(1, 128);  // s_last is rewritten by the next unit
@@ -221,13 +223,20 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           }
         }
       } else if (n < p.N) {
+        if (p.residual != nullptr) {  // all residual rows in flight before the first is consumed
+          float rs[32];
+#pragma unroll
+          for (int b = 0; b < 32; ++b)
+            rs[b] = b < B ? __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(p.residual) + (long)b * p.ldr + n) << 16)
+                          : 0.f;
+#pragma unroll
+          for (int b = 0; b < 32; ++b) f[b] = round_bf16(f[b]) + rs[b];
+        }
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
           if (b < B) {
-            float o = f[b];
-            if (p.residual != nullptr) o = round_bf16(o) + __bfloat162float(p.residual[(long)b * p.ldr + n]);
-            if (p.out_fp32) reinterpret_cast<float*>(p.C)[(long)b * p.ldc + n] = o;
-            else reinterpret_cast<bf16*>(p.C)[(long)b * p.ldc + n] = __float2bfloat16_rn(o);
+            if (p.out_fp32) reinterpret_cast<float*>(p.C)[(long)b * p.ldc + n] = f[b];
+            else reinterpret_cast<bf16*>(p.C)[(long)b * p.ldc + n] = __float2bfloat16_rn(f[b]);
           }
         }
       }
@@ -275,13 +284,17 @@ int gemm_skinny_bf16(const bf16* X, int ldx, const bf16* W, int ldw, int B, int 
   int best_s = 1;
   double best_cost = 1e30;
   const int max_s = (ws && counters) ? 16 : 1;
+  // every weight byte crosses HBM once: no split can beat tiles x k-blocks x 16 KB at ~3370 B/clk
+  const double hbm_floor = (double)p.tiles * p.num_kb * (SKM * SKK * 2) / 3370.0;
   for (int S = 1; S <= max_s; ++S) {
     const int kbs = (p.num_kb + S - 1) / S;
     if (S > 1 && (kbs < 4 || (long)p.tiles * S > kSkinnyMaxUnits || p.tiles > kSkinnyMaxTiles)) break;
     if ((S - 1) * kbs >= p.num_kb) continue;  // an empty last split
     const long units = (long)p.tiles * S;
-    const long waves = (units + kNumSMs - 1) / kNumSMs;
-    const double cost = (double)waves * ((double)kbs * 420.0 + (S > 1 ? 4000.0 : 2500.0));
+    const long per_sm = (units + kNumSMs - 1) / kNumSMs;  // units the busiest SM works through
+    double cost = (double)per_sm * ((double)kbs * 420.0 + 3000.0);
+    if (cost < hbm_floor) cost = hbm_floor;
+    if (S > 1) cost += 3000.0 + 700.0 * S;  // partial sums out, counter round trip, S loads back
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best_s = S;
