@@ -784,7 +784,7 @@ def run_c4(args):
         msk = mask_host.to("cuda", non_blocking=True)
         return model.generate_from_ids(ids, msk, image=img, num_beams=beams, max_new_tokens=new_tokens, min_len=new_tokens,
                                        length_penalty=-1).cpu()
-    for _ in range(max(1, args.warmup - 2)):
+    for _ in range(args.warmup):
         one_step()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -849,7 +849,7 @@ def run_c4(args):
             "gpu_launches": int(launches),
             "vit_ms": vit_ms, "prefill_ms": prefill_ms, "decode_ms": decode_ms, "decode_step_ms": step_ms,
             "tokens_sha1": hashlib.sha1(toks.to(torch.int64).numpy().tobytes()).hexdigest()[:16],
-            "roofline": {"bound": "hbm", "kernel": "wide decode step (tcgen05 GEMM with M = %d cache rows + split-KV attention)" % (batch * beams),
+            "roofline": {"bound": "hbm", "kernel": "wide decode step: gemm_skinny_kernel (tcgen05, weights as the 128-row operand, %d cache rows as N) + split-KV attn_decode_kernel through the beam row table" % (batch * beams),
                          "achieved": alg_bytes / (step_ms / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg_bytes / (step_ms / 1000.0) / 1e9 / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_step_per_gpu": alg_bytes, "traffic": None},
