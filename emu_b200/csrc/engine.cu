@@ -975,6 +975,27 @@ static int wide_gemm(EmuEngine* e, const bf16* X, int ldx, const bf16* W, int ld
   return gemm_bf16(X, ldx, W, ldw, B, N, K, ep, st);
 }
 
+// tensor-parallel tail of a row-parallel projection of the wide step: h += sum over ranks of X_r W_r^T.  With the peer-memory
+// exchange: fp32 partial -> one kernel that pushes it to every rank over NVLink, waits for the others and adds the fixed-order
+// sum to h (no NCCL launch; the partials meet in fp32 and are rounded once, as in the unsharded model).  Otherwise NCCL.
+static int wide_row_parallel(EmuEngine* e, const bf16* X, int ldx, const bf16* W, int ldw, int B, int Hd, int K, bf16* h,
+                             cudaStream_t st, int* nl) {
+  GemmEpilogue ep;
+  if (e->tp_p2p && !((long)B * Hd & 3)) {
+    ep.C = e->dec_part; ep.ldc = Hd; ep.out_fp32 = 1;
+    EMU_TRY(wide_gemm(e, X, ldx, W, ldw, B, Hd, K, ep, st));
+    EMU_TRY(tp_reduce_add(e, e->dec_part, h, (long)B * Hd, g_pdl_chain, st));
+    *nl += 1;
+    return EMU_OK;
+  }
+  ep.C = e->dec_tmp; ep.ldc = Hd;
+  EMU_TRY(wide_gemm(e, X, ldx, W, ldw, B, Hd, K, ep, st));
+  EMU_TRY(nccl_allreduce_bf16(e, e->dec_tmp, (size_t)B * Hd, st));
+  EMU_TRY(add_rows(h, e->dec_tmp, h, (long)B * Hd, st));
+  *nl += 2;
+  return EMU_OK;
+}
+
 static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const void* embeds, int B, float* logits,
                                  void* hidden, int32_t* next_ids, int ban_id, cudaStream_t st, int* n_launch) {
   const EmuConfig& c = e->cfg;
@@ -1010,11 +1031,7 @@ static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const v
       eo.C = h; eo.ldc = Hd; eo.residual = h; eo.ldr = Hd;
       EMU_TRY(wide_gemm(e, e->dec_attn, Hl * D, L.wo, Hl * D, B, Hd, Hl * D, eo, st));
     } else {
-      eo.C = e->dec_tmp; eo.ldc = Hd;
-      EMU_TRY(wide_gemm(e, e->dec_attn, Hl * D, L.wo, Hl * D, B, Hd, Hl * D, eo, st));
-      EMU_TRY(nccl_allreduce_bf16(e, e->dec_tmp, (size_t)B * Hd, st));
-      EMU_TRY(add_rows(h, e->dec_tmp, h, (long)B * Hd, st));
-      nl += 2;
+      EMU_TRY(wide_row_parallel(e, e->dec_attn, Hl * D, L.wo, Hl * D, B, Hd, Hl * D, h, st, &nl));
     }
     EMU_TRY(rmsnorm(h, L.ln2, xn, B, Hd, c.llm_rms_eps, 0, st));
     GemmEpilogue eg;
@@ -1025,11 +1042,7 @@ static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const v
       ed.C = h; ed.ldc = Hd; ed.residual = h; ed.ldr = Hd;
       EMU_TRY(wide_gemm(e, e->dec_act, Fl, L.wdown, Fl, B, Hd, Fl, ed, st));
     } else {
-      ed.C = e->dec_tmp; ed.ldc = Hd;
-      EMU_TRY(wide_gemm(e, e->dec_act, Fl, L.wdown, Fl, B, Hd, Fl, ed, st));
-      EMU_TRY(nccl_allreduce_bf16(e, e->dec_tmp, (size_t)B * Hd, st));
-      EMU_TRY(add_rows(h, e->dec_tmp, h, (long)B * Hd, st));
-      nl += 2;
+      EMU_TRY(wide_row_parallel(e, e->dec_act, Fl, L.wdown, Fl, B, Hd, Fl, h, st, &nl));
     }
     nl += 9;
   }
