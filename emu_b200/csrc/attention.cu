@@ -61,27 +61,53 @@ __global__ void __launch_bounds__(kDecThreads) attn_decode_kernel(
 #pragma unroll
   for (int i = 0; i < EPL; ++i) qreg[i] = qs[part * EPL + i];
   float lmax = -INFINITY;
-  for (int tb = t0 + warp * 4; tb < t1; tb += 16) {  // warp-uniform trip count (shuffles below need all lanes)
-    const int t = tb + tig;
-    float s = 0.f;
-    const bool ok = t < t1;
-    if (ok) {
-      const int row = ind ? __ldg(ind + t) : b;
-      const uint4* kr = reinterpret_cast<const uint4*>(kb + row * row_stride + (long)t * D + part * EPL);
+  // two token groups per trip: both K rows are requested before either is reduced (the long-context case has few CTAs per
+  // SM, so the bytes in flight have to come from each warp)
+  for (int tb = t0 + warp * 4; tb < t1; tb += 32) {  // warp-uniform trip count (shuffles below need all lanes)
+    const int ta = tb + tig, tc = tb + 16 + tig;
+    const bool oka = ta < t1, okc = tc < t1;
+    uint4 ka[VPL], kc[VPL];
+    if (oka) {
+      const int row = ind ? __ldg(ind + ta) : b;
+      const uint4* kr = reinterpret_cast<const uint4*>(kb + row * row_stride + (long)ta * D + part * EPL);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) ka[v] = ldg_stream(kr + v);
+    }
+    if (okc) {
+      const int row = ind ? __ldg(ind + tc) : b;
+      const uint4* kr = reinterpret_cast<const uint4*>(kb + row * row_stride + (long)tc * D + part * EPL);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) kc[v] = ldg_stream(kr + v);
+    }
+    float sa = 0.f, sc2 = 0.f;
+    if (oka) {
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
-        const uint4 kv = ldg_stream(kr + v);
-        const uint32_t k4[4] = {kv.x, kv.y, kv.z, kv.w};
+        const uint32_t k4[4] = {ka[v].x, ka[v].y, ka[v].z, ka[v].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          s += bf16_lo(k4[j]) * qreg[v * 8 + 2 * j] + bf16_hi(k4[j]) * qreg[v * 8 + 2 * j + 1];
+          sa += bf16_lo(k4[j]) * qreg[v * 8 + 2 * j] + bf16_hi(k4[j]) * qreg[v * 8 + 2 * j + 1];
       }
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (ok && part == 0) sc[t - t0] = s;
-    if (ok) lmax = fmaxf(lmax, s);
+    if (okc) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const uint32_t k4[4] = {kc[v].x, kc[v].y, kc[v].z, kc[v].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sc2 += bf16_lo(k4[j]) * qreg[v * 8 + 2 * j] + bf16_hi(k4[j]) * qreg[v * 8 + 2 * j + 1];
+      }
+    }
+    sa += __shfl_xor_sync(0xffffffffu, sa, 4);
+    sc2 += __shfl_xor_sync(0xffffffffu, sc2, 4);
+    sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+    sc2 += __shfl_xor_sync(0xffffffffu, sc2, 2);
+    sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+    sc2 += __shfl_xor_sync(0xffffffffu, sc2, 1);
+    if (oka && part == 0) sc[ta - t0] = sa;
+    if (okc && part == 0) sc[tc - t0] = sc2;
+    if (oka) lmax = fmaxf(lmax, sa);
+    if (okc) lmax = fmaxf(lmax, sc2);
   }
   lmax = warp_max(lmax);
   if (lane == 0) red[warp] = lmax;
@@ -101,6 +127,7 @@ __global__ void __launch_bounds__(kDecThreads) attn_decode_kernel(
   float acc[EPL];
 #pragma unroll
   for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
+#pragma unroll 4
   for (int t = t0 + tl; t < t1; t += 16) {
     const float p = sc[t - t0];
     const int row = ind ? __ldg(ind + t) : b;
@@ -167,6 +194,14 @@ int attn_decode(const bf16* q, const bf16* k_cache, const bf16* v_cache, int B, 
   int nsplit = (2 * kNumSMs + H * B - 1) / (H * B);
   const int by_len = (max_len_hint + 63) / 64;
   if (nsplit > by_len) nsplit = by_len;
+  {
+    // long contexts: aim for ~8 CTAs (32 warps) per SM so that enough loads are in flight, in splits of >= 512 tokens
+    // (4 prompts x 5 beams x 26 heads at 4k context was ONE split: 3.5 CTAs per SM, half the HBM rate)
+    int want = (8 * kNumSMs + H * B - 1) / (H * B);
+    const int cap = max_len_hint / 512;
+    if (want > cap) want = cap;
+    if (nsplit < want) nsplit = want;
+  }
   if (nsplit > 16) nsplit = 16;
   if (nsplit < 1) nsplit = 1;
   const int per = (max_len_hint + nsplit - 1) / nsplit + 8;

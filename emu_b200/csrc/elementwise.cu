@@ -197,7 +197,7 @@ int layernorm(const bf16* x, const bf16* w, const bf16* b, const bf16* residual,
 // ----------------------------------------------------------------------------------------------
 __global__ void rope_kv_write_kernel(bf16* qkv, int B, int N, int H, int D, const bf16* __restrict__ cos_t,
                                      const bf16* __restrict__ sin_t, const int* pos_off, int pos0, bf16* k_cache,
-                                     bf16* v_cache, int t_max, const int* __restrict__ pos_dev) {
+                                     bf16* v_cache, int t_max, const int* __restrict__ pos_dev, bf16* q_out) {
   const int half = D >> 1;
   if (pos_dev) pos0 = pos_dev[0];  // CUDA-graphed decode: the cache slot of the new token lives on the device
   const long total = (long)B * N * H * half;
@@ -214,7 +214,9 @@ __global__ void rope_kv_write_kernel(bf16* qkv, int B, int N, int H, int D, cons
     uint32_t* qp = reinterpret_cast<uint32_t*>(base + h * D + 2 * j);
     const uint32_t qv = *qp;
     const float q1 = bf16_lo(qv), q2 = bf16_hi(qv);
-    *qp = pack_bf16(round_bf16(q1 * c) + round_bf16(-q2 * s), round_bf16(q2 * c) + round_bf16(q1 * s));
+    // decode (N == 1) may want the rotated q compact [B, H*D] for the attention kernel instead of in place
+    uint32_t* qd = q_out ? reinterpret_cast<uint32_t*>(q_out + ((long)b * N + n) * H * D + h * D + 2 * j) : qp;
+    *qd = pack_bf16(round_bf16(q1 * c) + round_bf16(-q2 * s), round_bf16(q2 * c) + round_bf16(q1 * s));
     const uint32_t kv = *reinterpret_cast<const uint32_t*>(base + (H + h) * D + 2 * j);
     const float k1 = bf16_lo(kv), k2 = bf16_hi(kv);
     const long coff = (((long)b * H + h) * t_max + pos0 + n) * D + 2 * j;
@@ -225,10 +227,10 @@ __global__ void rope_kv_write_kernel(bf16* qkv, int B, int N, int H, int D, cons
 }
 
 int rope_kv_write(bf16* qkv, int B, int N, int H, int D, const bf16* cos_t, const bf16* sin_t, const int* pos_off,
-                  int pos0, bf16* k_cache, bf16* v_cache, int t_max, cudaStream_t st, const int* pos_dev) {
+                  int pos0, bf16* k_cache, bf16* v_cache, int t_max, cudaStream_t st, const int* pos_dev, bf16* q_out) {
   const long total = (long)B * N * H * (D / 2);
   const int grid = (int)((total + 255) / 256 < 4 * kNumSMs ? (total + 255) / 256 : 4 * kNumSMs);
-  rope_kv_write_kernel<<<grid, 256, 0, st>>>(qkv, B, N, H, D, cos_t, sin_t, pos_off, pos0, k_cache, v_cache, t_max, pos_dev);
+  rope_kv_write_kernel<<<grid, 256, 0, st>>>(qkv, B, N, H, D, cos_t, sin_t, pos_off, pos0, k_cache, v_cache, t_max, pos_dev, q_out);
   return cudaGetLastError() == cudaSuccess ? EMU_OK : EMU_ERR_CUDA;
 }
 

@@ -1020,10 +1020,8 @@ static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const v
     GemmEpilogue ep;
     ep.C = qkv; ep.ldc = 3 * Hl * D;
     EMU_TRY(wide_gemm(e, xn, Hd, L.wqkv, Hd, B, 3 * Hl * D, Hd, ep, st));
-    EMU_TRY(rope_kv_write(qkv, B, 1, Hl, D, e->rope_cos, e->rope_sin, e->d_posoff, 0, kc, vc, c.llm_max_seq, st, e->d_pos));
-    if (cudaMemcpy2DAsync(e->dec_q, (size_t)Hl * D * 2, qkv, (size_t)3 * Hl * D * 2, (size_t)Hl * D * 2, B,
-                          cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-      return e->fail(EMU_ERR_CUDA, "q gather failed");
+    EMU_TRY(rope_kv_write(qkv, B, 1, Hl, D, e->rope_cos, e->rope_sin, e->d_posoff, 0, kc, vc, c.llm_max_seq, st, e->d_pos,
+                          e->dec_q));
     EMU_TRY(attn_decode(e->dec_q, kc, vc, B, Hl, D, c.llm_max_seq, e->d_pos, e->d_start, scale, e->dec_attn, e->dec_attn_ws,
                         e->dec_counters, c.llm_max_seq, 0, st, e->kv_indir));
     GemmEpilogue eo;
@@ -1044,7 +1042,7 @@ static int decode_step_body_wide(EmuEngine* e, const int32_t* token_ids, const v
     } else {
       EMU_TRY(wide_row_parallel(e, e->dec_act, Fl, L.wdown, Fl, B, Hd, Fl, h, st, &nl));
     }
-    nl += 9;
+    nl += 8;
   }
   if (hidden) {
     EMU_TRY(rmsnorm(h, e->final_norm, (bf16*)hidden, B, Hd, c.llm_rms_eps, 0, st));

@@ -149,7 +149,8 @@ int layernorm(const bf16* x, const bf16* w, const bf16* b, const bf16* residual,
               cudaStream_t st);  // y = residual + LN(x)  (residual may be null)
 int rope_kv_write(bf16* qkv /*[B,N,3*H*D] pair-interleaved q,k*/, int B, int N, int H, int D, const bf16* cos,
                   const bf16* sin, const int* pos_off /*[B]*/, int pos0, bf16* k_cache, bf16* v_cache, int t_max,
-                  cudaStream_t st, const int* pos_dev = nullptr /*device slot of the new token (N == 1), overrides pos0*/);
+                  cudaStream_t st, const int* pos_dev = nullptr /*device slot of the new token (N == 1), overrides pos0*/,
+                  bf16* q_out = nullptr /*decode: the rotated q goes compact [B*N, H*D] here instead of in place*/);
 int embed_gather(const bf16* table, const int* ids, bf16* out, int n, int dim, cudaStream_t st);
 int argmax_rows(const float* logits, int rows, int cols, int* out_idx, cudaStream_t st);
 int vit_im2col(const bf16* img_nchw, bf16* out, int B, int C, int HW, int P, int Kpad, cudaStream_t st);
