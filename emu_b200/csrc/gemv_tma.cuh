@@ -153,6 +153,15 @@ static __device__ __forceinline__ void tma_produce(const CUtensorMap* tm, int cp
 // latency: loads are issued four deep per thread before anything is consumed (round 1 walked one 16-byte load at a time:
 // 4.2 k cycles without and 8.9 k with the RMSNorm for K = 6656, profiles/r02_gemv_phases_*.txt), and the norm weights —
 // which do not depend on the predecessor kernel — are fetched by the caller before griddepcontrol.wait (XPre).
+// LlamaRMSNorm on two packed bf16: w * bf16(x * rstd).  cvt.rn.bf16x2.f32 rounds both products in one instruction and
+// mul.rn.bf16x2 rounds the exact bf16 x bf16 product once — bit-identical to round_bf16(round_bf16(x * rstd) * w) in fp32.
+static __device__ __forceinline__ uint32_t rmsnorm_pair(uint32_t x2, float rstd, uint32_t w2) {
+  const float lo = __uint_as_float(x2 << 16) * rstd, hi = __uint_as_float(x2 & 0xffff0000u) * rstd;
+  uint32_t n2, o2;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(n2) : "f"(hi), "f"(lo));
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(o2) : "r"(n2), "r"(w2));
+  return o2;
+}
 struct XPre {
   uint4 w[4];  // this thread's norm-weight vectors of columns (threadIdx.x + 256 j) * 8, j < 4 (K <= 8192)
   bool have = false;
@@ -204,9 +213,7 @@ static __device__ __forceinline__ void tma_stage_x_seg(const GemvTmaParams& p, b
           const uint32_t v4[4] = {v[j].x, v[j].y, v[j].z, v[j].w}, w4[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
           uint32_t o4[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q)  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
-            o4[q] = pack_bf16(round_bf16(bf16_lo(v4[q]) * rstd) * bf16_lo(w4[q]),
-                              round_bf16(bf16_hi(v4[q]) * rstd) * bf16_hi(w4[q]));
+          for (int q = 0; q < 4; ++q) o4[q] = rmsnorm_pair(v4[q], rstd, w4[q]);  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
           o = make_uint4(o4[0], o4[1], o4[2], o4[3]);
         }
         dst[i] = o;
@@ -343,8 +350,7 @@ static __device__ __forceinline__ void tma_stage_x_bulk(const GemvTmaParams& p, 
         const uint32_t v4[4] = {v.x, v.y, v.z, v.w};
         uint32_t o4[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
-          o4[q] = pack_bf16(round_bf16(bf16_lo(v4[q]) * rstd) * bf16_lo(w4[q]), round_bf16(bf16_hi(v4[q]) * rstd) * bf16_hi(w4[q]));
+        for (int q = 0; q < 4; ++q) o4[q] = rmsnorm_pair(v4[q], rstd, w4[q]);  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
         row[i] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
       }
     }
@@ -358,8 +364,7 @@ static __device__ __forceinline__ void tma_stage_x_bulk(const GemvTmaParams& p, 
         const uint32_t v4[4] = {v.x, v.y, v.z, v.w};
         uint32_t o4[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          o4[q] = pack_bf16(round_bf16(bf16_lo(v4[q]) * rstd) * bf16_lo(w4[q]), round_bf16(bf16_hi(v4[q]) * rstd) * bf16_hi(w4[q]));
+        for (int q = 0; q < 4; ++q) o4[q] = rmsnorm_pair(v4[q], rstd, w4[q]);
         row[i] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
       }
     }
