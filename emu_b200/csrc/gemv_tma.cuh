@@ -343,15 +343,20 @@ static __device__ __forceinline__ void tma_stage_x_bulk(const GemvTmaParams& p, 
       if (i >= vec_per_row) break;
       const uint4 w = use_pre ? pre->w[j] : __ldg(wsrc + i);
       const uint32_t w4[4] = {w.x, w.y, w.z, w.w};
-      for (int b = 0; b < B; ++b) {
-        uint4* row = reinterpret_cast<uint4*>(xs + (long)b * p.ldxs);
-        const float rstd = s_rstd[b];
-        const uint4 v = row[i];
-        const uint32_t v4[4] = {v.x, v.y, v.z, v.w};
-        uint32_t o4[4];
+      uint4 v[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) o4[q] = rmsnorm_pair(v4[q], rstd, w4[q]);  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
-        row[i] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      for (int b = 0; b < 8; ++b)  // every row's vector is requested before the first is used
+        if (b < B) v[b] = reinterpret_cast<const uint4*>(xs + (long)b * p.ldxs)[i];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (b < B) {
+          const float rstd = s_rstd[b];
+          const uint32_t v4[4] = {v[b].x, v[b].y, v[b].z, v[b].w};
+          uint32_t o4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o4[q] = rmsnorm_pair(v4[q], rstd, w4[q]);  // HF: weight * (x.float() * rsqrt(var + eps)).to(bf16)
+          reinterpret_cast<uint4*>(xs + (long)b * p.ldxs)[i] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
       }
     }
     for (int i = (int)threadIdx.x + 1024; i < vec_per_row; i += 256) {  // K > 8192
