@@ -208,37 +208,43 @@ class EmuVisualGeneration:
                                      prompt_embeds, text_embeds, time_ids)
         return latents
 
-    # ---- Emu2/emu/diffusion.py:168-212 ----
+    # ---- boundary: Emu2/emu/diffusion.py:168-212 (same inputs, same two modes, same cache keys) ----
+    def _split_prompt(self, inputs, placeholder):
+        """interleaved [str | PIL.Image] -> (text with one placeholder per picture, stacked pictures or None, saw any text)"""
+        pieces, pictures, saw_text = [], [], False
+        for item in inputs:
+            if isinstance(item, str):
+                pieces.append(item)
+                saw_text = True
+            else:
+                pieces.append(placeholder)
+                pictures.append(self.transform(item, self.device_))
+        stacked = torch.stack(pictures).to(self.device_, torch.bfloat16) if pictures else None
+        return "".join(pieces), stacked, saw_text
+
+    def _unconditional(self, key, make):
+        """The classifier-free-guidance branch does not depend on the request: made once per mode, kept in
+        `negative_prompt` under the reference's keys ("[NULL_IMAGE]" for autoencoding, "" for generation)."""
+        if key not in self.negative_prompt:
+            self.negative_prompt[key] = make()
+        return self.negative_prompt[key]
+
     @torch.no_grad()
     def _prepare_and_encode_inputs(self, inputs, do_classifier_free_guidance=False,
                                    placeholder: str = DEFAULT_IMG_PLACEHOLDER):
-        has_image, has_text = False, False
-        text_prompt, image_prompt = "", []
-        for x in inputs:
-            if isinstance(x, str):
-                has_text = True
-                text_prompt += x
-            else:
-                has_image = True
-                text_prompt += placeholder
-                image_prompt.append(self.transform(x, self.device_))
-        image_prompt = torch.stack(image_prompt).to(self.device_, torch.bfloat16) if image_prompt else None
+        text, pictures, saw_text = self._split_prompt(inputs, placeholder)
         enc = self.multimodal_encoder
-        if has_image and not has_text:  # autoencoding mode: exactly one image
-            prompt = enc.encode_image(image=image_prompt)
-            if do_classifier_free_guidance:
-                key = "[NULL_IMAGE]"
-                if key not in self.negative_prompt:
-                    self.negative_prompt[key] = enc.encode_image(image=torch.zeros_like(image_prompt))
-                prompt = torch.cat([prompt, self.negative_prompt[key]], dim=0)
+        if pictures is not None and not saw_text:
+            # autoencoding mode (pictures only): the condition is the encoder's own image embedding
+            key, cond = "[NULL_IMAGE]", enc.encode_image(image=pictures)
+            make_uncond = lambda: enc.encode_image(image=torch.zeros_like(pictures))
         else:
-            prompt = enc.generate_image(text=[text_prompt], image=image_prompt)
-            if do_classifier_free_guidance:
-                key = ""
-                if key not in self.negative_prompt:
-                    self.negative_prompt[key] = enc.generate_image(text=[key])
-                prompt = torch.cat([prompt, self.negative_prompt[key]], dim=0)
-        return prompt
+            # generation mode: the decoder regresses the visual embeddings from the interleaved prompt
+            key, cond = "", enc.generate_image(text=[text], image=pictures)
+            make_uncond = lambda: enc.generate_image(text=[""])
+        if not do_classifier_free_guidance:
+            return cond
+        return torch.cat([cond, self._unconditional(key, make_uncond)], dim=0)
 
     # ---- Emu2/emu/diffusion.py:214-234 ----
     def decode_latents(self, latents: torch.Tensor) -> np.ndarray:

@@ -129,3 +129,47 @@ def test_chat_prompt_assembly_vs_live_reference():
         a, b = mine._prepare_chat_inputs(inp, is_grounding=grounding), ref._prepare_chat_inputs(inp, is_grounding=grounding)
         assert a[0] == b[0]
         assert (a[1] is None) == (b[1] is None) and (a[1] is None or torch.equal(a[1], b[1]))
+
+
+class _FakeEncoder:
+    """records what EmuVisualGeneration asks of its multimodal encoder (Emu2/emu/diffusion.py:168-212)"""
+
+    def __init__(self):
+        self.calls = []
+
+    def encode_image(self, image):
+        self.calls.append(("encode_image", tuple(image.shape), float(image.abs().sum())))
+        return torch.full((image.shape[0], 2, 3), 1.0 if float(image.abs().sum()) else -1.0)
+
+    def generate_image(self, text, image=None):
+        self.calls.append(("generate_image", list(text), None if image is None else tuple(image.shape)))
+        return torch.full((len(text), 2, 3), 2.0 if text[0] else -2.0)
+
+
+def _bare_visual_generation():
+    from emu_b200.emu2.diffusion import EmuVisualGeneration
+    g = EmuVisualGeneration.__new__(EmuVisualGeneration)   # host logic only: no engine behind it
+    g.multimodal_encoder, g.negative_prompt, g.device_ = _FakeEncoder(), {}, torch.device("cpu")
+    g.transform = lambda img, device=None: torch.ones(3, 4, 4) * img
+    return g
+
+
+def test_visual_generation_prompt_modes():
+    """The two modes of the reference's _prepare_and_encode_inputs: pictures only -> autoencoding (encode_image, negative =
+    the zero image, cached under "[NULL_IMAGE]"); anything with text -> generate_image on the concatenated text with one
+    placeholder per picture (negative = the empty prompt, cached under ""); [cond; uncond] order; no CFG -> cond only."""
+    g = _bare_visual_generation()
+    enc = g.multimodal_encoder
+    out = g._prepare_and_encode_inputs([5.0], True)           # a "picture" (the fake transform scales a ones tensor)
+    assert out.shape[0] == 2 and float(out[0, 0, 0]) == 1.0 and float(out[1, 0, 0]) == -1.0
+    assert [c[0] for c in enc.calls] == ["encode_image", "encode_image"] and enc.calls[1][2] == 0.0
+    g._prepare_and_encode_inputs([7.0], True)
+    assert len(enc.calls) == 3 and list(g.negative_prompt) == ["[NULL_IMAGE]"]      # the negative branch is cached
+    enc.calls.clear()
+    out = g._prepare_and_encode_inputs(["a cat ", 3.0, " on a mat", 4.0], True)
+    assert enc.calls[0] == ("generate_image", ["a cat [<IMG_PLH>] on a mat[<IMG_PLH>]"], (2, 3, 4, 4))
+    assert enc.calls[1] == ("generate_image", [""], None)
+    assert float(out[0, 0, 0]) == 2.0 and float(out[1, 0, 0]) == -2.0 and set(g.negative_prompt) == {"[NULL_IMAGE]", ""}
+    enc.calls.clear()
+    out = g._prepare_and_encode_inputs(["only text"], False)
+    assert out.shape[0] == 1 and enc.calls == [("generate_image", ["only text"], None)]
