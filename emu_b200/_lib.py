@@ -243,6 +243,7 @@ class Engine:
                                      _ptr(st.running_scores), _ptr(st.sequences), _ptr(st.beam_scores), _ptr(st.is_finished),
                                      _ptr(st.fin_len), _ptr(st.unsat), _ptr(st.done), _ptr(st.next_tokens), _ptr(st.beam_src),
                                      _stream()), self.h)
+        st.done_calls.add_(st.done)   # device-side count of the calls that ended with `done` set (see BeamState.result)
 
     # ---- Emu1 Causal-Former ----
     def cformer_forward(self, vit_tokens, n_queries, out_dim):
@@ -458,6 +459,7 @@ class BeamState:
         self.fin_len = torch.zeros(batch, beams, **i32)
         self.unsat = torch.ones(batch, **i32)
         self.done = torch.zeros(1, **i32)
+        self.done_calls = torch.zeros(1, **i32)
         self.next_tokens = torch.zeros(batch * beams, **i32)
         self.beam_src = torch.zeros(batch * beams, **i32)
 
@@ -468,9 +470,20 @@ class BeamState:
     def is_done(self):
         return bool(self.done.item())   # the only device->host synchronisation of the loop
 
-    def result(self, cur_len):
-        best = self.sequences[self.live(cur_len), :, 0, :]
-        gen_len = int(self.fin_len[:, 0].max())
+    def final_len(self, cur_len):
+        """The step count at which the search finished.  The host polls `done` only every few steps and the steps launched
+        in between are no-ops on this state — they do not flip the sequence planes either — so the plane that holds the
+        final hypotheses is the one of the step that SET `done`, not of the step at which the host noticed:
+        calls made = cur_len, of which done_calls ended with `done` set  =>  finished after cur_len + 1 - done_calls steps."""
+        late = int(self.done_calls.item())
+        return cur_len + 1 - late if late > 0 else cur_len
+
+    def result(self, cur_len, n=1):
+        """the n best finished hypotheses of every batch row, best first: [batch * n, longest of them] (HF
+        num_return_sequences; the reference's default and Emu1's num_captions=1 take n = 1)"""
+        cur_len = self.final_len(cur_len)
+        best = self.sequences[self.live(cur_len), :, :n, :].reshape(self.batch * n, self.max_length)
+        gen_len = int(self.fin_len[:, :n].max())
         return best[:, :gen_len].to(torch.int64)
 
 

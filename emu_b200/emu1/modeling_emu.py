@@ -112,14 +112,6 @@ class Emu:
     def generate(self, samples, do_sample=False, num_beams=5, max_new_tokens=50, min_length=1, top_p=0.9,
                  repetition_penalty=1.0, length_penalty=0.0, num_captions=1, temperature=1, penalty_alpha=None,
                  top_k=None, no_repeat_ngram_size=None, **kwargs):
-        # knobs the reference forwards to HF generate (modeling_emu.py:162-179) that this engine does not implement must not
-        # be accepted and silently dropped
-        if penalty_alpha is not None:
-            raise NotImplementedError("contrastive search (penalty_alpha) is not supported")
-        if num_captions != 1:
-            raise NotImplementedError("num_captions (num_return_sequences) > 1 is not supported")
-        if do_sample and num_beams > 1:
-            raise NotImplementedError("beam-sample (do_sample=True with num_beams > 1) is not supported: pass num_beams=1")
         prompt = samples["prompt"] if "prompt" in samples else self.prompt
         if isinstance(prompt, str):
             prompt = [prompt]
@@ -128,14 +120,15 @@ class Emu:
                                      num_beams=num_beams, max_new_tokens=max_new_tokens, min_length=min_length,
                                      top_p=top_p, repetition_penalty=repetition_penalty, length_penalty=length_penalty,
                                      temperature=temperature, top_k=top_k, no_repeat_ngram_size=no_repeat_ngram_size,
-                                     **kwargs)
+                                     penalty_alpha=penalty_alpha, num_return_sequences=num_captions, **kwargs)
         return self.decoder.tokenizer.batch_decode(out, skip_special_tokens=True)
 
     @torch.no_grad()
     def generate_from_ids(self, input_ids, attention_mask, image=None, image_token_id=32003, do_sample=False,
                           num_beams=5, max_new_tokens=50, min_length=1, top_p=0.9, repetition_penalty=1.0,
                           length_penalty=0.0, temperature=1, top_k=None, eos_token_id=None, pad_token_id=None,
-                          no_repeat_ngram_size=None, prefix_allowed_tokens_fn=None, **kwargs):
+                          no_repeat_ngram_size=None, prefix_allowed_tokens_fn=None, penalty_alpha=None,
+                          num_return_sequences=1, **kwargs):
         tok = self.decoder.tokenizer
         eos = eos_token_id if eos_token_id is not None else tok.eos_token_id
         pad = pad_token_id if pad_token_id is not None else tok.pad_token_id
@@ -144,18 +137,15 @@ class Emu:
         if image is not None:
             f = self.encode_image(image.to(torch.bfloat16))
             embeds[input_ids == image_token_id] = f.reshape(-1, f.shape[-1])
-        if do_sample:
-            return generation.sample_search(self.engine, embeds, attention_mask, max_new_tokens, eos, pad,
-                                            min_length=min_length, temperature=temperature, top_k=top_k, top_p=top_p)
-        constrained = bool(no_repeat_ngram_size) or prefix_allowed_tokens_fn is not None or repetition_penalty != 1.0
-        if num_beams == 1 and not constrained:
-            return generation.greedy_search(self.engine, embeds, attention_mask, max_new_tokens, eos, pad,
-                                            min_length=min_length)
-        # beam search with one beam IS greedy search with the logits processors applied
-        return generation.beam_search(self.engine, embeds, attention_mask, num_beams, max_new_tokens, eos, pad,
-                                      min_length=min_length, length_penalty=length_penalty,
-                                      repetition_penalty=repetition_penalty, no_repeat_ngram_size=no_repeat_ngram_size or 0,
-                                      prefix_allowed_tokens_fn=prefix_allowed_tokens_fn)
+        # every knob modeling_emu.py:162-179 forwards to lm.generate; num_captions arrives as num_return_sequences
+        return generation.generate(self.engine, embeds, attention_mask, max_new_tokens, eos, pad, do_sample=do_sample,
+                                   num_beams=num_beams, min_length=min_length, length_penalty=length_penalty,
+                                   repetition_penalty=repetition_penalty, penalty_alpha=penalty_alpha, top_k=top_k,
+                                   top_p=top_p, temperature=temperature, no_repeat_ngram_size=no_repeat_ngram_size or 0,
+                                   prefix_allowed_tokens_fn=prefix_allowed_tokens_fn,
+                                   num_return_sequences=num_return_sequences,
+                                   early_stopping=kwargs.get("early_stopping", False), generator=kwargs.get("generator"),
+                                   check_every=kwargs.get("check_every"))
 
     @torch.no_grad()
     def generate_image(self, text: List[str], image: Optional[torch.Tensor] = None,

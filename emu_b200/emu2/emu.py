@@ -175,10 +175,6 @@ class EmuModel:
         tok = self.decoder.tokenizer
         eos = eos_token_id if eos_token_id is not None else tok.eos_token_id
         pad = pad_token_id if pad_token_id is not None else tok.pad_token_id
-        if penalty_alpha is not None:
-            raise NotImplementedError("contrastive search (penalty_alpha) is not supported")
-        if do_sample and num_beams > 1:
-            raise NotImplementedError("beam-sample (do_sample=True with num_beams > 1) is not supported: pass num_beams=1")
         input_ids = input_ids.to(self.device_)
         attention_mask = attention_mask.to(self.device_)
         text_embeds = self.engine.llm_embed(input_ids)  # [B, N, H]
@@ -190,18 +186,17 @@ class EmuModel:
             e = self.encode_image(video, n_query=self.v_query)
             e = self._project_up(e.reshape(-1, e.shape[-1]))
             text_embeds[input_ids == video_token_id] = e
-        if do_sample:
-            return generation.sample_search(self.engine, text_embeds, attention_mask, max_new_tokens, eos, pad,
-                                            min_length=min_len, temperature=temperature, top_k=top_k, top_p=top_p)
-        if num_beams == 1:
-            if repetition_penalty != 1.0:
-                raise NotImplementedError("repetition_penalty with greedy search")
-            return generation.greedy_search(self.engine, text_embeds, attention_mask, max_new_tokens, eos, pad,
-                                            min_length=min_len, check_every=kwargs.get("check_every", 16))
-        return generation.beam_search(self.engine, text_embeds, attention_mask, num_beams, max_new_tokens, eos, pad,
-                                      min_length=min_len, length_penalty=length_penalty,
-                                      early_stopping=kwargs.get("early_stopping", False),
-                                      repetition_penalty=repetition_penalty)
+        # strategy selection as GenerationMixin does it from these knobs; the extra HF knobs the reference lets through its
+        # **kwargs (no_repeat_ngram_size, prefix_allowed_tokens_fn, num_return_sequences, early_stopping) are honoured too
+        return generation.generate(self.engine, text_embeds, attention_mask, max_new_tokens, eos, pad, do_sample=do_sample,
+                                   num_beams=num_beams, min_length=min_len, length_penalty=length_penalty,
+                                   repetition_penalty=repetition_penalty, penalty_alpha=penalty_alpha, top_k=top_k,
+                                   top_p=top_p, temperature=temperature,
+                                   no_repeat_ngram_size=kwargs.get("no_repeat_ngram_size", 0),
+                                   prefix_allowed_tokens_fn=kwargs.get("prefix_allowed_tokens_fn"),
+                                   num_return_sequences=kwargs.get("num_return_sequences", 1),
+                                   early_stopping=kwargs.get("early_stopping", False), generator=kwargs.get("generator"),
+                                   check_every=kwargs.get("check_every"))
 
     # ---- Emu2/emu/emu.py:92-153 ----
     @torch.no_grad()

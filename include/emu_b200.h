@@ -203,7 +203,9 @@ int emu_image_to_uint8(const float* image01, uint8_t* out, int64_t n, emu_stream
  *   log_softmax(logits) -> RepetitionPenaltyLogitsProcessor -> NoRepeatNGramLogitsProcessor -> MinLength EOS ban ->
  *   PrefixConstrainedLogitsProcessor -> + running beam score -> topk(2*beams) over the flattened [beams*vocab] scores of
  *   every batch row.
- * logits [batch*beams, vocab] fp32 is used as scratch (overwritten); running_scores [batch*beams] may be NULL;
+ * logits [batch*beams, vocab] fp32 is processed IN PLACE: on return it holds the processed log-probabilities + the row's running
+ * score (HF's accumulated_log_probs) — the sampling strategies rely on that (beam-sample draws its candidates from them,
+ * `_sample` with processors feeds them to emu_sample_tokens); keep <= 32.  running_scores [batch*beams] may be NULL;
  * prev_tokens: DEVICE int32 rows of the tokens generated so far, row r at prev_tokens + r*prev_stride, prev_len valid (may be
  * NULL); penalty_on_logits = 1 applies the repetition penalty to the raw logits (HF greedy / sampling) instead of the
  * log-probabilities (HF beam search); no_repeat_ngram = n-gram size (0 = off); allowed [batch*beams, vocab] bytes, 0 = banned

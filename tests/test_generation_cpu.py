@@ -63,13 +63,14 @@ class OracleEngine:
     def beam_topk(self, logits, running_scores, batch, beams, keep, ban_id=-1, prev_tokens=None, prev_len=0,
                   repetition_penalty=1.0, penalty_on_logits=False, no_repeat_ngram=0, allowed=None):
         return torch_beam_topk(logits, running_scores, batch, beams, keep, ban_id, prev_tokens, prev_len, repetition_penalty,
-                               penalty_on_logits, no_repeat_ngram, allowed)
+                               penalty_on_logits, no_repeat_ngram, allowed, write_back=True)
 
     def beam_state(self, batch, beams, max_length, pad_token_id, device):
         return TorchBeamState(batch, beams, max_length, pad_token_id)
 
     def beam_step(self, st, topk_lp, topk_idx, cur_len, eos_token_id, length_penalty, early_stopping):
         st.step(topk_lp, topk_idx, self.cfg.llm_vocab, cur_len, eos_token_id, length_penalty, early_stopping)
+        st.done_calls.add_(st.done)       # as emu_b200._lib.Engine.beam_step does after the device kernel
 
     def sample_tokens(self, logits, temperature=1.0, top_k=0, top_p=1.0, ban_id=-1, seed=0, offset=0):
         """HF warpers + torch.multinomial (what emu_sample_tokens implements on the device)"""
@@ -90,7 +91,7 @@ class OracleEngine:
 
 
 def torch_beam_topk(logits, running_scores, batch, beams, keep, ban_id=-1, prev_tokens=None, prev_len=0,
-                    repetition_penalty=1.0, penalty_on_logits=False, no_repeat_ngram=0, allowed=None):
+                    repetition_penalty=1.0, penalty_on_logits=False, no_repeat_ngram=0, allowed=None, write_back=False):
     """torch formulation of the HF `_beam_search` step that emu_beam_topk implements on the device (HF processor classes
     restated: RepetitionPenalty, NoRepeatNGram, MinLength, PrefixConstrained)."""
     V = logits.shape[-1]
@@ -119,6 +120,8 @@ def torch_beam_topk(logits, running_scores, batch, beams, keep, ban_id=-1, prev_
     if allowed is not None:
         lp = lp.masked_fill(allowed.to(lp.device) == 0, float("-inf"))
     lp = lp.view(batch, beams, V) + running_scores.view(batch, beams)[:, :, None]
+    if write_back:   # emu_beam_topk works in place: `logits` holds the processed, running-score-shifted log-probabilities
+        logits.copy_(lp.view(batch * beams, V))
     v, i = torch.topk(lp.view(batch, beams * V), k=keep)
     return v, i.to(torch.int32)
 
@@ -127,6 +130,9 @@ def _gather_beams(t, idx):
     while idx.dim() < t.dim():
         idx = idx.unsqueeze(-1)
     return torch.take_along_dim(t, idx, dim=1)
+
+
+from emu_b200._lib import BeamState as _BeamStateCls  # noqa: E402  (importing _lib does not load the library)
 
 
 class TorchBeamState:
@@ -146,6 +152,7 @@ class TorchBeamState:
         self.fin_len = torch.zeros(batch, beams, dtype=torch.int32)
         self.unsat = torch.ones(batch, dtype=torch.int32)
         self.done = torch.zeros(1, dtype=torch.int32)
+        self.done_calls = torch.zeros(1, dtype=torch.int32)
         self.next_tokens = torch.zeros(batch * beams, dtype=torch.int32)
         self.beam_src = torch.zeros(batch * beams, dtype=torch.int32)
 
@@ -155,9 +162,12 @@ class TorchBeamState:
     def is_done(self):
         return bool(self.done.item())
 
-    def result(self, cur_len):
-        best = self.sequences[self.live(cur_len), :, 0, :]
-        return best[:, :int(self.fin_len[:, 0].max())].to(torch.int64)
+    final_len = _BeamStateCls.final_len        # the product's own plane arithmetic (host code, device independent)
+
+    def result(self, cur_len, n=1):
+        cur_len = self.final_len(cur_len)
+        best = self.sequences[self.live(cur_len), :, :n, :].reshape(self.batch * n, self.max_length)
+        return best[:, :int(self.fin_len[:, :n].max())].to(torch.int64)
 
     def step(self, topk_lp, topk_i, V, cur_len, eos, length_penalty, early_stopping):
         if self.is_done():
@@ -245,3 +255,206 @@ def test_beam_batch_limit(setup):
     gold, sd, emb = setup
     with pytest.raises(ValueError):
         generation.beam_search(OracleEngine(sd, max_batch=4), emb, gold["gen_attention_mask"], 5, 4, 2, 32000)
+
+
+# ---- generation control beyond plain greedy / beam search: pinned to the reference's own lm.generate (golden ids made by
+# ---- tests/golden/gen_golden_control.py from the unmodified reference decoder on the same tiny model) -------------------
+CTRL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "emu2_tiny_control.pt")
+SMALL = [6554, 18722, 15312, 29412, 3895, 1741]
+ALLOWED = list(range(100, 140)) + [2]
+
+
+def small_fn(batch_id, ids):
+    return SMALL + ([2] if len(ids) >= 8 else [])
+
+
+def prefix_fn(batch_id, ids):
+    return [2] if len(ids) >= 3 else ALLOWED
+
+
+@pytest.fixture(scope="module")
+def ctrl():
+    return torch.load(CTRL)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("greedy_rep", dict(repetition_penalty=1.5)),
+    ("greedy_ngram2", dict(no_repeat_ngram_size=2)),
+    ("greedy_rep_ngram", dict(repetition_penalty=1.3, no_repeat_ngram_size=3)),
+    ("greedy_prefix", dict(prefix_allowed_tokens_fn=prefix_fn)),
+    ("greedy_small", dict(prefix_allowed_tokens_fn=small_fn)),
+    ("greedy_small_rep", dict(prefix_allowed_tokens_fn=small_fn, repetition_penalty=1.5)),
+    ("greedy_small_ngram2", dict(prefix_allowed_tokens_fn=small_fn, no_repeat_ngram_size=2))])
+def test_greedy_with_logits_processors_matches_reference_generate(setup, ctrl, name, kw):
+    """HF greedy applies the repetition penalty to the RAW logits, then the n-gram ban / prefix constraint, pads finished rows
+    and stops when all rows have finished — ids must equal the reference's for every combination (the 6-token `small_fn`
+    vocabulary forces repeats so that the processors change the outcome)."""
+    from emu_b200 import generation
+    gold, sd, emb = setup
+    toks = generation.greedy_search(OracleEngine(sd), emb, gold["gen_attention_mask"], 12, 2, 32000, min_length=1,
+                                    check_every=4, **kw)
+    assert torch.equal(toks, ctrl[name]), (toks.tolist(), ctrl[name].tolist())
+
+
+def test_processors_change_the_outcome(ctrl):
+    """guards the fixture itself: the repeat-forcing cases must differ from their unprocessed twins"""
+    assert not torch.equal(ctrl["greedy_small"], ctrl["greedy_small_rep"])
+    assert ctrl["greedy_small"].shape != ctrl["greedy_small_ngram2"].shape
+    assert ctrl["beam3_small"].shape != ctrl["beam3_small_rep_ngram"].shape
+
+
+@pytest.mark.parametrize("name,nb,kw", [
+    ("beam3_rep_ngram", 3, dict(length_penalty=1.0, repetition_penalty=1.4, no_repeat_ngram_size=2)),
+    ("beam3_prefix", 3, dict(length_penalty=0.0, prefix_allowed_tokens_fn=prefix_fn)),
+    ("beam3_small", 3, dict(length_penalty=1.0, prefix_allowed_tokens_fn=small_fn)),
+    ("beam3_small_rep_ngram", 3, dict(length_penalty=1.0, prefix_allowed_tokens_fn=small_fn, repetition_penalty=1.4,
+                                      no_repeat_ngram_size=2)),
+    ("beam4_ret3", 4, dict(length_penalty=-1, num_return_sequences=3))])
+def test_beam_search_control_matches_reference_generate(setup, ctrl, name, nb, kw):
+    """beam search with the processors on the log-probabilities (HF `_beam_search` order), a prefix constraint, and
+    num_return_sequences = 3 (the n best hypotheses of every prompt, best first, [B * n, T])"""
+    from emu_b200 import generation
+    gold, sd, emb = setup
+    toks = generation.beam_search(OracleEngine(sd, max_batch=8), emb, gold["gen_attention_mask"], nb, 12, 2, 32000,
+                                  min_length=1, **kw)
+    assert torch.equal(toks, ctrl[name]), (toks.tolist(), ctrl[name].tolist())
+
+
+@pytest.mark.parametrize("name,B,nb,seed,kw", [
+    ("beamsample3", 2, 3, 77, dict(temperature=0.8, top_p=0.9, length_penalty=1.0)),
+    ("beamsample2_topk", 1, 2, 5, dict(top_k=8, length_penalty=-1))])
+def test_beam_sample_matches_reference_generate(setup, ctrl, name, B, nb, seed, kw):
+    """do_sample with num_beams > 1 (what the chat demo runs with its defaults when do_sample is ticked,
+    Emu2/demo/backend/pytorch_model/backend.py:196-214): processors -> warpers -> + running score -> 2*beams candidates drawn
+    without replacement.  On the CPU the draws come from the same torch generator stream as HF's, so with the same seed the
+    ids are the reference's, token for token."""
+    from emu_b200 import generation
+    gold, sd, emb = setup
+    torch.manual_seed(seed)
+    toks = generation.beam_search(OracleEngine(sd), emb[:B], gold["gen_attention_mask"][:B], nb, 12, 2, 32000, min_length=1,
+                                  do_sample=True, **kw)
+    assert torch.equal(toks, ctrl[name]), (toks.tolist(), ctrl[name].tolist())
+
+
+def test_beam_sample_rejects_top_k_below_two_beams(setup):
+    from emu_b200 import generation
+    gold, sd, emb = setup
+    with pytest.raises(ValueError):
+        generation.beam_search(OracleEngine(sd), emb[:1], gold["gen_attention_mask"][:1], 5, 4, 2, 32000, do_sample=True,
+                               top_k=3)
+
+
+@pytest.mark.parametrize("check_every", [1, 3, 5, 8, 0])
+def test_beam_search_result_does_not_depend_on_when_the_host_looks(setup, ctrl, check_every):
+    """The search below finishes after 9 of 12 steps.  The host polls `done` every `check_every` steps; the steps launched
+    after the search has finished are no-ops on the beam state and must not change which sequence plane is read back
+    (regression: an odd number of such steps used to return the hypotheses of the step BEFORE the last one)."""
+    from emu_b200 import generation
+    gold, sd, emb = setup
+    toks = generation.beam_search(OracleEngine(sd, max_batch=8), emb, gold["gen_attention_mask"], 3, 12, 2, 32000,
+                                  min_length=1, length_penalty=1.0, prefix_allowed_tokens_fn=small_fn,
+                                  repetition_penalty=1.4, no_repeat_ngram_size=2, check_every=check_every)
+    assert torch.equal(toks, ctrl["beam3_small_rep_ngram"])
+
+
+def test_sampling_with_processors_and_return_sequences(setup):
+    """do_sample with num_beams = 1: the processors run before the warpers (HF `_sample`), and num_return_sequences = n
+    yields n continuations per prompt from ONE prefill ([B * n, T], prompt-major like HF's expanded batch)."""
+    from emu_b200 import generation
+    gold, sd, emb = setup
+    g = torch.Generator().manual_seed(11)
+    toks = generation.sample_search(OracleEngine(sd, max_batch=8), emb, gold["gen_attention_mask"], 10, 2, 32000, min_length=10,
+                                    temperature=0.9, top_k=4, generator=g, prefix_allowed_tokens_fn=small_fn,
+                                    no_repeat_ngram_size=2, num_return_sequences=3)
+    assert toks.shape == (6, 10)
+    assert set(toks.flatten().tolist()) <= set(SMALL)                    # the prefix constraint held at every step
+    for row in toks.tolist():                                            # ... and no bigram occurs twice
+        grams = list(zip(row, row[1:]))
+        assert len(grams) == len(set(grams))
+    assert len({tuple(r) for r in toks[:3].tolist()}) > 1                # the n continuations of one prompt are different draws
+    with pytest.raises(ValueError):
+        generation.sample_search(OracleEngine(sd, max_batch=4), emb, gold["gen_attention_mask"], 4, 2, 32000,
+                                 num_return_sequences=3)
+
+
+def _literal_contrastive(sd, emb, mask, max_new, k, alpha, eos, pad, min_length):
+    """transformers 4.31 `contrastive_search` + `_ranking_fast` restated WITHOUT a cache (every candidate is a full forward of
+    prompt + generated + candidate), pads excluded from the similarity — the checker for generation.contrastive_search."""
+    B = emb.shape[0]
+    E = sd["decoder.lm.model.embed_tokens.weight"]
+
+    def fwd(e, m):
+        return O.llama_forward(sd, e, m, layers=L, heads=NH, position_ids=O.hf_position_ids(m))
+    seq, m = emb.clone(), mask.clone()
+    h = fwd(seq, m)
+    ctx, logits = h.float(), O.lm_logits(sd, h[:, -1]).float()
+    out, unfinished = [], torch.ones(B, dtype=torch.long)
+    for step in range(max_new):
+        if step < min_length:
+            logits[:, eos] = float("-inf")
+        top_p, top_ids = torch.topk(torch.softmax(logits, -1), k)
+        m1 = torch.cat((m, torch.ones(B, 1, dtype=m.dtype)), 1)
+        nh, nl = [], []
+        for j in range(k):
+            hh = fwd(torch.cat((seq, F.embedding(top_ids[:, j], E).unsqueeze(1)), 1), m1)
+            nh.append(hh[:, -1].float())
+            nl.append(O.lm_logits(sd, hh[:, -1]).float())
+        nh, nl = torch.stack(nh, 1), torch.stack(nl, 1)                                   # [B, k, H], [B, k, V]
+        cos = torch.matmul(nh / nh.norm(dim=2, keepdim=True), (ctx / ctx.norm(dim=2, keepdim=True)).transpose(1, 2))
+        cos = cos.masked_fill(m[:, None, :] == 0, float("-inf"))
+        sel = ((1.0 - alpha) * top_p - alpha * cos.max(-1)[0]).argmax(-1)
+        r = torch.arange(B)
+        nxt = top_ids[r, sel] * unfinished + pad * (1 - unfinished)
+        out.append(nxt)
+        seq = torch.cat((seq, F.embedding(top_ids[r, sel], E).unsqueeze(1)), 1)
+        ctx, logits, m = torch.cat((ctx, nh[r, sel][:, None]), 1), nl[r, sel], m1
+        unfinished = unfinished * (nxt != eos).long()
+        if int(unfinished.max()) == 0:
+            break
+    return torch.stack(out, 1)
+
+
+@pytest.mark.parametrize("k,alpha", [(4, 0.6), (2, 0.3)])
+def test_contrastive_search_matches_literal_restatement(setup, k, alpha):
+    """penalty_alpha + top_k with one beam: the engine form (candidates as cache rows, expand -> one decode step -> collapse)
+    against the cache-less literal algorithm.  PARITY UNPINNED for this strategy: transformers 5.5 (installed) no longer ships
+    contrastive search, so the reference itself cannot produce a golden here."""
+    from emu_b200 import generation
+    gold, sd, emb = setup
+    mask = gold["gen_attention_mask"]
+    want = _literal_contrastive(sd, emb, mask, 8, k, alpha, 2, 32000, 1)
+    got = generation.contrastive_search(OracleEngine(sd, max_batch=8), emb, mask, 8, 2, 32000, top_k=k, penalty_alpha=alpha,
+                                        min_length=1, check_every=4)
+    assert torch.equal(got, want), (got.tolist(), want.tolist())
+    plain = generation.greedy_search(OracleEngine(sd), emb, mask, 8, 2, 32000, min_length=1)
+    assert not torch.equal(got, plain) or alpha < 0.5          # the degeneration penalty does steer the search
+    with pytest.raises(ValueError):
+        generation.contrastive_search(OracleEngine(sd, max_batch=4), emb, mask, 4, 2, 32000, top_k=4, penalty_alpha=0.6)
+
+
+def test_generate_dispatch_follows_generation_mixin(setup, ctrl):
+    """generation.generate picks the strategy from (do_sample, num_beams, penalty_alpha, top_k) like GenerationMixin 4.31 and
+    forwards every knob; checked on cases whose ids are pinned to the reference above."""
+    from emu_b200 import generation
+    gold, sd, emb = setup
+    mask = gold["gen_attention_mask"]
+    common = dict(max_new_tokens=12, eos_token_id=2, pad_token_id=32000, min_length=1)
+    eng = lambda: OracleEngine(sd, max_batch=8)
+    assert torch.equal(generation.generate(eng(), emb, mask, num_beams=1, **common), gold["gen_ids_greedy"])
+    assert torch.equal(generation.generate(eng(), emb[:1], mask[:1], num_beams=5, length_penalty=-1, **common),
+                       gold["gen_ids_beam5"])
+    assert torch.equal(generation.generate(eng(), emb, mask, num_beams=1, repetition_penalty=1.5,
+                                           prefix_allowed_tokens_fn=small_fn, **common), ctrl["greedy_small_rep"])
+    assert torch.equal(generation.generate(eng(), emb, mask, num_beams=4, length_penalty=-1, num_return_sequences=3,
+                                           **common), ctrl["beam4_ret3"])
+    torch.manual_seed(77)
+    assert torch.equal(generation.generate(eng(), emb, mask, num_beams=3, do_sample=True, temperature=0.8, top_p=0.9,
+                                           **common), ctrl["beamsample3"])
+    # penalty_alpha alone (top_k unset) is NOT contrastive search in HF: greedy
+    assert torch.equal(generation.generate(eng(), emb, mask, num_beams=1, penalty_alpha=0.6, **common), gold["gen_ids_greedy"])
+    c = generation.generate(eng(), emb, mask, num_beams=1, penalty_alpha=0.6, top_k=4, **common)
+    assert torch.equal(c, generation.contrastive_search(eng(), emb, mask, 12, 2, 32000, top_k=4, penalty_alpha=0.6, min_length=1))
+    with pytest.raises(ValueError):
+        generation.generate(eng(), emb, mask, num_beams=1, num_return_sequences=2, **common)
+    with pytest.raises(ValueError):
+        generation.generate(eng(), emb, mask, num_beams=2, num_return_sequences=3, **common)
