@@ -224,10 +224,9 @@ def beam_search(engine, inputs_embeds, attention_mask, num_beams, max_new_tokens
         raise ValueError("batch x num_beams = %d exceeds the engine's llm_max_batch = %d" % (Bt * nb, engine.cfg.llm_max_batch))
     V = engine.cfg.llm_vocab
     keep = 2 * nb
-    if do_sample and top_k and max(int(top_k), 2) < keep:
-        # the first step draws 2*beams DISTINCT candidates from the single live beam; top_k leaves it fewer than that
-        # (torch.multinomial refuses the same call inside HF: "not enough non-negative category to sample")
-        raise ValueError("beam-sample needs top_k >= 2 * num_beams (= %d) or top_k unset; got top_k = %d" % (keep, top_k))
+    # (do_sample with top_k < 2 * num_beams — the chat demo's defaults, top_k = 3 with 5 beams — leaves the first step fewer
+    # live candidates than the 2 * num_beams it draws: torch.multinomial then returns zero-probability entries, whose
+    # accumulated score is -inf; those beams are dead from the start, exactly as in HF)
     max_length = max_new_tokens
     # HF expands the inputs to batch x beams and prefills num_beams identical copies of every prompt; here each prompt is
     # prefilled ONCE and its cache row is then mapped to num_beams rows (same cache contents, 1 / num_beams of the work)

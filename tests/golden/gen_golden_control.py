@@ -49,6 +49,9 @@ CASES = {
     "beam3_prefix": dict(B=2, kw=dict(num_beams=3, length_penalty=0.0, prefix_allowed_tokens_fn=prefix_fn)),
     "beamsample3": dict(B=2, seed=77, kw=dict(num_beams=3, do_sample=True, temperature=0.8, top_p=0.9, length_penalty=1.0)),
     "beamsample2_topk": dict(B=1, seed=5, kw=dict(num_beams=2, do_sample=True, top_k=8, length_penalty=-1)),
+    # Emu2/demo/frontend/libs/chat_frontend.py:178-184 defaults with "Do Sample" ticked
+    "beamsample5_demo": dict(B=1, seed=9, kw=dict(num_beams=5, do_sample=True, top_k=3, top_p=0.9, temperature=0.7,
+                                                  length_penalty=1.0)),
 }
 
 
