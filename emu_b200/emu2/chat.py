@@ -55,6 +55,43 @@ class EmuChatGeneration:
 
     __call__ = forward
 
+    @torch.no_grad()
+    def forward_batch(self, batch_inputs, is_grounding: bool = False, num_beams: int = 5, max_new_tokens: int = 10,
+                      min_len: int = 1, do_sample: bool = False, penalty_alpha: Optional[float] = None,
+                      top_p: Optional[float] = None, top_k: Optional[int] = None, temperature: Optional[float] = None,
+                      length_penalty: float = -1, repetition_penalty: float = 1.0, skip_special_tokens: bool = True,
+                      **kwargs):
+        """`forward` for several independent requests with the same decoding knobs in ONE generate call (the serving shell's
+        batch, emu_b200/serve.py): the prompts are left-padded to the longest (EmuModel.generate does that for a list of
+        texts, Emu2/emu/emu.py:189), the pictures of all requests are concatenated in request order — which is the order in
+        which the spliced <image> slots are filled (emu.py:199-203).  Returns one string per request."""
+        assert isinstance(batch_inputs, list) and batch_inputs, "batch_inputs must be a non-empty list of `inputs` lists"
+        device, dtype = self.emu_model.device(), self.emu_model.dtype()
+        texts, images, videos = [], [], []
+        for inputs in batch_inputs:
+            assert isinstance(inputs, list), "inputs must be a list"
+            if isinstance(inputs[0], list):
+                assert len(inputs) % 2 == 1, "last message must be user input"
+                text, image, video, iph, vph = self._prepare_chat_inputs(inputs, is_grounding, device, dtype)
+            else:
+                text, image, video, iph, vph = self._prepare_inputs(inputs, device, dtype)
+            texts += text
+            if image is not None:
+                images.append(image)
+            if video is not None:
+                videos.append(video)
+        return self.emu_model.generate(
+            text=texts, image=torch.cat(images) if images else None, video=torch.cat(videos) if videos else None,
+            image_placeholder=iph, video_placeholder=vph, num_beams=num_beams, max_new_tokens=max_new_tokens,
+            min_len=min_len, do_sample=do_sample, penalty_alpha=penalty_alpha, top_p=top_p, top_k=top_k,
+            temperature=temperature, length_penalty=length_penalty, repetition_penalty=repetition_penalty,
+            skip_special_tokens=skip_special_tokens, **kwargs)
+
+    def max_requests_per_batch(self, num_beams: int = 5) -> int:
+        """how many requests one generate call can hold: every request takes num_beams KV-cache rows"""
+        rows = int(self.emu_model.engine.cfg.llm_max_batch)
+        return max(1, rows // max(1, int(num_beams)))
+
     # ---- prompt assembly (behaviour of Emu2/emu/chat.py:121-195, pinned by tests/test_host_cpu.py against the live
     #      reference).  A message is a flat list of strings and PIL images; "[VIDEO]" ... "[/VIDEO]" brackets frames. ----
     @staticmethod

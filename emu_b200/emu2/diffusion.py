@@ -186,6 +186,31 @@ class EmuVisualGeneration:
     __call__ = forward
 
     @torch.no_grad()
+    def forward_batch(self, batch_inputs, height: int = 1024, width: int = 1024, num_inference_steps: int = 50,
+                      guidance_scale: float = 3., crop_info: List[int] = [0, 0], original_size: List[int] = [1024, 1024],
+                      generator: Optional[torch.Generator] = None):
+        """`forward` for several independent requests with the same sampler settings through ONE denoising loop (the serving
+        shell's batch; BASELINE configs[4] is this with 32 prompts): every request is encoded as in `forward`, the conditional
+        rows are stacked in front of the unconditional ones ([cond_1..cond_n; uncond_1..uncond_n], the layout `denoise` and
+        emu_denoise_step take), one latent per request.  Returns one EmuVisualGenerationPipelineOutput per request."""
+        assert isinstance(batch_inputs, list) and batch_inputs, "batch_inputs must be a non-empty list of `inputs` lists"
+        do_cfg = guidance_scale > 1.0
+        cond, uncond = [], []
+        for inputs in batch_inputs:
+            e = self._prepare_and_encode_inputs(inputs if isinstance(inputs, list) else [inputs], do_cfg)
+            cond.append(e[:1])
+            if do_cfg:
+                uncond.append(e[1:2])
+        prompt_embeds = torch.cat(cond + uncond, dim=0).to(torch.bfloat16).contiguous()
+        latents = self.denoise(prompt_embeds, len(batch_inputs), height, width, num_inference_steps, guidance_scale,
+                               crop_info, original_size, generator=generator)
+        u8 = self.decode_latents_uint8(latents)
+        u8, flags = self.run_safety_checker(u8)
+        return [EmuVisualGenerationPipelineOutput(image=Image.fromarray(u8[i]),
+                                                  nsfw_content_detected=None if flags is None else flags[i])
+                for i in range(len(batch_inputs))]
+
+    @torch.no_grad()
     def denoise(self, prompt_embeds, batch_size, height=1024, width=1024, num_inference_steps=50, guidance_scale=3.,
                 crop_info=(0, 0), original_size=(1024, 1024), generator=None, latents=None):
         """Steps 2-4 of the reference forward (time ids, pooled text embedding, timesteps, latents, denoise loop)."""

@@ -173,3 +173,49 @@ def test_visual_generation_prompt_modes():
     enc.calls.clear()
     out = g._prepare_and_encode_inputs(["only text"], False)
     assert out.shape[0] == 1 and enc.calls == [("generate_image", ["only text"], None)]
+
+
+def test_chat_forward_batch_builds_one_generate_call():
+    """several requests, one EmuModel.generate: texts in request order, pictures concatenated in request order (the order in
+    which the <image> slots are filled), one answer per request — each text equal to what `forward` would have sent alone"""
+    from PIL import Image
+    from emu_b200.emu2.chat import EmuChatGeneration
+    fm = _FakeModel()
+    fm.generate = lambda **kw: (fm.calls.append(kw), ["answer %d" % i for i in range(len(kw["text"]))])[1]
+    fm.engine = type("E", (), {"cfg": type("C", (), {"llm_max_batch": 20})()})()
+    pipe = EmuChatGeneration(fm)
+    a, b = Image.new("RGB", (30, 20), (255, 0, 0)), Image.new("RGB", (20, 30), (0, 0, 255))
+    reqs = [[a, "describe"], ["no picture here"], [["hi", b], ["hello"], ["and?"]]]
+    out = pipe.forward_batch(reqs, num_beams=3, max_new_tokens=7)
+    assert out == ["answer 0", "answer 1", "answer 2"]
+    kw = fm.calls[-1]
+    assert kw["num_beams"] == 3 and kw["max_new_tokens"] == 7 and kw["length_penalty"] == -1
+    assert kw["image"].shape == (2, 3, 448, 448) and kw["video"] is None
+    singles = []
+    for r in reqs:
+        pipe.forward(r)
+        singles.append(fm.calls[-1])
+    assert kw["text"] == [s["text"][0] for s in singles]
+    assert torch.equal(kw["image"], torch.cat([s["image"] for s in singles if s["image"] is not None]))
+    assert pipe.max_requests_per_batch(5) == 4 and pipe.max_requests_per_batch(1) == 20 and pipe.max_requests_per_batch(32) == 1
+
+
+def test_visual_generation_forward_batch_layout():
+    """n requests through one denoise loop: prompt rows [cond_1..cond_n; uncond_1..uncond_n] (the layout emu_denoise_step
+    takes), batch_size n, one output per request; without CFG only the cond rows"""
+    import numpy as np
+    g = _bare_visual_generation()
+    seen = {}
+
+    def denoise(prompt_embeds, batch_size, *a, **k):
+        seen["embeds"], seen["n"] = prompt_embeds.float(), batch_size
+        return torch.zeros(batch_size, 4, 2, 2)
+    g.denoise = denoise
+    g.decode_latents_uint8 = lambda lat: np.stack([np.full((4, 4, 3), 10 * i, dtype=np.uint8) for i in range(lat.shape[0])])
+    g.safety_checker, g._warned_unfiltered = None, True
+    outs = g.forward_batch([["a cat"], [5.0], ["a dog ", 2.0]], guidance_scale=3.0)
+    assert seen["n"] == 3 and seen["embeds"].shape[0] == 6
+    assert seen["embeds"][:, 0, 0].tolist() == [2.0, 1.0, 2.0, -2.0, -1.0, -2.0]   # generation / autoencoding / generation
+    assert [o.image.getpixel((0, 0))[0] for o in outs] == [0, 10, 20] and all(o.nsfw_content_detected is None for o in outs)
+    g.forward_batch([["a cat"], ["a dog"]], guidance_scale=1.0)
+    assert seen["n"] == 2 and seen["embeds"][:, 0, 0].tolist() == [2.0, 2.0]
