@@ -452,3 +452,73 @@ def test_generate_dispatch_follows_generation_mixin(setup, ctrl):
         generation.generate(eng(), emb, mask, num_beams=1, num_return_sequences=2, **common)
     with pytest.raises(ValueError):
         generation.generate(eng(), emb, mask, num_beams=2, num_return_sequences=3, **common)
+
+
+# ---- BASELINE configs[0] in miniature: Emu1 image -> text (Emu1/inference.py:66-80 -> Emu.generate) ------------------------
+class Emu1OracleEngine(OracleEngine):
+    """OracleEngine + the Emu1 image path (pre-norm EVA ViT -> ln_visual, Causal-Former), same surface as _lib.Engine"""
+
+    def __init__(self, sd, vis, max_batch=8):
+        super().__init__(sd, max_batch)
+        self.vis = vis
+        self.cfg.llm_vocab = sd["decoder.lm.lm_head.weight"].shape[0]
+
+    def vit_forward(self, image, n_query, pool=True):
+        v, dt = self.vis, self.sd["ln_visual.weight"].dtype
+        feats = O.vit_forward_features(self.sd, image.to(dt), patch=v["patch_size"], num_heads=v["width"] // v["head_width"],
+                                       layers=v["layers"], postnorm=False)
+        return F.layer_norm(feats, (v["width"],), self.sd["ln_visual.weight"], self.sd["ln_visual.bias"], 1e-6)
+
+    def cformer_forward(self, feats, n_queries, out_dim):
+        from helpers import emu1_t5_cfg
+        from oracle import t5_oracle as T
+        return T.causal_former(self.sd, feats, emu1_t5_cfg())
+
+    def llm_embed(self, ids):
+        return F.embedding(ids.long(), self.sd["decoder.lm.model.embed_tokens.weight"])
+
+
+def _emu1_model(dtype):
+    from types import SimpleNamespace as NS
+    from helpers import EMU1_VIS, StubTokenizer, emu1_state_dict
+    from emu_b200.emu1.modeling_emu import Emu
+    sd = {k: v.to(dtype) for k, v in emu1_state_dict(EMU1_VIS).items()}
+    m = Emu.__new__(Emu)                      # host code only: the engine behind it is the CPU test double
+    m.engine, m.device_ = Emu1OracleEngine(sd, EMU1_VIS), torch.device("cpu")
+    m.decoder, m.n_causal, m.hidden = NS(tokenizer=StubTokenizer()), 8, 256
+    return m, sd
+
+
+@pytest.mark.parametrize("name,kw", [("greedy", dict(num_beams=1)), ("beam3", dict(num_beams=3, length_penalty=0.0)),
+                                     ("beam3_lp1_ret2", dict(num_beams=3, length_penalty=1.0, num_return_sequences=2))])
+def test_emu1_generate_matches_reference(name, kw):
+    """`Emu.generate` of the UNMODIFIED Emu1 reference, run the way it runs itself (bf16 model under bf16 autocast; two
+    left-padded prompts of different length with one image each, tests/golden/gen_golden_emu1_generate.py), against this repo's
+    Emu1 host code over the oracle in the same dtype policy.  Random-init logits are nearly flat and the reference's bf16
+    kernels need not round like the oracle's, so: every row must reproduce the reference ids up to its first near-tie flip, and
+    where it departs, the token it chose must be within the bf16 noise margin of the best one under the fp32 oracle."""
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "emu1_generate_tiny.pt"))
+    m, sd = _emu1_model(torch.bfloat16)
+    ids = m.generate_from_ids(gold["input_ids"], gold["attention_mask"], image=gold["image"], max_new_tokens=12, min_length=1,
+                              eos_token_id=2, pad_token_id=32000, **kw)
+    ref = gold["ids_" + name]
+    assert ids.shape == ref.shape, (ids.shape, ref.shape)
+    if torch.equal(ids, ref):
+        return
+    m32, sd32 = _emu1_model(torch.float32)
+    emb = m32.engine.llm_embed(gold["input_ids"])
+    f = m32.encode_image(gold["image"])
+    emb[gold["input_ids"] == 32003] = f.reshape(-1, f.shape[-1])
+    n = ids.shape[0] // gold["input_ids"].shape[0]
+    emb, mask = emb.repeat_interleave(n, 0), gold["attention_mask"].repeat_interleave(n, 0)
+    for b in range(ids.shape[0]):
+        diff = (ids[b] != ref[b]).nonzero()
+        if diff.numel() == 0:
+            continue
+        t = int(diff[0])
+        assert t >= 1, "row %d departs from the reference at the first token" % b
+        e = torch.cat((emb[b:b + 1], m32.engine.llm_embed(ref[b:b + 1, :t])), 1)
+        mk = torch.cat((mask[b:b + 1], torch.ones(1, t, dtype=mask.dtype)), 1)
+        h = O.llama_forward(sd32, e, mk, layers=L, heads=NH, position_ids=O.hf_position_ids(mk))
+        lp = torch.log_softmax(O.lm_logits(sd32, h[:, -1]).float(), -1)[0]
+        assert float(lp[ref[b, t]] - lp[ids[b, t]]) <= 3e-2 * float(lp.abs().max()), (name, b, t, ids[b], ref[b])
