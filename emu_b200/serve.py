@@ -122,8 +122,26 @@ class BatchingWorker(threading.Thread):
         if self.announce is not None:
             self.announce(self.kind, inputs, knobs)
         if len(batch) > 1 and hasattr(self.pipeline, "forward_batch"):
-            return list(self.pipeline.forward_batch(inputs, **knobs))
-        return [self.pipeline(inputs=i, **knobs) for i in inputs]
+            outs = list(self.pipeline.forward_batch(inputs, **knobs))
+        else:
+            outs = [self.pipeline(inputs=i, **knobs) for i in inputs]
+        if len(outs) != len(batch):
+            raise RuntimeError("pipeline returned %d results for %d requests" % (len(outs), len(batch)))
+        return outs
+
+    def _settle(self, batch):
+        """run the batch; a request fails on its own account only: when a shared call raises, its requests are retried one
+        by one, so that one bad prompt does not answer `code -1` to the callers it happened to be batched with"""
+        try:
+            for r, o in zip(batch, self._run_batch(batch)):
+                r.result = o
+        except Exception as ex:  # the request fails, the server lives (backend.py:141-146)
+            log.error("%s batch of %d failed: %s\n%s", self.kind, len(batch), ex, traceback.format_exc())
+            if len(batch) == 1:
+                batch[0].error = ex
+            else:
+                for r in batch:
+                    self._settle([r])
 
     def run(self):
         while not self._halt.is_set() or self.held:
@@ -131,16 +149,7 @@ class BatchingWorker(threading.Thread):
             if batch is None:
                 break
             t0 = time.time()
-            try:
-                outs = self._run_batch(batch)
-                if len(outs) != len(batch):
-                    raise RuntimeError("pipeline returned %d results for %d requests" % (len(outs), len(batch)))
-                for r, o in zip(batch, outs):
-                    r.result = o
-            except Exception as ex:  # the request fails, the server lives (backend.py:141-146)
-                log.error("batch of %d failed: %s\n%s", len(batch), ex, traceback.format_exc())
-                for r in batch:
-                    r.error = ex
+            self._settle(batch)
             self.batches.append(len(batch))
             log.info("%s batch of %d done in %.1f ms (queued %.1f ms)", self.kind, len(batch), (time.time() - t0) * 1e3,
                      (t0 - batch[0].t_in) * 1e3)
@@ -213,8 +222,9 @@ class EmuServer:
     --chat-concurrency / --generate-concurrency instances); requests go to the worker with the shortest queue."""
 
     def __init__(self, chat=None, generate=None, host="0.0.0.0", port=9000, max_wait_ms=0.0, max_images_per_batch=4,
-                 cache_dir=None, announce=None):
+                 cache_dir=None, announce=None, max_body_bytes=256 << 20):
         self.cache_dir = cache_dir
+        self.max_body_bytes = int(max_body_bytes)
         if cache_dir:
             os.makedirs(cache_dir, exist_ok=True)
 
@@ -240,6 +250,9 @@ class EmuServer:
 
             def do_POST(self):
                 n = int(self.headers.get("Content-Length") or 0)
+                if n > server.max_body_bytes:          # a prompt is a few pictures: refuse to buffer anything absurd
+                    self.send_error(413, "request body of %d bytes exceeds the limit of %d" % (n, server.max_body_bytes))
+                    return
                 body = self.rfile.read(n) if n else b""
                 route = {"/v1/mmc": server.handle_chat, "/v1/mmg": server.handle_generate}.get(self.path.split("?")[0])
                 if route is None:

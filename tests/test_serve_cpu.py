@@ -148,6 +148,36 @@ def test_concurrent_requests_share_generate_calls():
     assert len(chat.thread_ids) == 1                                     # one thread owns the pipeline
 
 
+def test_one_bad_request_does_not_fail_its_batch_mates():
+    """a shared generate call that raises is retried request by request: only the culprit answers code -1"""
+    chat = FakeChat(rows=20, delay=0.1)
+    srv = serve.EmuServer(chat=chat, host="127.0.0.1", port=0, max_wait_ms=0).start()
+    url = "http://127.0.0.1:%d" % srv.port
+    answers = {}
+    texts = ["warm up", "fine one", "boom", "fine two"]
+
+    def client(i):
+        answers[i] = post_chat(url, [["TEXT", texts[i]]]).json()
+    ts = [threading.Thread(target=client, args=(i,)) for i in range(4)]
+    ts[0].start()
+    time.sleep(0.03)
+    for t in ts[1:]:
+        t.start()
+    for t in ts:
+        t.join()
+    srv.shutdown()
+    assert answers[2] == {"code": -1, "data": "decoder exploded"}
+    assert [answers[i]["code"] for i in (0, 1, 3)] == [0, 0, 0] and answers[3]["data"].endswith("fine two")
+    assert [n for n, _ in chat.calls] == [1, 3, 1, 1, 1]                # alone | shared (raises) | one by one
+
+
+def test_oversized_body_is_refused():
+    srv = serve.EmuServer(chat=FakeChat(), host="127.0.0.1", port=0, max_body_bytes=1000).start()
+    r = requests.post("http://127.0.0.1:%d/v1/mmc" % srv.port, data={"prompt": "x" * 5000}, timeout=30)
+    srv.shutdown()
+    assert r.status_code == 413
+
+
 def test_max_wait_gathers_a_batch_from_an_idle_queue():
     chat = FakeChat(rows=8)
     w = serve.BatchingWorker(chat, "chat", lambda knobs: chat.max_requests_per_batch(knobs["num_beams"]), max_wait_ms=150)
