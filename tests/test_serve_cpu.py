@@ -22,6 +22,7 @@ class FakeChat:
         self.rows, self.delay = rows, delay
         self.calls = []                     # (n_requests, knobs) per generate call
         self.thread_ids = set()
+        self.gate = None                    # an Event: the FIRST call waits on it (lets a test pile requests up behind it)
 
     def _describe(self, inputs):
         return " ".join(i if isinstance(i, str) else "<img %dx%d>" % i.size for i in inputs)
@@ -32,6 +33,8 @@ class FakeChat:
     def forward_batch(self, batch_inputs, **knobs):
         self.thread_ids.add(threading.get_ident())
         self.calls.append((len(batch_inputs), dict(knobs)))
+        if self.gate is not None and len(self.calls) == 1:
+            assert self.gate.wait(30)
         if self.delay:
             time.sleep(self.delay)
         if any("boom" in self._describe(i) for i in batch_inputs):
@@ -58,6 +61,13 @@ class FakeGen:
             outs.append(type("Out", (), {"image": Image.new("RGB", (16, 16), (shade, num_inference_steps, 7)),
                                          "nsfw_content_detected": None})())
         return outs
+
+
+def wait_until(cond, timeout=30.0):
+    t0 = time.time()
+    while not cond():
+        assert time.time() - t0 < timeout, "timed out"
+        time.sleep(0.002)
 
 
 def png_bytes(size=(8, 6), color=(10, 200, 30)):
@@ -122,37 +132,40 @@ def test_errors_answer_code_minus_one_and_the_server_survives(server):
 def test_concurrent_requests_share_generate_calls():
     """While the pipeline is busy, requests pile up; the next admission takes everything with the same knobs up to
     rows // num_beams, leaves the others in line, and every caller gets ITS answer.  The reference would have run 9 calls."""
-    chat = FakeChat(rows=20, delay=0.15)
+    chat = FakeChat(rows=20)
+    chat.gate = threading.Event()
     srv = serve.EmuServer(chat=chat, host="127.0.0.1", port=0, max_wait_ms=0).start()
     url = "http://127.0.0.1:%d" % srv.port
+    worker = srv.chat_workers[0]
     answers = {}
 
     def client(i, beams):
         answers[i] = post_chat(url, [["TEXT", "request %d" % i]], num_beams=beams).json()
     first = threading.Thread(target=client, args=(0, 5))
     first.start()
-    time.sleep(0.05)                                         # request 0 is now being served alone
+    wait_until(lambda: len(chat.calls) == 1)                 # request 0 is inside the pipeline, alone
     rest = [threading.Thread(target=client, args=(i, 5 if i < 7 else 2)) for i in range(1, 9)]
-    for t in rest:
+    for i, t in enumerate(rest):
         t.start()
-        time.sleep(0.002)
+        wait_until(lambda: worker.q.qsize() == i + 1)        # queued in order 1..8
+    chat.gate.set()
     for t in [first] + rest:
         t.join()
     srv.shutdown()
     for i in range(9):
         assert answers[i] == {"code": 0, "data": "echo[%d beams]: request %d" % (5 if i < 7 else 2, i)}
-    sizes = [n for n, _ in chat.calls]
-    assert sizes[0] == 1 and sum(sizes) == 9 and len(sizes) <= 4        # 1 | 4 (cap 20 // 5) | 2 | 2 (other knobs)
-    assert max(sizes) == 4
-    assert all(k["num_beams"] in (5, 2) for _, k in chat.calls)
+    assert [(n, k["num_beams"]) for n, k in chat.calls] == [(1, 5), (4, 5), (2, 5), (2, 2)]   # cap 20 // 5 = 4; other knobs last
+    assert worker.batches == [1, 4, 2, 2]
     assert len(chat.thread_ids) == 1                                     # one thread owns the pipeline
 
 
 def test_one_bad_request_does_not_fail_its_batch_mates():
     """a shared generate call that raises is retried request by request: only the culprit answers code -1"""
-    chat = FakeChat(rows=20, delay=0.1)
+    chat = FakeChat(rows=20)
+    chat.gate = threading.Event()
     srv = serve.EmuServer(chat=chat, host="127.0.0.1", port=0, max_wait_ms=0).start()
     url = "http://127.0.0.1:%d" % srv.port
+    worker = srv.chat_workers[0]
     answers = {}
     texts = ["warm up", "fine one", "boom", "fine two"]
 
@@ -160,9 +173,11 @@ def test_one_bad_request_does_not_fail_its_batch_mates():
         answers[i] = post_chat(url, [["TEXT", texts[i]]]).json()
     ts = [threading.Thread(target=client, args=(i,)) for i in range(4)]
     ts[0].start()
-    time.sleep(0.03)
-    for t in ts[1:]:
+    wait_until(lambda: len(chat.calls) == 1)
+    for i, t in enumerate(ts[1:]):
         t.start()
+        wait_until(lambda: worker.q.qsize() == i + 1)
+    chat.gate.set()
     for t in ts:
         t.join()
     srv.shutdown()
@@ -180,7 +195,8 @@ def test_oversized_body_is_refused():
 
 def test_max_wait_gathers_a_batch_from_an_idle_queue():
     chat = FakeChat(rows=8)
-    w = serve.BatchingWorker(chat, "chat", lambda knobs: chat.max_requests_per_batch(knobs["num_beams"]), max_wait_ms=150)
+    # cap 8 // 2 = 4 > 3 requests: the batch closes when the window does; a long window keeps slow machines from splitting it
+    w = serve.BatchingWorker(chat, "chat", lambda knobs: chat.max_requests_per_batch(knobs["num_beams"]), max_wait_ms=1500)
     w.start()
     out = {}
     ts = [threading.Thread(target=lambda i=i: out.__setitem__(i, w.submit(["q%d" % i], dict(num_beams=2)))) for i in range(3)]
