@@ -306,11 +306,9 @@ UNET_FLOP_PER_SAMPLE_STEP = 6.74e12  # 6.74 TFLOP per sample per
 
 
 def emu2_unet_json():
-    return dict(in_channels=4, out_channels=4, block_out_channels=[320, 640, 1280], layers_per_block=2,
-                transformer_layers_per_block=[1, 2, 10], attention_head_dim=[5, 10, 20], cross_attention_dim=1792,
-                down_block_types=["DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"],
-                use_linear_projection=True, addition_time_embed_dim=256, projection_class_embeddings_input_dim=3328,
-                norm_num_groups=32, norm_eps=1e-5)
+    """the published Emu2-Gen UNet configuration (kept in the package: emu_b200/emu2/conf.py)"""
+    from emu_b200.emu2.conf import EMU2_GEN_UNET
+    return dict(EMU2_GEN_UNET)
 
 
 def unet_param_shapes(cfg):

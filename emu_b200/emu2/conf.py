@@ -59,3 +59,30 @@ def load_llama_config(path_or_dict):
     if cfg.get("num_key_value_heads", cfg["num_attention_heads"]) != cfg["num_attention_heads"]:
         raise ValueError("grouped-query attention is not part of the Emu decoder")
     return cfg
+
+
+# The published Emu2-Gen diffusion configuration (the values of Emu2/emu/conf/diffusion_config/{unet,vae,scheduler}/*.json, the
+# directory `EmuVisualGeneration.from_pretrained` / `from_config` default to in the reference, Emu2/emu/diffusion.py:254,272) —
+# used when no configuration directory is given, so that `from_pretrained("<...>.safetensors")` works as it does there.
+EMU2_GEN_UNET = dict(
+    in_channels=4, out_channels=4, sample_size=128, block_out_channels=[320, 640, 1280], layers_per_block=2,
+    down_block_types=["DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"],
+    up_block_types=["CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"], mid_block_type="UNetMidBlock2DCrossAttn",
+    transformer_layers_per_block=[1, 2, 10], attention_head_dim=[5, 10, 20], cross_attention_dim=1792,
+    use_linear_projection=True, addition_embed_type="text_time", addition_time_embed_dim=256,
+    projection_class_embeddings_input_dim=3328, norm_num_groups=32, norm_eps=1e-5, act_fn="silu")
+EMU2_GEN_VAE = dict(in_channels=3, out_channels=3, latent_channels=4, block_out_channels=[128, 256, 512, 512],
+                    layers_per_block=2, norm_num_groups=32, sample_size=1024, scaling_factor=0.13025, act_fn="silu")
+EMU2_GEN_SCHEDULER = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                          prediction_type="epsilon", interpolation_type="linear", timestep_spacing="leading", steps_offset=1,
+                          use_karras_sigmas=False)
+
+
+def load_diffusion_config(config_path=None):
+    """-> (unet, vae, scheduler) config dicts from a diffusers-style directory (`unet/config.json`, `vae/config.json`,
+    `scheduler/scheduler_config.json`); a part that is not on disk — or no directory at all — takes the published values"""
+    def read(rel, default):
+        p = osp.join(config_path, *rel) if config_path else None
+        return json.load(open(p)) if p and osp.exists(p) else dict(default)
+    return (read(("unet", "config.json"), EMU2_GEN_UNET), read(("vae", "config.json"), EMU2_GEN_VAE),
+            read(("scheduler", "scheduler_config.json"), EMU2_GEN_SCHEDULER))

@@ -294,12 +294,13 @@ class EmuVisualGeneration:
 
     # ---- Emu2/emu/diffusion.py:251-318 ----
     @classmethod
-    def from_config(cls, config_path: str, llama_config_path: Optional[str] = None, tokenizer=None, safety_checker=None,
-                    requires_safety_checker: bool = False, **kwargs):
-        unet_cfg = json.load(open(osp.join(config_path, "unet", "config.json")))
-        vae_p = osp.join(config_path, "vae", "config.json")
-        vae_cfg = json.load(open(vae_p)) if osp.exists(vae_p) else None
-        sched = EulerDiscreteScheduler.from_config(osp.join(config_path, "scheduler"))
+    def from_config(cls, config_path: Optional[str] = None, llama_config_path: Optional[str] = None, tokenizer=None,
+                    safety_checker=None, requires_safety_checker: bool = False, **kwargs):
+        """`config_path`: a diffusers-style directory (unet/, vae/, scheduler/); None = the published Emu2-Gen configuration,
+        which is what the reference's default (its own conf/diffusion_config, Emu2/emu/diffusion.py:272) holds."""
+        from .conf import load_diffusion_config
+        unet_cfg, vae_cfg, sched_cfg = load_diffusion_config(config_path)
+        sched = EulerDiscreteScheduler(**{k: v for k, v in sched_cfg.items() if not k.startswith("_")})
         tcfg = TextDecoderCfg(llama_config_path=llama_config_path) if llama_config_path else TextDecoderCfg()
         enc = EmuModel(CLIPVisionCfg(), tcfg, tokenizer=tokenizer, **kwargs)
         return cls(multimodal_encoder=enc, scheduler=sched, unet_config=unet_cfg, vae_config=vae_cfg,
@@ -308,7 +309,9 @@ class EmuVisualGeneration:
     @classmethod
     def from_pretrained(cls, model_path: str, config_path: Optional[str] = None, dtype=torch.bfloat16,
                         use_safetensors: bool = True, **kwargs):
-        if config_path is None:
+        # the reference takes the WEIGHTS FILE here and reads the configuration from its package (diffusion.py:251-267); a
+        # directory that carries its own unet/ vae/ scheduler/ configs next to the weights is accepted as well
+        if config_path is None and osp.isdir(model_path) and osp.exists(osp.join(model_path, "unet", "config.json")):
             config_path = model_path
         ins = cls.from_config(config_path, **kwargs)
         from .. import checkpoint

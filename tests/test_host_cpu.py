@@ -219,3 +219,30 @@ def test_visual_generation_forward_batch_layout():
     assert [o.image.getpixel((0, 0))[0] for o in outs] == [0, 10, 20] and all(o.nsfw_content_detected is None for o in outs)
     g.forward_batch([["a cat"], ["a dog"]], guidance_scale=1.0)
     assert seen["n"] == 2 and seen["embeds"][:, 0, 0].tolist() == [2.0, 2.0]
+
+
+def test_builtin_diffusion_config_is_the_published_one(tmp_path):
+    """`EmuVisualGeneration.from_pretrained(<weights file>)` reads its configuration from the package in the reference
+    (Emu2/emu/diffusion.py:254,272); here the published values are built in — same engine configuration either way, and a
+    directory overrides them part by part"""
+    import ctypes
+    import bench
+    from emu_b200.emu2 import conf
+    from emu_b200.emu2.diffusion import unet_config_from_json, vae_config_from_json
+
+    def raw(struct):
+        return ctypes.string_at(ctypes.addressof(struct), ctypes.sizeof(struct))
+    unet, vae, sched = conf.load_diffusion_config(None)
+    assert unet == conf.EMU2_GEN_UNET and vae == conf.EMU2_GEN_VAE and sched == conf.EMU2_GEN_SCHEDULER
+    assert bench.emu2_unet_json() == conf.EMU2_GEN_UNET
+    ref_dir = "/root/reference/Emu2/emu/conf/diffusion_config"
+    if os.path.isdir(ref_dir):
+        r_unet, r_vae, r_sched = conf.load_diffusion_config(ref_dir)
+        for mine, ref in ((unet, r_unet), (vae, r_vae), (sched, r_sched)):
+            assert all(ref[k] == v for k, v in mine.items())
+        assert raw(unet_config_from_json(unet)) == raw(unet_config_from_json(r_unet))
+        assert raw(vae_config_from_json(vae)) == raw(vae_config_from_json(r_vae))
+    (tmp_path / "scheduler").mkdir()
+    json.dump(dict(conf.EMU2_GEN_SCHEDULER, steps_offset=0), open(tmp_path / "scheduler" / "scheduler_config.json", "w"))
+    u2, v2, s2 = conf.load_diffusion_config(str(tmp_path))
+    assert s2["steps_offset"] == 0 and u2 == conf.EMU2_GEN_UNET and v2 == conf.EMU2_GEN_VAE
