@@ -40,8 +40,10 @@ class _Decoder:
 
 class Emu:
     def __init__(self, embed_dim=1024, multimodal_cfg=None, vision_cfg=None, vladapter_cfg=None, *, tokenizer=None,
-                 llama_config=None, llama_config_path="./models/llama_config", cformer_cfg=None, args=None,
+                 llama_config=None, llama_config_path="./models/llama_config", cformer_cfg=None, args=None, prompt=None,
                  max_batch: int = 8, max_seq: Optional[int] = None, device="cuda", **_ignored):
+        # (_ignored: quick_gelu / cast_dtype / pad_id / apply_lemmatizer of the reference constructor — training / eval knobs
+        # with no effect on generate; `prompt` is the default prompt `generate` falls back to, modeling_emu.py:128)
         vision_cfg = dict(EMU1_VISION, **(vision_cfg or {}))
         vladapter_cfg = vladapter_cfg or {"n_causal": 32}
         self.vision_cfg = vision_cfg
@@ -72,7 +74,7 @@ class Emu:
         self.hidden = c.llm_hidden
         self.n_tokens = (vision_cfg["image_size"] // vision_cfg["patch_size"]) ** 2 + 1
         self.image_placeholder = "[IMG]" + "<image>" * self.n_causal + "[/IMG]"
-        self.prompt = None
+        self.prompt = prompt
 
     @classmethod
     def from_json(cls, path, **kw):

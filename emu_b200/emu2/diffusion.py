@@ -294,12 +294,27 @@ class EmuVisualGeneration:
 
     # ---- Emu2/emu/diffusion.py:251-318 ----
     @classmethod
-    def from_config(cls, config_path: Optional[str] = None, llama_config_path: Optional[str] = None, tokenizer=None,
+    def from_config(cls, path: Optional[str] = None, llama_config_path: Optional[str] = None, tokenizer=None,
                     safety_checker=None, requires_safety_checker: bool = False, **kwargs):
-        """`config_path`: a diffusers-style directory (unet/, vae/, scheduler/); None = the published Emu2-Gen configuration,
-        which is what the reference's default (its own conf/diffusion_config, Emu2/emu/diffusion.py:272) holds."""
+        """`path` (the reference's argument name, Emu2/emu/diffusion.py:270-273): a diffusers-style directory (unet/, vae/,
+        scheduler/); None = the published Emu2-Gen configuration, which is what the reference's default (its own
+        conf/diffusion_config) holds.  Sub-directory overrides as in the reference: unet= / vae= / scheduler= keyword paths."""
         from .conf import load_diffusion_config
-        unet_cfg, vae_cfg, sched_cfg = load_diffusion_config(config_path)
+        path = kwargs.pop("config_path", path)
+        unet_cfg, vae_cfg, sched_cfg = load_diffusion_config(path)
+        for part, rel in (("unet", "config.json"), ("vae", "config.json"), ("scheduler", "scheduler_config.json")):
+            d = kwargs.pop(part, None)                       # reference: kwargs.pop("unet", None) etc., diffusion.py:275-279
+            if d is not None:
+                cfg = json.load(open(osp.join(d, rel)))
+                if part == "unet":
+                    unet_cfg = cfg
+                elif part == "vae":
+                    vae_cfg = cfg
+                else:
+                    sched_cfg = cfg
+        kwargs.pop("feature_extractor", None)                # CLIP pre-processing of the third-party safety checker: see the hook
+        if isinstance(safety_checker, str):                  # the reference passes a config DIRECTORY here; the hook is a callable
+            safety_checker = None
         sched = EulerDiscreteScheduler(**{k: v for k, v in sched_cfg.items() if not k.startswith("_")})
         tcfg = TextDecoderCfg(llama_config_path=llama_config_path) if llama_config_path else TextDecoderCfg()
         enc = EmuModel(CLIPVisionCfg(), tcfg, tokenizer=tokenizer, **kwargs)
@@ -326,6 +341,12 @@ class EmuVisualGeneration:
         f = osp.join(model_path, "model.safetensors" if use_safetensors else "pytorch_model.bin")
         checkpoint.load_into(ins.engine, f if osp.exists(f) else model_path, rename=keep)
         return ins
+
+    def device(self, module=None):
+        return self.device_
+
+    def dtype(self, module=None):
+        return torch.bfloat16
 
     def multito(self, device_list):
         """The reference places layers on several GPUs of ONE process (Emu2/emu/mixin.py); this engine is one
