@@ -522,3 +522,32 @@ def test_emu1_generate_matches_reference(name, kw):
         h = O.llama_forward(sd32, e, mk, layers=L, heads=NH, position_ids=O.hf_position_ids(mk))
         lp = torch.log_softmax(O.lm_logits(sd32, h[:, -1]).float(), -1)[0]
         assert float(lp[ref[b, t]] - lp[ids[b, t]]) <= 3e-2 * float(lp.abs().max()), (name, b, t, ids[b], ref[b])
+
+
+# ---- EmuModel.generate with an image AND a video in the prompt (Emu2/emu/emu.py:197-211) ------------------------------------
+def _emu2_model():
+    """EmuModel's host code (tokens -> embeddings -> <image> / [gIMG] splice -> strategy) over the CPU test double"""
+    from types import SimpleNamespace as NS
+    from helpers import StubTokenizer
+    from emu_b200.emu2.emu import EmuModel
+    sd = make_emu2_state_dict()
+    m = EmuModel.__new__(EmuModel)
+    eng = OracleEngine(sd, max_batch=8)
+    eng.llm_embed = lambda ids: F.embedding(ids.long(), sd["decoder.lm.model.embed_tokens.weight"])
+    m.engine, m.device_ = eng, torch.device("cpu")
+    m.decoder, m.n_query, m.v_query = NS(tokenizer=StubTokenizer()), 4, 4
+    m.encode_image = lambda image, n_query=None: O.encode_image(sd, image, patch=14, num_heads=4, layers=2, n_query=n_query or 4)
+    m._project_up = lambda x: F.linear(x, sd["project_up.weight"])
+    return m
+
+
+@pytest.mark.parametrize("name,kw", [("greedy", dict(num_beams=1)), ("beam3", dict(num_beams=3, length_penalty=1.0))])
+def test_generate_with_image_and_video_matches_reference(name, kw):
+    """one picture (4 <image> slots) and three video frames (3 x 4 [gIMG] slots) in one prompt: ids of the unmodified
+    reference's EmuModel.generate (tests/golden/gen_golden_video.py)"""
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "emu2_tiny_video.pt"))
+    assert int((gold["input_ids"] == 32003).sum()) == 4 and int((gold["input_ids"] == 32004).sum()) == 12
+    ids = _emu2_model().generate_from_ids(gold["input_ids"], gold["attention_mask"], image=gold["image"], video=gold["video"],
+                                          image_token_id=32003, video_token_id=32004, max_new_tokens=10, min_len=1,
+                                          eos_token_id=2, pad_token_id=32000, **kw)
+    assert torch.equal(ids, gold["ids_" + name]), (ids.tolist(), gold["ids_" + name].tolist())
