@@ -60,4 +60,28 @@ def test_sd15_param_count():
     import math
     cfg = dict(D.EMU1_UNET, cross_attention_dim=768, mid_block_layers=1)
     n = sum(math.prod(s) for s in D.unet_param_shapes(cfg).values())
-    assert abs(n - 859.52e6) < 0.05e6, n
+    assert n == 859_520_964, n          # the exact published parameter count of the SD-1.5 UNet
+
+
+def test_sdxl_topology_param_count():
+    """External anchor for the Emu2-Gen UNet restatement: Emu2's UNet is the SDXL-base topology with a 1792-wide context and a
+    3328-wide text_time input (Emu2/emu/conf/diffusion_config/unet/config.json).  With SDXL-base's own two widths (2048 / 2816)
+    the oracle's module tree must add up to SDXL-base's published 2,567,463,684 parameters exactly; with Emu2's it gives the
+    2.526 B the survey computed from the reference's JSON."""
+    import math
+    sdxl = dict(D.EMU2_UNET, cross_attention_dim=2048, projection_class_embeddings_input_dim=2816)
+    assert sum(math.prod(s) for s in D.unet_param_shapes(sdxl).values()) == 2_567_463_684
+    assert sum(math.prod(s) for s in D.unet_param_shapes(D.EMU2_UNET).values()) == 2_525_520_644
+
+
+def test_vae_decoder_param_count():
+    """External anchor for the unpinned VAE restatement (diffusers is not installable here): the Stable-Diffusion
+    AutoencoderKL of the reference's vae/config.json (block_out_channels 128/256/512/512, 2 layers per block, 4 latent
+    channels) has a 49,490,179-parameter decoder — the published size of the SD / SDXL VAE decoder — plus the 20-parameter
+    1x1 post_quant_conv.  The oracle's module tree (which the engine's weight loader mirrors key for key) must add up to it."""
+    import torch
+    from oracle import diffusion_oracle as D
+    shapes = D.vae_decoder_param_shapes(D.EMU2_VAE)
+    total = sum(torch.Size(s).numel() for s in shapes.values())
+    pqc = sum(torch.Size(s).numel() for k, s in shapes.items() if k.startswith("post_quant_conv"))
+    assert pqc == 20 and total - pqc == 49_490_179
