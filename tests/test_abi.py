@@ -79,3 +79,63 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def _struct_fields(name):
+    src = open(HEADER).read()
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(int|float)\s+", "", decl)
+        for n in decl.split(","):
+            m = re.match(r"(\w+)(?:\[(\d+)\])?", n.strip())
+            out.append((m.group(1), int(m.group(2) or 1)))
+    return out
+
+
+@pytest.mark.parametrize("name", ["EmuUNetConfig", "EmuVAEConfig"])
+def test_diffusion_config_struct_layouts_match_header(name):
+    """field order and array lengths of the ctypes mirrors == the C structs (every field is a 4-byte int / float)"""
+    from emu_b200 import _lib
+    cls = getattr(_lib, name)
+    mine = [(f[0], ctypes.sizeof(f[1]) // 4) for f in cls._fields_]
+    assert mine == _struct_fields(name)
+    assert ctypes.sizeof(cls) == 4 * sum(n for _, n in mine)
+
+
+def test_null_arguments_are_refused_not_dereferenced(lib):
+    """Every entry point validates its handle / pointers before doing anything (header: "return value 0 = ok, negative = error
+    ... nothing throws or aborts"): a NULL engine or NULL buffers come back as EMU_ERR_INVALID, also on a machine without a GPU."""
+    N = None
+    calls = {
+        "emu_engine_create": (N, 0, 1, N, N),
+        "emu_engine_load_tensor": (N, b"k", N, 1, N, 0, N),
+        "emu_vit_forward": (N, N, 1, N, 4, 1, N),
+        "emu_llm_reset": (N, N),
+        "emu_llm_embed": (N, N, 1, N, N),
+        "emu_llm_prefill": (N, N, N, 1, 1, 1, N, N, N),
+        "emu_llm_decode": (N, N, N, N, 1, N, N, N, -1, N),
+        "emu_llm_expand": (N, N, 1, N),
+        "emu_project": (N, 0, N, 1, N, N),
+        "emu_cformer_forward": (N, N, 1, 1, N, N),
+        "emu_unet_configure": (N, N),
+        "emu_vae_configure": (N, N),
+        "emu_vae_decode": (N, N, 1, 1, 1, N, N),
+        "emu_beam_topk": (N, N, 1, 1, 10, 2, -1, N, 0, 0, ctypes.c_float(1.0), 0, 0, N, N, N, N),
+        "emu_beam_step": (N, N, 1, 1, 10, 0, 4, 2, ctypes.c_float(1.0), ctypes.c_float(1.0), 0, N, N, N, N, N, N, N, N, N, N, N),
+    }
+    for name, args in calls.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        saved = fn.argtypes
+        fn.argtypes = None                       # raw call: ctypes converts None -> NULL, ints -> int
+        try:
+            rc = fn(*args)
+        finally:
+            fn.argtypes = saved
+        assert rc == -1, (name, rc)
+    assert lib.emu_llm_cur_len(None) == -1
