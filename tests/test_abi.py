@@ -110,7 +110,7 @@ def test_diffusion_config_struct_layouts_match_header(name):
 def test_null_arguments_are_refused_not_dereferenced(lib):
     """Every entry point validates its handle / pointers before doing anything (header: "return value 0 = ok, negative = error
     ... nothing throws or aborts"): a NULL engine or NULL buffers come back as EMU_ERR_INVALID, also on a machine without a GPU."""
-    N = None
+    N, F = None, ctypes.c_float
     calls = {
         "emu_engine_create": (N, 0, 1, N, N),
         "emu_engine_load_tensor": (N, b"k", N, 1, N, 0, N),
@@ -127,7 +127,29 @@ def test_null_arguments_are_refused_not_dereferenced(lib):
         "emu_vae_decode": (N, N, 1, 1, 1, N, N),
         "emu_beam_topk": (N, N, 1, 1, 10, 2, -1, N, 0, 0, ctypes.c_float(1.0), 0, 0, N, N, N, N),
         "emu_beam_step": (N, N, 1, 1, 10, 0, 4, 2, ctypes.c_float(1.0), ctypes.c_float(1.0), 0, N, N, N, N, N, N, N, N, N, N, N),
+        "emu_sample_tokens": (N, 1, 1, F(1.0), 0, F(1.0), -1, ctypes.c_uint64(0), ctypes.c_uint64(0), N, N),
+        "emu_unet_forward": (N, N, F(0.0), N, 1, N, N, 1, 1, 1, N, N),
+        "emu_denoise_step": (N, N, F(1.0), F(0.5), F(1.0), F(3.0), N, 1, N, N, 1, 1, 1, N),
+        "emu_denoise_step_multistep": (N, N, N, N, F(1.0), F(3.0), N, 1, 1, 1, 1, N),
+        "emu_preprocess_image": (N, 1, 1, 1, 1, N, N, N, 0, N),
+        "emu_image_to_uint8": (N, N, ctypes.c_int64(1), N),
+        "emu_tp_head_range": (4, 2, 0, N, N),
+        # the stand-alone operators take bare pointers: same rule
+        "emu_op_gemm": (N, 0, N, 0, 1, 1, 1, N, N, 0, 0, N, 0, 0, 0, N),
+        "emu_op_gemm_skinny": (N, 0, N, 0, 1, 1, 1, N, 0, 0, N, 0, 0, N),
+        "emu_op_conv3x3": (N, 1, 1, 1, 1, N, 1, N, N, N, N),
+        "emu_op_gemv": (N, 1, 1, N, 0, 1, N, F(1e-6), 0, N, N, 0, N, 0, 0, 0, N),
+        "emu_op_gemv_rope_qkv": (N, 1, 1, 1, N, 0, 1, N, F(1e-6), N, N, N, N, N, N, N, 1, N),
+        "emu_op_attn_prefill": (N, N, N, N, 1, 1, 1, 1, 1, N, F(1.0), 0, N, N, N),
+        "emu_op_attn_decode": (N, N, N, 1, 1, 1, 1, N, N, F(1.0), N, 1, N),
+        "emu_op_rmsnorm": (N, N, N, 1, 1, F(1e-6), N),
+        "emu_op_layernorm": (N, N, N, N, N, 1, 1, F(1e-6), N),
+        "emu_debug_gemm_phases": (N, 0, N, 0, 1, 1, 1, N, N, 0, 0, N, 0, 0, N, N),
+        "emu_debug_gemv_phases": (N, 1, 1, N, 0, 1, N, F(1e-6), 0, N, 0, N, 0, 0, N, N),
     }
+    skipped = set(header_symbols()) - set(calls)          # what is left takes no pointer that could be NULL-checked this way
+    assert skipped == {"emu_engine_destroy", "emu_last_error", "emu_nccl_unique_id", "emu_llm_cur_len", "emu_launch_count",
+                       "emu_version"}, skipped
     for name, args in calls.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
